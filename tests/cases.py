@@ -1,0 +1,158 @@
+"""Seeded inputs shared by the golden generator, the oracle tests and the GPU parity tests.
+
+The known-answer inputs restate those of the reference's own tests (file:line given per builder);
+the block cases are the parity configurations of SURVEY 8d scaled to sizes the CPU oracle finishes
+in seconds.
+"""
+
+import types
+
+import numpy as np
+
+from pyimcom_b200.synth import ARCSEC, StampConfig, SynthBlock
+
+GETW_FH = (-0.5, -0.3137, -0.01, 0.0, 0.2718, 0.49, 0.5)
+
+
+def interp_inputs():
+    """tests/pyimcom/test_routine.py:8-63: sin grid (2,64,32), 100 quasi-random points, 3x(12,20) grid."""
+    nx, ny, N = 32, 64, 10
+    npts = N * N
+    infunc = np.sin(np.linspace(0, 200, 2 * nx * ny)).reshape((2, ny, nx))
+    x_, _ = np.modf(np.arange(npts) / np.sqrt(5))
+    x_ *= 40
+    y_, _ = np.modf(np.arange(npts) * 2 / np.sqrt(5))
+    y_ *= 40
+    xs_, ys_ = x_.copy(), y_.copy()
+    for i in range(1, N):
+        for j in range(i):
+            xs_[i * N + j] = xs_[j * N + i]
+            ys_[i * N + j] = ys_[j * N + i]
+    npi, nxo, nyo = 3, 12, 20
+    xpos = np.zeros((npi, nxo))
+    ypos = np.zeros((npi, nyo))
+    for i in range(npi):
+        xpos[i, :] = np.linspace(2 + i, nx - 2 - i, nxo)
+        ypos[i, :] = np.linspace(2 + i, ny - 2 - i, nyo)
+    return infunc, x_, y_, xs_, ys_, xpos, ypos
+
+
+def kernel_toy():
+    """tests/pyimcom/test_routine.py:66-108: 33x33 -> 25x25 Gaussian-overlap toy, scaled by 0.7."""
+    sigma, m1, n1 = 4.0, 25, 33
+    gi = np.arange(n1, dtype=np.float64)
+    y = np.repeat(gi, n1)
+    x = np.tile(gi, n1)
+    go = 5 + 0.25 * np.arange(m1)
+    yout = np.repeat(go, m1)
+    xout = np.tile(go, m1)
+    A = np.exp(-1.0 / sigma**2 * ((x[:, None] - x[None, :]) ** 2 + (y[:, None] - y[None, :]) ** 2))
+    mBhalf = np.exp(-1.0 / sigma**2 * ((x[None, :] - xout[:, None]) ** 2 + (y[None, :] - yout[:, None]) ** 2))
+    return A * 0.7, mBhalf * 0.7, 0.7
+
+
+def reduced_inputs(m=257, nv=4, seed=7):
+    """Random but well-posed node statistics for build_reduced_T_wrap (routine.py:487-588).
+
+    Built the way CholKernel._call_multi_kappa builds them (lakernel.py:361-380) from a small random
+    SPD system, so that bracket selection and bisection branches are exercised on both sides.
+    """
+    rng = np.random.default_rng(seed)
+    n = 24
+    G = rng.standard_normal((n, 3 * n))
+    A = G @ G.T / (3 * n)
+    w, Q = np.linalg.eigh(A)
+    A = (Q * (w * np.logspace(-6, 0, n))) @ Q.T
+    B = rng.standard_normal((m, n)) @ A * rng.uniform(0.2, 1.0, size=(m, 1))
+    Cn = 1.3 * np.max(np.einsum("ai,ai->a", B @ np.linalg.pinv(A), B))
+    kap = np.array([1e-5, 1e-3, 1e-1, 3.0])[:nv]
+    Tpi = np.stack([np.linalg.solve(A + k * Cn * np.eye(n), B.T).T for k in kap])
+    Dp = np.einsum("ai,pai->ap", B, Tpi)
+    Npq = np.einsum("pai,qai->apq", Tpi, Tpi)
+    Epq = np.zeros((m, nv, nv))
+    for p in range(nv):
+        for q in range(p + 1):
+            Epq[:, q, p] = Epq[:, p, q] = Dp[:, q] - kap[p] * Cn * Npq[:, p, q]
+    return Npq.ravel().copy(), (Dp.ravel() / Cn).copy(), (Epq.ravel() / Cn).copy(), kap, 1e-4, 0.6
+
+
+def la_outst(kappaC, uctarget=1e-4, sigmamax=0.5, iterative=False):
+    """tests/pyimcom/test_la.py:46-230: 6x6 circulant cosine system, 16 output pixels, duck-typed outst."""
+    N = 6
+    idx = np.arange(N)
+    d = 2 * np.pi * (idx[:, None] - idx[None, :]) / N
+    A = np.zeros((N, N))
+    for k in range(1, N // 2 + 1):
+        A += np.cos(k * d) / k / N
+    mBhalf = np.zeros((1, 16, N))
+    for i in range(N):
+        for j in range(16):
+            _d = 2 * np.pi * (i - 0.4 * j) / N
+            for k in range(1, N // 2 + 1):
+                mBhalf[0, j, i] += np.cos(k * _d) / k / N
+    cfg = types.SimpleNamespace(n2f=4, n_out=1, kappaC_arr=np.asarray(kappaC, dtype=np.float64), uctarget=uctarget,
+                                sigmamax=sigmamax, linear_algebra="x", fade_kernel=0)
+    if iterative:
+        cfg.instamp_pad = 2.0 * ARCSEC
+        cfg.dtheta = 0.11 / 3600.0
+        cfg.iter_rtol = 1e-2
+        cfg.iter_max = 8
+    outst = types.SimpleNamespace(blk=types.SimpleNamespace(cfg=cfg), inpix_cumsum=np.array([N]), sysmata=A,
+                                  mhalfb=mBhalf, outovlc=np.array([A[0, 0]]))
+    if iterative:
+        outst.yx_val = [np.linspace(0, 6, 16), np.zeros(16)]
+        outst.iny_val = np.zeros(N)
+        outst.inx_val = np.linspace(0, N - 1, N)
+    return outst
+
+
+# name -> (kernel class, kappaC, la_outst kwargs)
+LA_CASES = {
+    "eigen1": ("EigenKernel", [1e-2], dict(sigmamax=0.5)),
+    "eigen3": ("EigenKernel", [1e-4, 1e-3, 1e-2], dict(sigmamax=1.0)),
+    "chol1": ("CholKernel", [1e-2], dict(sigmamax=0.5)),
+    "chol3": ("CholKernel", [1e-4, 1e-3, 1e-2], dict(sigmamax=1.0)),
+    "iter2": ("IterKernel", [1e-3, 1e-2], dict(sigmamax=1.0, iterative=True)),
+    "iter1": ("IterKernel", [1e-3], dict(sigmamax=1.0, iterative=True)),
+}
+
+# Synthetic blocks pushed through the reference's own OutStamp path (make_golden.py).
+_MINI = dict(n1=2, n2=8, dtheta_arcsec=0.04, fade_kernel=1, postage_pad=0, npixpsf=16, oversamp=4,
+             instamp_pad_arcsec=0.3, n_inframe=3)
+BLOCK_CASES = {
+    # config 1 analogue: Cholesky, one kappa node
+    "chol1": dict(cfg=_MINI, n_image=2, seed=1, kernel="Cholesky", kappaC=[5e-4], stamps=[(1, 1), (2, 2)],
+                  store_ab=True, store_ti64=True),
+    # Cholesky, three kappa nodes -> build_reduced_T_wrap
+    "chol3": dict(cfg=_MINI, n_image=2, seed=2, kernel="Cholesky", kappaC=[1e-5, 1e-4, 1e-3], stamps=[(1, 2)]),
+    # config 2 analogue: Eigen with per-pixel kappa bisection
+    "eigen3": dict(cfg=_MINI, n_image=2, seed=3, kernel="Eigen", kappaC=[1e-5, 1e-4, 1e-3], stamps=[(2, 1)]),
+    "eigen1": dict(cfg=_MINI, n_image=2, seed=3, kernel="Eigen", kappaC=[5e-4], stamps=[(2, 1)]),
+    # config 3 analogue: Iterative, kappa = 0, no fade
+    "iter0": dict(cfg=dict(_MINI, fade_kernel=0, instamp_pad_arcsec=0.25), n_image=3, seed=4, kernel="Iterative",
+                  kappaC=[0.0], stamps=[(1, 1)], iter_rtol=1.5e-3, iter_max=30),
+    "iter2": dict(cfg=dict(_MINI, fade_kernel=0, instamp_pad_arcsec=0.25), n_image=3, seed=4, kernel="Iterative",
+                  kappaC=[1e-4, 1e-3], stamps=[(1, 1)], iter_rtol=1.5e-3, iter_max=30),
+    # config 5 analogue: two output PSFs + PSF splitting (doubled overlap sampling), flat penalty on
+    "nout2split": dict(cfg=dict(_MINI, n_out=2, psfsplit=True, sigmatarget=0.95, sigmatarget_extra=(1.1,),
+                                outpsf_extra=("GAUSSIAN",), flat_penalty=1e-7), n_image=2, seed=5, kernel="Cholesky",
+                       kappaC=[5e-4], stamps=[(1, 1)], store_ab=True),
+    # 4x4 block with padding so that interior stamps have full 3x3 neighbourhoods and four PSF groups
+    "pad4": dict(cfg=dict(_MINI, n1=2, postage_pad=1, n_inframe=2), n_image=3, seed=6, kernel="Cholesky",
+                 kappaC=[5e-4], stamps=[(2, 2), (3, 2)], store_ab=True),
+    # truncated PSF support (npixpsf=12) makes A + kappa*I indefinite -> the eigen-shift repair branch
+    # of CholKernel._cholesky_wrapper (lakernel.py:262-279) fires in the reference
+    "repair": dict(cfg=dict(_MINI, n1=2, postage_pad=1, n_inframe=2, npixpsf=12), n_image=3, seed=6, kernel="Cholesky",
+                   kappaC=[5e-4], stamps=[(2, 2)]),
+}
+
+
+def make_block(spec):
+    kw = dict(spec["cfg"])
+    kw["kappaC_arr"] = np.asarray(spec["kappaC"], dtype=np.float64)
+    kw["linear_algebra"] = spec["kernel"]
+    for k in ("iter_rtol", "iter_max"):
+        if k in spec:
+            kw[k] = spec[k]
+    cfg = StampConfig(**kw)
+    return SynthBlock(cfg, n_image=spec["n_image"], seed=spec["seed"])
