@@ -1,0 +1,200 @@
+/*
+ * pyimcom_b200.h -- C ABI of libpyimcom_b200.so: the B200 (sm_100a) implementation of PyIMCOM's
+ * per-postage-stamp coaddition hot path.
+ *
+ * Conventions
+ *   - Every entry point returns 0 on success or a non-zero code; b200_last_error() then returns a
+ *     human-readable message (thread-local).  Nothing is thrown across the boundary.
+ *   - Plain pointers and sizes only.  "Host seam" functions (section 1) take HOST pointers, do their own
+ *     H2D/D2H copies on the default stream and return after the result is in the caller's array: they
+ *     are what a ctypes/CPython binding of furry_parakeet.pyimcom_croutines would bind.
+ *   - "Device" functions (b200_dev_*, sections 2-6) take DEVICE pointers plus a cudaStream_t passed as
+ *     void* (NULL = legacy default stream), only enqueue work and never synchronise.
+ *   - All matrices are row-major ("C order"), float64 unless stated.
+ *
+ * Each declaration cites the reference interface (file:line under the PyIMCOM source tree) it replaces.
+ */
+#ifndef PYIMCOM_B200_H
+#define PYIMCOM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- 0. library ------------------------------------------------------------------------------- */
+const char* b200_last_error(void);
+int b200_version(void);
+/* number of kernels launched by this library in this process since load (bench.py's gpu_launches) */
+long long b200_launch_count(void);
+/* frees the grow-only device scratch used by the host-seam functions */
+int b200_release_scratch(void);
+
+/* ---- 1. host seam: furry_parakeet.pyimcom_croutines / pyimcom.routine ------------------------- */
+/* routine.py:125-181  iD5512C(infunc (nlayer,ngy,ngx), xpos (nout), ypos (nout), fhatout (nlayer,nout));
+ * off-grid points leave fhatout untouched (routine.py:166-167). */
+int b200_iD5512C(const double* infunc, int nlayer, int ngy, int ngx, const double* xpos, const double* ypos,
+                 long nout, double* fhatout);
+/* routine.py:184-253  same, nout a perfect square, upper triangle evaluated then mirrored. */
+int b200_iD5512C_sym(const double* infunc, int nlayer, int ngy, int ngx, const double* xpos, const double* ypos,
+                     long nout, double* fhatout);
+/* routine.py:256-338  gridD5512C(infunc (ngy,ngx), xpos (npi,nxo), ypos (npi,nyo), fhatout (npi,nyo*nxo));
+ * off-grid rows/columns produce 0 (routine.py:307-310). */
+int b200_gridD5512C(const double* infunc, int ngy, int ngx, const double* xpos, const double* ypos, long npi,
+                    int nxo, int nyo, double* fhatout);
+/* routine.py:29-122  the ten D5512 weights for fh = frac - 1/2. */
+int b200_iD5512C_getw(double* w, double fh);
+/* routine.py:341-430  lakernel1(lam (n), Q (unused, as in the reference), mPhalf (m,n), C, targetleak, kCmin,
+ * kCmax, nbis, kappa (m), Sigma (m), UC (m), T (m,n), smax). */
+int b200_lakernel1(const double* lam, const double* mPhalf, long m, long n, double C, double targetleak,
+                   double kCmin, double kCmax, int nbis, double* kappa, double* Sigma, double* UC, double* T,
+                   double smax);
+/* routine.py:433-484  lsolve_sps(N, A (N,N) destroyed, x (N) out, b (N)). */
+int b200_lsolve_sps(int N, double* A, double* x, const double* b);
+/* routine.py:487-588  build_reduced_T_wrap(Nflat (m*nv*nv), Dflat (m*nv), Eflat (m*nv*nv), kappa (nv), ucmin, smax,
+ * out_kappa (m), out_Sigma (m), out_UC (m), out_w (m*nv)); out_iv/out_branch (int32, m) optional diagnostics:
+ * bracket index and the 12-step branch word (bit k set = step k divided kappa). */
+int b200_build_reduced_T_wrap(const double* Nflat, const double* Dflat, const double* Eflat, const double* kappa,
+                              int nv, long m, double ucmin, double smax, double* out_kappa, double* out_Sigma,
+                              double* out_UC, double* out_w, int32_t* out_iv, int32_t* out_branch);
+
+/* ---- 2. device: interpolation and system-matrix assembly (stage a) ---------------------------- */
+int b200_dev_iD5512C(const double* infunc, int nlayer, int ngy, int ngx, const double* xpos, const double* ypos,
+                     long nout, double* fhatout, void* stream);
+int b200_dev_iD5512C_sym(const double* infunc, int nlayer, int ngy, int ngx, const double* xpos, const double* ypos,
+                         long nout, double* fhatout, void* stream);
+int b200_dev_gridD5512C(const double* infunc, int ngy, int ngx, const double* xpos, const double* ypos, long npi,
+                        int nxo, int nyo, double* fhatout, void* stream);
+
+/* One PSF-overlap table as seen by the A-assembly kernel. */
+typedef struct b200_table_ref {
+    long long offset;   /* offset in doubles of the zero-padded (ngrid x ngrid) table inside the arena; <0: absent */
+    int flip;           /* read the table mirrored in both axes (psfutil.py:1659-1665) */
+    int pad_;
+    double penalty_sub; /* flat_penalty / n_in of this PSF-group pair (psfutil.py:1484, 1706) */
+} b200_table_ref;
+
+/* Gather the selected input pixels of one output stamp (coadd.py:969-977): out[k] = src[idx[k]] for positions,
+ * codes (src_code/pcode may both be NULL) and the n_inframe float32 layers (src_data (n_inframe, src_ld) ->
+ * indata (n_inframe, ldi), zero padded). */
+int b200_dev_gather_stamp(const int* idx, int n, int npad, const double* src_x, const double* src_y,
+                          const int* src_code, const float* src_data, long src_ld, int n_inframe, double* px,
+                          double* py, int* pcode, float* indata, int ldi, void* stream);
+
+/* A (npad x lda) for one output stamp: replaces PSFOvl._call_ii_self/_call_ii_cross (psfutil.py:1401-1495,
+ * 1597-1732) and the 9+36 block scatter of OutStamp._build_system_matrices (coadd.py:1028-1069).
+ * px,py (n): positions in output pixels; pcode (n): local_group*nimg + image; lut (ncode*ncode).
+ * Entries with index >= n form an identity block; diag_add is added to the first n diagonal entries. */
+int b200_dev_build_A(const double* px, const double* py, const int* pcode, int n, int npad, const double* tables,
+                     const b200_table_ref* lut, int nimg, int ncode, int ngrid, double dscale, double nc,
+                     double flat_penalty, double* A, int lda, double diag_add, void* stream);
+/* mBhalf (n_out, mpad, ldb) for one output stamp: replaces PSFOvl._call_io_cross (psfutil.py:1497-1595) and
+ * coadd.py:1075-1082.  lut_io (ncode*n_out) table offsets (<0 absent); output pixel (iy,ix) sits at
+ * (x0out + ix, y0out + iy) (coadd.py:879-882).  Padding rows/columns are zero-filled. */
+int b200_dev_build_B(const double* px, const double* py, const int* pcode, int n, int npad, const double* tables,
+                     const long long* lut_io, int n_out, int ngrid, double dscale, double nc, int n2f, int mpad,
+                     double x0out, double y0out, double* B, int ldb, size_t strideB, void* stream);
+
+/* ---- 3. device: dense FP64 linear algebra on the DMMA tensor pipe (stage b, CholKernel) -------- */
+#define B200_NB 128   /* block size of the factorisation == GEMM tile edge */
+#define B200_MAXB 16  /* systems per batched call */
+
+/* One SPD system (A + kappa I) Ti^T = mBhalf^T (lakernel.py:295-304).  Padded sizes are multiples of B200_NB. */
+typedef struct b200_solve_sys {
+    double* W;    /* (npad, ldw) in: A + kappa I (lower triangle read, identity padding); out: L (lower) and L^T
+                     in the strictly upper block triangle */
+    double* X;    /* (mpad, ldx) in: mBhalf rows; out: Ti rows */
+    double* Dinv; /* (2*npad/128, 128, 128) workspace: inverses of the diagonal blocks of L and their transposes */
+    int* info;    /* device int, LAPACK dpotrf convention: 0 or 1 + index of the first non-positive pivot */
+    int npad, mpad, ldw, ldx;
+} b200_solve_sys;
+
+/* scipy.linalg.cholesky + cho_solve (lakernel.py:263, 276, 304, 358) for up to B200_MAXB systems at once. */
+int b200_dev_chol_solve(const b200_solve_sys* sys, int nsys, int do_factor, int do_solve, void* stream);
+/* W <- A (n x n) + sum(incs) on the diagonal, identity in rows/cols n..npad-1 (lakernel.py:295-299, 356). */
+int b200_dev_pad_system(double* W, int ldw, int n, int npad, const double* A, int lda, const double* incs, int ninc,
+                        void* stream);
+/* C (M x N) = [C +/-] A (M x K) * B (N x K)^T; M,N multiples of 128, K multiple of 16; accumulate 0/+1/-1. */
+int b200_dev_gemm_nt(const double* A, int lda, const double* B, int ldb, double* C, int ldc, int M, int N, int K,
+                     int accumulate, void* stream);
+int b200_dev_transpose(const double* A, int lda, double* At, int ldat, int rows, int cols, void* stream);
+/* np.linalg.eigh (lakernel.py:162, 201, 266): parallel one-sided Jacobi.  A (n x n, lda) is destroyed; Vt (n, ldv)
+ * receives the eigenvectors as ROWS, lam (n) the eigenvalues (unsorted).  Returns the sweep count in *sweeps
+ * (host int, may be NULL).  This call synchronises the stream once per sweep (convergence test). */
+int b200_dev_eigh(double* A, int lda, int n, double* Vt, int ldv, double* lam, int max_sweeps, int* sweeps,
+                  void* stream);
+
+/* ---- 4. device: per-output-pixel Lagrange multiplier (stage b) --------------------------------- */
+int b200_dev_lakernel1(const double* lam, const double* mPhalf, int ldp, int m, int n, double C, double targetleak,
+                       double kCmin, double kCmax, int nbis, double* kappa, double* Sigma, double* UC, double* T,
+                       int ldt, double smax, void* stream);
+/* EigenKernel._call_single_kappa closed forms (lakernel.py:165-170). */
+int b200_dev_eigen_single(const double* lam, const double* mPhalf, int ldp, int m, int n, double C, double kappa,
+                          double* Sigma, double* UC, double* T, int ldt, void* stream);
+int b200_dev_lsolve_sps(int N, double* A, double* x, const double* b, double* work, void* stream);
+int b200_dev_build_reduced_T(const double* Nflat, const double* Dflat, const double* Eflat, const double* kappa,
+                             int nv, int m, double ucmin, double smax, double* out_kappa, double* out_Sigma,
+                             double* out_UC, double* out_w, int* out_iv, int* out_branch, void* stream);
+/* D_p, N_pq, E_pq of the nv node solutions (lakernel.py:361-368); DpC/EpqC are D/C and E/C as handed to
+ * build_reduced_T_wrap (lakernel.py:375-380).  Epq_in != NULL supplies an exact E (lakernel.py:709-716). */
+int b200_dev_node_stats(const double* mB, int ldb, const double* Tpi, int ldt, size_t strideT, int nv, int m, int n,
+                        const double* kappa_nodes, double Cnorm, double* Dp, double* Npq, double* Epq, double* DpC,
+                        double* EpqC, const double* Epq_in, void* stream);
+int b200_dev_rowdot(const double* X, int ldx, const double* Y, int ldy, int m, int n, double* out, int ostride,
+                    void* stream);
+/* single-kappa outputs (lakernel.py:312-316, 643-648): Sigma = N, UC = 1 - (kappa N + D)/C or, with E given,
+ * UC = 1 + (E - 2D)/C; kappa map filled with the scalar. */
+int b200_dev_single_kappa_maps(const double* D, const double* N, const double* E, int m, double kappa, double C,
+                               double* kappa_out, double* Sigma_out, double* UC_out, void* stream);
+/* out[a] = scale * in[a] (kappa = out_kappa * C, lakernel.py:390, and the Eigen quirk lakernel.py:222) */
+int b200_dev_scale(const double* in, double scale, int m, double* out, void* stream);
+
+/* ---- 5. device: IterKernel (lakernel.py:397-443, 548-590, 615-619) ------------------------------ */
+/* Per output pixel a at (outx[a], outy[a]): acceptance mask hypot(dy,dx) < rho_acc over the input pixels
+ * (inx, iny), CG on the gathered sub-system of AA + diag_add I, result rounded to float32 and scattered into
+ * Ti (m, ldt) (stored as f64).  niter/nsel (m) optional. */
+int b200_dev_iter_cg(const double* AA, int lda, double diag_add, const double* mB, int ldb, int m, int n,
+                     const double* inx, const double* iny, const double* outx, const double* outy, double rho_acc,
+                     double rtol, int maxiter, double* Ti, int ldt, int* niter, int* nsel, void* stream);
+
+/* ---- 6. device: apply T (stage c; coadd.py:1221-1363, 1976-1994) -------------------------------- */
+typedef struct b200_finalize_args {
+    const double* Tpi;     /* (nv, m, ldt) f64 node solutions (nv == 1: the solution itself) */
+    size_t strideT;
+    int ldt;
+    const double* w;       /* (m, nv) node weights, or NULL when nv == 1 */
+    int nv;
+    const double* mB;      /* (m, ldb) -B/2 rows (for D); may be NULL */
+    int ldb;
+    int m, n, n2f, fade;
+    const double* fade_w;  /* (2*fade) trapezoid weights s_k - sin(2 pi s_k)/(2 pi) (coadd.py:1269-1271) */
+    const float* indata;   /* (n_inframe, ldi) f32 input layers in the stamp's pixel order */
+    int ldi, n_inframe;
+    const int* seg_end;    /* (nseg) exclusive end column of each (instamp,image) segment, ascending */
+    const int* seg_img;    /* (nseg) image index of each segment */
+    int nseg, n_img;
+    float* T32;            /* (m, ldt32) f32 faded T out (nullable) */
+    int ldt32;
+    double* Ti64;          /* (m, ldt64) f64 pre-cast, pre-fade combined T out (nullable) */
+    int ldt64;
+    double* D;             /* (m) sum_i mB*Ti (nullable) */
+    double* N;             /* (m) sum_i Ti^2  (nullable) */
+    float* outimage;       /* (n_inframe, m) f32 */
+    double* Tsum_image;    /* (m, n_img) f64 sums of the faded f32 T per image */
+} b200_finalize_args;
+
+int b200_dev_finalize(const b200_finalize_args* args, void* stream);
+int b200_dev_stamp_maps(const double* kappa, const double* Sigma, const double* UC, int m, int n2f, int fade,
+                        int clamp_iter, const double* fade_w, float* kappa32, float* Sigma32, float* UC32,
+                        const double* Tsum_image, int n_img, int n2, double* Tsum_stamp, double* Tsum_inpix,
+                        double* Neff, void* stream);
+/* dst[l, y0+iy, x0+ix] += src[l, iy, ix] for an (nlayer, n2f, n2f) stamp into an (nlayer, side, side) f32 canvas. */
+int b200_dev_accumulate(const void* src, int src_is_f64, int nlayer, int n2f, float* dst, int side, int y0, int x0,
+                        void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PYIMCOM_B200_H */

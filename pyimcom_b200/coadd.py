@@ -1,0 +1,370 @@
+"""Device-resident block driver: the OutStamp loop of one mosaic block on a B200.
+
+Mirrors, for the hot path only, ``coadd.Block.coadd_output_stamps`` / ``_output_stamp_wrapper``
+(coadd.py:1939-2084) and ``OutStamp.__call__`` (coadd.py:979-1363):
+
+    per OutStamp:  _process_input_stamps  -> gather of the selected input pixels      (coadd.py:886-977)
+                   _build_system_matrices -> fused A / mBhalf assembly kernels        (coadd.py:1002-1085)
+                   LAKERNEL[...]          -> pyimcom_b200.lakernel solvers            (lakernel.py)
+                   trapezoid, _perform_coaddition -> finalize / stamp_maps kernels    (coadd.py:1221-1363)
+                   overlap-add into the block maps                                    (coadd.py:1976-1994)
+
+Inputs are a block object exposing what the reference's ``Block`` exposes to ``OutStamp`` (``cfg``,
+``n_inimage``, ``instamps[j][i]`` with ``x_val, y_val, data, pix_count, pix_cumsum, make_selection``) and a
+``PSFTables`` object holding the PSF-overlap tables (psfovl_host.py).  Everything between the upload of
+those inputs and the download of the block maps stays in HBM.
+
+The reference's SysMatA/SysMatB reference-counted caches (psfutil.py:1764-2199) exist to bound CPU RAM;
+here every stamp's A and mBhalf are assembled directly from positions and tables by one kernel each.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from .lakernel import SOLVERS, ApplySpec, DeviceSystem, apply_T, eigen_decompose, ptr, rup, solve_eigen, stream_handle
+from .lakernel import trapezoid_weights
+from .psfovl_host import anchor
+
+TABLEREF_DTYPE = np.dtype([("offset", "<i8"), ("flip", "<i4"), ("pad_", "<i4"), ("penalty_sub", "<f8")])
+assert TABLEREF_DTYPE.itemsize == C.sizeof(_lib.TableRef)
+
+
+class _Arena:
+    """PSF-overlap tables in HBM: each table set is stored once, zero-padded by 6 (np.pad(ovl, 6), psfutil.py:1471)."""
+
+    def __init__(self, nsamp_ovl):
+        self.ngrid = nsamp_ovl + 12
+        self.chunks = []
+        self.base = {}
+        self.size = 0
+        self._keep = []
+
+    def offset(self, arr, idx):
+        """Offset (in doubles) of table arr[idx] inside the arena; registers arr on first use."""
+        key = id(arr)
+        if key not in self.base:
+            self.base[key] = self.size
+            self._keep.append(arr)  # ids stay unique while the arrays are alive
+            lead = int(np.prod(arr.shape[:-2]))
+            pad = np.zeros((lead, self.ngrid, self.ngrid))
+            pad[:, 6:-6, 6:-6] = arr.reshape(lead, arr.shape[-2], arr.shape[-1])
+            self.chunks.append(pad.reshape(-1))
+            self.size += pad.size
+        flat = int(np.ravel_multi_index(idx, arr.shape[:-2]))
+        return self.base[key] + flat * self.ngrid * self.ngrid
+
+    def upload(self):
+        if not self.chunks:
+            return torch.zeros(1, dtype=torch.float64, device="cuda")
+        host = np.concatenate(self.chunks)
+        return torch.from_numpy(host).cuda()
+
+
+class StampPlan:
+    """Host-side description of one OutStamp (what OutStamp.__init__ / _process_input_stamps derive)."""
+
+    __slots__ = ("j_st", "i_st", "n", "idx", "pcode", "groups", "seg_end", "seg_img", "inpix_cumsum", "x0out", "y0out",
+                 "lut", "lut_io")
+
+
+class GpuBlock:
+    """One mosaic block on one GPU."""
+
+    def __init__(self, blk, tables, kernel: str | None = None):
+        if not torch.cuda.is_available():
+            raise RuntimeError("pyimcom_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+        self.blk, self.tab = blk, tables
+        self.cfg = blk.cfg
+        self.kernel = kernel or self.cfg.linear_algebra
+        if self.kernel not in SOLVERS:
+            raise ValueError(f"unsupported LAKERNEL {self.kernel!r} (Cholesky, Eigen, Iterative)")
+        self.plans = {}
+        self.order = []
+        self._uploaded = False
+
+    # ---------------------------------------------------------------------------------------------
+    # host-side planning (coadd.py:846-977)
+    # ---------------------------------------------------------------------------------------------
+    def _global_pixels(self):
+        blk, cfg = self.blk, self.cfg
+        ns = cfg.n1P + 2
+        self.inst_off = np.zeros((ns, ns), dtype=np.int64)
+        xs, ys, imgs, datas = [], [], [], []
+        off = 0
+        for j in range(ns):
+            for i in range(ns):
+                st = blk.instamps[j][i]
+                self.inst_off[j, i] = off
+                npix = int(st.pix_cumsum[-1])
+                xs.append(st.x_val)
+                ys.append(st.y_val)
+                imgs.append(np.repeat(np.arange(blk.n_inimage, dtype=np.int32), st.pix_count.astype(np.int64)))
+                datas.append(st.data)
+                off += npix
+        self.h_x = np.concatenate(xs) if xs else np.zeros(0)
+        self.h_y = np.concatenate(ys) if ys else np.zeros(0)
+        self.h_img = np.concatenate(imgs).astype(np.int32) if imgs else np.zeros(0, dtype=np.int32)
+        self.h_data = np.ascontiguousarray(np.concatenate(datas, axis=1), dtype=np.float32)
+        self.npix_total = off
+
+    def plan_stamp(self, j_st, i_st) -> StampPlan:
+        blk, cfg, tab = self.blk, self.cfg, self.tab
+        nimg = blk.n_inimage
+        p = StampPlan()
+        p.j_st, p.i_st = j_st, i_st
+        bottom, left = (j_st - 1) * cfg.n2, (i_st - 1) * cfg.n2
+        top, right = bottom + cfg.n2 - 1, left + cfg.n2 - 1
+        fk = cfg.fade_kernel
+        p.x0out, p.y0out = float(left - fk), float(bottom - fk)
+        r = cfg.rpix_search
+        idx, pcode, seg_end, seg_img, counts = [], [], [], [], []
+        groups = []
+        pos = 0
+        for dj in (-1, 0, 1):
+            for di in (-1, 0, 1):
+                jj, ii = j_st + dj, i_st + di
+                st = blk.instamps[jj][ii]
+                xp = [left - 0.5, None, right + 0.5][di + 1]  # coadd.py:929-931
+                yp = [bottom - 0.5, None, top + 0.5][dj + 1]
+                sel = st.make_selection((xp, yp), r)
+                G = anchor((jj, ii))
+                if G not in groups:
+                    groups.append(G)
+                lg = groups.index(G)
+                base = int(self.inst_off[jj, ii])
+                if sel is None:
+                    loc = np.arange(int(st.pix_cumsum[-1]), dtype=np.int64)
+                    cum = st.pix_cumsum.astype(np.int64)
+                else:
+                    loc = sel.astype(np.int64)
+                    cum = np.searchsorted(sel, st.pix_cumsum).astype(np.int64)
+                idx.append(base + loc)
+                pcode.append(lg * nimg + self.h_img[base + loc])
+                for k in range(nimg):  # (instamp, image) segments for Tsum_image (coadd.py:1327-1337)
+                    if cum[k + 1] > cum[k]:
+                        seg_end.append(pos + int(cum[k + 1]))
+                        seg_img.append(k)
+                counts.append(loc.size)
+                pos += loc.size
+        p.n = pos
+        p.idx = np.concatenate(idx).astype(np.int32)
+        p.pcode = np.concatenate(pcode).astype(np.int32)
+        p.groups = groups
+        p.seg_end = np.asarray(seg_end, dtype=np.int32)
+        p.seg_img = np.asarray(seg_img, dtype=np.int32)
+        p.inpix_cumsum = np.cumsum([0] + counts, dtype=np.uint32)
+        # table look-ups for the (<= 4 groups) x (n_inimage) codes of this stamp
+        ncode = 4 * nimg
+        lut = np.zeros((ncode, ncode), dtype=TABLEREF_DTYPE)
+        lut["offset"] = -1
+        lut_io = np.full((ncode, cfg.n_out), -1, dtype=np.int64)
+        present = np.unique(p.pcode)
+        for ca in present:
+            Ga, ka = groups[ca // nimg], int(ca % nimg)
+            tab.group(Ga)
+            io = tab.get_io(Ga)
+            for o in range(cfg.n_out):
+                lut_io[ca, o] = self.arena.offset(io, (tab.grp_index(Ga, ka), o))
+            for cb in present:
+                Gb, kb = groups[cb // nimg], int(cb % nimg)
+                tab.group(Gb)
+                t, tidx, flip = tab.table_ii_ref(Ga, ka, Gb, kb)
+                n_in = len(tab.grp_imgs[Ga]) if Ga == Gb else (len(tab.grp_imgs[Ga]) * len(tab.grp_imgs[Gb])) ** 0.5
+                lut[ca, cb] = (self.arena.offset(t, tidx), int(flip), 0, cfg.flat_penalty / n_in)
+        p.lut, p.lut_io = lut, lut_io
+        return p
+
+    def prepare(self, stamps=None):
+        """Plan the requested OutStamps (default: the whole block in the reference's 2x2-group order) and upload."""
+        self._global_pixels()
+        self.arena = _Arena(self.cfg.nsamp_ovl)
+        self.order = list(stamps) if stamps is not None else list(self.blk.stamp_order())
+        self.plans = {ji: self.plan_stamp(*ji) for ji in self.order}
+        self.upload()
+        return self
+
+    def upload(self):
+        cfg = self.cfg
+        dev = "cuda"
+        self.d_x = torch.from_numpy(self.h_x).to(dev)
+        self.d_y = torch.from_numpy(self.h_y).to(dev)
+        self.d_data = torch.from_numpy(self.h_data).to(dev)
+        self.d_tables = self.arena.upload()
+        plans = [self.plans[ji] for ji in self.order]
+        # per-stamp metadata packed into a few arrays, one H2D copy each
+        self.off_pix = np.concatenate([[0], np.cumsum([p.n for p in plans])]).astype(np.int64)
+        self.off_seg = np.concatenate([[0], np.cumsum([p.seg_end.size for p in plans])]).astype(np.int64)
+        cat = lambda arrs, dt: np.concatenate(arrs).astype(dt) if arrs else np.zeros(0, dtype=dt)  # noqa: E731
+        self.d_idx = torch.from_numpy(cat([p.idx for p in plans], np.int32)).to(dev)
+        self.d_pcode_all = torch.from_numpy(cat([p.pcode for p in plans], np.int32)).to(dev)
+        self.d_seg_end = torch.from_numpy(cat([p.seg_end for p in plans], np.int32)).to(dev)
+        self.d_seg_img = torch.from_numpy(cat([p.seg_img for p in plans], np.int32)).to(dev)
+        lut = np.stack([p.lut for p in plans]) if plans else np.zeros((0, 1, 1), dtype=TABLEREF_DTYPE)
+        self.d_lut = torch.from_numpy(lut.view(np.uint8).reshape(len(plans), -1)).to(dev)
+        lut_io = np.stack([p.lut_io for p in plans]) if plans else np.zeros((0, 1, 1), dtype=np.int64)
+        self.d_lut_io = torch.from_numpy(np.ascontiguousarray(lut_io)).to(dev)
+        self.d_fade_w = torch.from_numpy(trapezoid_weights(cfg.fade_kernel)).to(dev) if cfg.fade_kernel > 0 else None
+        self.h2d_bytes = sum(t.numel() * t.element_size() for t in (self.d_x, self.d_y, self.d_data, self.d_tables,
+                                                                     self.d_idx, self.d_pcode_all, self.d_seg_end,
+                                                                     self.d_seg_img, self.d_lut, self.d_lut_io))
+        # block maps (coadd.py:2028-2047)
+        side = cfg.NsideP + 2 * cfg.fade_kernel
+        self.side = side
+        n_out = cfg.n_out
+        self.out_map = torch.zeros((n_out, cfg.n_inframe, side, side), dtype=torch.float32, device=dev)
+        self.T_weightmap = torch.zeros((n_out, self.blk.n_inimage, cfg.n1P, cfg.n1P), dtype=torch.float32, device=dev)
+        self.UC_map = torch.zeros((n_out, side, side), dtype=torch.float32, device=dev)
+        self.Sigma_map = torch.zeros_like(self.UC_map)
+        self.kappa_map = torch.zeros_like(self.UC_map)
+        self.Tsum_map = torch.zeros_like(self.UC_map)
+        self.Neff_map = torch.zeros_like(self.UC_map)
+        self._uploaded = True
+
+    # ---------------------------------------------------------------------------------------------
+    # device pipeline of one OutStamp
+    # ---------------------------------------------------------------------------------------------
+    def build_system(self, k: int):
+        """Stage (a): gather + A + mBhalf for stamp number k of self.order.  Returns (DeviceSystem, indata)."""
+        cfg = self.cfg
+        p = self.plans[self.order[k]]
+        st = stream_handle()
+        n, m = p.n, cfg.n2f**2
+        npad, mpad = rup(n), rup(m)
+        nimg = self.blk.n_inimage
+        px = torch.empty(npad, dtype=torch.float64, device="cuda")
+        py = torch.empty(npad, dtype=torch.float64, device="cuda")
+        indata = torch.empty((cfg.n_inframe, npad), dtype=torch.float32, device="cuda")
+        o = int(self.off_pix[k])
+        idx = self.d_idx[o:o + n]
+        pcode = self.d_pcode_all[o:o + n]
+        # positions and layers: gathered through idx; the table codes are per (stamp, pixel) and were planned on the host
+        _lib.dev_gather_stamp(ptr(idx), n, npad, ptr(self.d_x), ptr(self.d_y), None, ptr(self.d_data),
+                              self.d_data.stride(0), cfg.n_inframe, ptr(px), ptr(py), None, ptr(indata),
+                              indata.stride(0), st)
+        A = torch.empty((npad, npad), dtype=torch.float64, device="cuda")
+        ncode = 4 * nimg
+        _lib.dev_build_A(ptr(px), ptr(py), ptr(pcode), n, npad, ptr(self.d_tables), ptr(self.d_lut[k]), nimg, ncode,
+                         self.arena.ngrid, float(cfg.dscale), float(cfg.nc_ovl), float(cfg.flat_penalty), ptr(A),
+                         A.stride(0), 0.0, st)
+        mB = torch.empty((cfg.n_out, mpad, npad), dtype=torch.float64, device="cuda")
+        _lib.dev_build_B(ptr(px), ptr(py), ptr(pcode), n, npad, ptr(self.d_tables), ptr(self.d_lut_io[k]), cfg.n_out,
+                         self.arena.ngrid, float(cfg.dscale), float(cfg.nc_ovl), cfg.n2f, mpad, p.x0out, p.y0out, ptr(mB),
+                         mB.stride(1), mB.stride(0), st)
+        ds = DeviceSystem(n=n, m=m, n2f=cfg.n2f, A=A, mB=mB, C=np.asarray(self.tab.outovlc, dtype=np.float64),
+                          px=px, py=py)
+        if self.kernel == "Iterative":
+            g = torch.arange(cfg.n2f, dtype=torch.float64, device="cuda")
+            ds.outy = (p.y0out + g).repeat_interleave(cfg.n2f).contiguous()
+            ds.outx = (p.x0out + g).repeat(cfg.n2f).contiguous()
+        return ds, indata
+
+    def apply_spec(self, k: int, indata, want_T32=True, want_Ti64=False) -> ApplySpec:
+        cfg = self.cfg
+        a, b = int(self.off_seg[k]), int(self.off_seg[k + 1])
+        return ApplySpec(fade=cfg.fade_kernel, fade_w=self.d_fade_w, indata=indata, seg_end=self.d_seg_end[a:b],
+                         seg_img=self.d_seg_img[a:b], n_img=self.blk.n_inimage, n2=cfg.n2,
+                         clamp_iter=(self.kernel == "Iterative"), want_T32=want_T32, want_Ti64=want_Ti64)
+
+    def coadd_stamp(self, k: int, keep: bool = False):
+        """OutStamp.__call__ (coadd.py:979-1000) + overlap-add (coadd.py:1976-1994) for stamp k of self.order.
+
+        keep=True returns the per-stamp device results (parity tests); otherwise nothing is retained."""
+        cfg = self.cfg
+        p = self.plans[self.order[k]]
+        st = stream_handle()
+        kept = {}
+        if p.n == 0:  # lakernel.py:110-119 and coadd.py:1094-1100: nothing to add except UC = kappa = 1
+            return self._empty_stamp(p, keep)
+        ds, indata = self.build_system(k)
+        spec = self.apply_spec(k, indata, want_T32=keep, want_Ti64=keep)
+        eig = eigen_decompose(ds) if self.kernel == "Eigen" else None
+        y0, x0 = (p.j_st - 1) * cfg.n2, (p.i_st - 1) * cfg.n2
+        for j_out in range(cfg.n_out):
+            if self.kernel == "Eigen":
+                ko = solve_eigen(ds, cfg, j_out, eig=eig)
+            else:
+                ko = SOLVERS[self.kernel](ds, cfg, j_out)
+            res = apply_T(ds, ko, j_out, spec)
+            acc = lambda src, f64, nl, dst: _lib.dev_accumulate(ptr(src), int(f64), nl, cfg.n2f, ptr(dst), self.side, y0,  # noqa: E731
+                                                                x0, st)
+            acc(res["outimage"], False, cfg.n_inframe, self.out_map[j_out])
+            acc(res["UC"], False, 1, self.UC_map[j_out])
+            acc(res["Sigma"], False, 1, self.Sigma_map[j_out])
+            acc(res["kappa"], False, 1, self.kappa_map[j_out])
+            acc(res["Tsum_inpix"], True, 1, self.Tsum_map[j_out])
+            acc(res["Neff"], True, 1, self.Neff_map[j_out])
+            self.T_weightmap[j_out, :, p.j_st - 1, p.i_st - 1] = res["Tsum_stamp"][: self.blk.n_inimage].float()
+            if keep:
+                kept[j_out] = dict(res=res, ko=ko)
+        if keep:
+            kept["ds"], kept["indata"], kept["plan"] = ds, indata, p
+        return kept
+
+    def _empty_stamp(self, p, keep):
+        cfg = self.cfg
+        y0, x0 = (p.j_st - 1) * cfg.n2, (p.i_st - 1) * cfg.n2
+        sl = (slice(None), slice(y0, y0 + cfg.n2f), slice(x0, x0 + cfg.n2f))
+        w = trapezoid_weights(cfg.fade_kernel)
+        one = np.ones((cfg.n2f, cfg.n2f), dtype=np.float32)
+        if cfg.fade_kernel > 0:
+            fk2 = 2 * cfg.fade_kernel
+            for arr in (one,):
+                arr[:fk2, :] *= w[:, None]
+                arr[::-1][:fk2, :] *= w[:, None]
+                arr[:, :fk2] *= w[None, :]
+                arr[:, ::-1][:, :fk2] *= w[None, :]
+        t = torch.from_numpy(one).cuda()
+        self.UC_map[sl] += t
+        self.kappa_map[sl] += t
+        return {}
+
+    def run(self):
+        """coadd_output_stamps(sim_mode=False) (coadd.py:2056-2069): every planned stamp, in order."""
+        assert self._uploaded, "call prepare() first"
+        for k in range(len(self.order)):
+            self.coadd_stamp(k)
+        return self
+
+    def download(self):
+        """Block maps to host (the final gather of the output cube starts from these)."""
+        torch.cuda.current_stream().synchronize()
+        names = ("out_map", "T_weightmap", "UC_map", "Sigma_map", "kappa_map", "Tsum_map", "Neff_map")
+        return {nm: getattr(self, nm).cpu().numpy() for nm in names}
+
+
+class GpuOutStamp:
+    """Host view of one coadded OutStamp with the reference's attribute names (coadd.py:795-1363)."""
+
+    def __init__(self, gblk: GpuBlock, j_st: int, i_st: int):
+        k = gblk.order.index((j_st, i_st))
+        cfg = gblk.cfg
+        kept = gblk.coadd_stamp(k, keep=True)
+        torch.cuda.synchronize()
+        p = gblk.plans[(j_st, i_st)]
+        n, m, n2f = p.n, cfg.n2f**2, cfg.n2f
+        self.inpix_cumsum = p.inpix_cumsum
+        ds = kept["ds"]
+        self.sysmata = ds.A[:n, :n].cpu().numpy()
+        self.mhalfb = ds.mB[:, :m, :n].cpu().numpy()
+        self.outovlc = np.asarray(gblk.tab.outovlc)
+        self.indata = kept["indata"][:, :n].cpu().numpy()
+        n_out = cfg.n_out
+        g = lambda key, j: kept[j]["res"][key].cpu().numpy()  # noqa: E731
+        self.T = np.stack([g("T32", j)[:, :n] for j in range(n_out)])
+        self.Ti64 = np.stack([g("Ti64", j)[:, :n] for j in range(n_out)])
+        self.UC = np.stack([g("UC", j).reshape(n2f, n2f) for j in range(n_out)])
+        self.Sigma = np.stack([g("Sigma", j).reshape(n2f, n2f) for j in range(n_out)])
+        self.kappa = np.stack([g("kappa", j).reshape(n2f, n2f) for j in range(n_out)])
+        self.outimage = np.stack([g("outimage", j).reshape(cfg.n_inframe, n2f, n2f) for j in range(n_out)])
+        self.Tsum_stamp = np.stack([g("Tsum_stamp", j)[: gblk.blk.n_inimage] for j in range(n_out)])
+        self.Tsum_inpix = np.stack([g("Tsum_inpix", j).reshape(n2f, n2f) for j in range(n_out)])
+        self.Neff = np.stack([g("Neff", j).reshape(n2f, n2f) for j in range(n_out)])
+        self.extras = [
+            {k_: (v.cpu().numpy() if torch.is_tensor(v) else v) for k_, v in kept[j]["ko"].extras.items()}
+            for j in range(n_out)
+        ]

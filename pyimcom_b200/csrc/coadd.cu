@@ -1,0 +1,284 @@
+// Stage (c): apply the coaddition matrix.
+//   k_finalize     lakernel.py:309-317, 390-393 (D, N, node combination) + coadd.py:1321-1354
+//                  (fade T, float32 cast, Tsum per input image, outimage = T . indata)
+//   k_stamp_maps   coadd.py:1104-1122, 1339-1350 (clamp, fade the U/S/K maps, Tsum_stamp/inpix, Neff)
+//   k_accumulate   coadd.py:1976-1994 (overlap-add of one stamp into the block cube / maps)
+//
+// k_finalize is the HBM-bound T-apply: it reads the f64 node solutions once (8*nv*m*n B) plus -B/2
+// (8*m*n B), writes the float32 T (4*m*n B) and produces everything else from registers/shared memory.
+// Eight output pixels per CTA; the  (8 pixels) x (n_inframe <= 8 per pass) x n  product runs on the
+// FP64 tensor pipe (DMMA.8x8x4) from a shared-memory tile of the faded float32 row values, accumulated
+// in f64 (the reference's einsum is float32; f64 accumulation is at least as accurate).
+#include "common.cuh"
+#include "kernels.h"
+
+namespace b200 {
+
+namespace {
+
+constexpr int FT = 256;     // threads per CTA
+constexpr int ROWS = 8;     // output pixels per CTA
+constexpr int CH = 512;     // columns per chunk held in shared memory
+constexpr int LDT = CH + 4; // smem row stride (doubles): 516 = 4 mod 16 -> conflict-free DMMA fragment loads
+
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+
+// trapezoid weight sequence applied to one float32 value exactly as numpy does it (coadd.py:1269-1282):
+// each "*=" promotes to float64, multiplies, and rounds back to float32.
+__device__ __forceinline__ float fade32(float v, int iy, int ix, int ny, int nx, int fk2, const double* __restrict__ s) {
+    if (fk2 <= 0) return v;
+    if (iy < fk2) v = (float)((double)v * s[iy]);
+    if (iy > ny - 1 - fk2) v = (float)((double)v * s[ny - 1 - iy]);
+    if (ix < fk2) v = (float)((double)v * s[ix]);
+    if (ix > nx - 1 - fk2) v = (float)((double)v * s[nx - 1 - ix]);
+    return v;
+}
+__device__ __forceinline__ double fade64(double v, int iy, int ix, int ny, int nx, int fk2, const double* __restrict__ s) {
+    if (fk2 <= 0) return v;
+    if (iy < fk2) v = v * s[iy];
+    if (iy > ny - 1 - fk2) v = v * s[ny - 1 - iy];
+    if (ix < fk2) v = v * s[ix];
+    if (ix > nx - 1 - fk2) v = v * s[nx - 1 - ix];
+    return v;
+}
+
+__global__ void __launch_bounds__(FT) k_finalize(FinalizeArgs A) {
+    extern __shared__ __align__(16) double sm[];
+    double* tile = sm;                         // [ROWS][LDT] faded f32 values (as doubles) of this chunk
+    double* din = tile + ROWS * LDT;           // [8][LDT] indata chunk (as doubles), frames of the current pass
+    double* red = din + 8 * LDT;               // [ROWS][8 warps][2] D,N partials ; then [8 warps][64] outimage
+    double* segsum = red + 8 * 64 + ROWS * 8 * 2;  // [ROWS][nseg]
+    __shared__ double sfade[64];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int a0 = blockIdx.x * ROWS;
+    const int fk2 = 2 * A.fade;
+    for (int k = tid; k < fk2 && k < 64; k += FT) sfade[k] = A.fade_w[k];
+    for (int t = tid; t < ROWS * A.nseg; t += FT) segsum[t] = 0.0;
+    __syncthreads();
+
+    // warp w owns output pixel a0 + w for the streaming part
+    const int a = a0 + warp;
+    const bool live = a < A.m;
+    const int iy = live ? a / A.n2f : 0, ix = live ? a - iy * A.n2f : 0;
+    double wnode[16];
+#pragma unroll
+    for (int p = 0; p < 16; p++) wnode[p] = (A.w && live && p < A.nv) ? A.w[(size_t)a * A.nv + p] : 0.0;
+    double dsum = 0.0, nsum = 0.0;
+    const int npass = (A.n_inframe + 7) / 8;
+    double oacc[2][2] = {{0.0, 0.0}, {0.0, 0.0}};  // DMMA accumulators: pass 0/1, (pixel g, frames 2q,2q+1)
+    int seg = 0;  // warp-uniform running segment pointer (columns are visited in increasing order)
+
+    for (int c0 = 0; c0 < A.n; c0 += CH) {
+        const int cw = min(CH, A.n - c0);
+        // ---- stream: combine nodes, D/N partials, fade + float32 cast, T32 store, tile fill ----
+        for (int j = lane; j < CH; j += 32) {
+            const int col = c0 + j;
+            double tv = 0.0;
+            if (live && j < cw) {
+                double ti;
+                if (A.w) {
+                    ti = 0.0;
+#pragma unroll
+                    for (int p = 0; p < 16; p++)
+                        if (p < A.nv) ti += A.Tpi[p * A.strideT + (size_t)a * A.ldt + col] * wnode[p];
+                } else {
+                    ti = A.Tpi[(size_t)a * A.ldt + col];
+                }
+                if (A.Ti64) A.Ti64[(size_t)a * A.ldt64 + col] = ti;
+                if (A.mB) dsum += A.mB[(size_t)a * A.ldb + col] * ti;
+                nsum += ti * ti;
+                const float t32 = fade32((float)ti, iy, ix, A.n2f, A.n2f, fk2, sfade);
+                if (A.T32) A.T32[(size_t)a * A.ldt32 + col] = t32;
+                tv = (double)t32;
+            }
+            tile[warp * LDT + j] = tv;
+        }
+        __syncwarp();
+        // per-(instamp,image) segment sums of the faded float32 T (coadd.py:1327-1337), from the tile row
+        while (live && seg < A.nseg) {
+            const int sb = seg ? A.seg_end[seg - 1] : 0, se = A.seg_end[seg];
+            if (sb >= c0 + cw) break;
+            const int lo = max(sb, c0), hi = min(se, c0 + cw);
+            double sp = 0.0;
+            for (int j = lo + lane; j < hi; j += 32) sp += tile[warp * LDT + j - c0];
+            sp = warp_sum(sp);
+            if (lane == 0) segsum[warp * A.nseg + seg] += sp;
+            if (se <= c0 + cw) seg++;
+            else break;
+        }
+        // ---- outimage on the tensor pipe: (8 pixels) x (8 frames) += tile(8 x cw) * din(8 x cw)^T ----
+#pragma unroll
+        for (int ps = 0; ps < 2; ps++) {
+            if (ps < npass) {
+                __syncthreads();
+                for (int e = tid; e < 8 * CH; e += FT) {
+                    const int f = e / CH, j = e - f * CH;
+                    const int fr = ps * 8 + f;
+                    din[f * LDT + j] =
+                        (fr < A.n_inframe && j < cw) ? (double)A.indata[(size_t)fr * A.ldi + c0 + j] : 0.0;
+                }
+                __syncthreads();
+                // warp w takes the k-range [w*64, w*64+64) of the chunk
+                const int g = lane >> 2, q = lane & 3;
+                const double* ap = tile + g * LDT + warp * 64 + q;
+                const double* bp = din + g * LDT + warp * 64 + q;
+#pragma unroll
+                for (int kk = 0; kk < 16; kk++) dmma884(oacc[ps][0], oacc[ps][1], ap[kk * 4], bp[kk * 4]);
+            }
+        }
+        __syncthreads();
+    }
+    // ---- reductions ----
+    dsum = warp_sum(dsum);
+    nsum = warp_sum(nsum);
+    if (live && lane == 0) {
+        if (A.D) A.D[a] = dsum;
+        if (A.N) A.N[a] = nsum;
+    }
+    // outimage: sum the 8 warps' partial 8x8 blocks (fixed order -> deterministic)
+#pragma unroll
+    for (int ps = 0; ps < 2; ps++) {
+        if (ps >= npass) break;
+        __syncthreads();
+        const int g = lane >> 2, q = lane & 3;
+        red[warp * 64 + g * 8 + q * 2] = oacc[ps][0];
+        red[warp * 64 + g * 8 + q * 2 + 1] = oacc[ps][1];
+        __syncthreads();
+        if (tid < 64) {
+            double s = 0.0;
+#pragma unroll
+            for (int w8 = 0; w8 < 8; w8++) s += red[w8 * 64 + tid];
+            const int pg = tid >> 3, f = ps * 8 + (tid & 7);
+            if (a0 + pg < A.m && f < A.n_inframe) A.outimage[(size_t)f * A.m + a0 + pg] = (float)s;
+        }
+    }
+    __syncthreads();
+    // Tsum_image[a][img] = sum of this pixel's segment sums belonging to image img, in segment order
+    for (int t = tid; t < ROWS * A.n_img; t += FT) {
+        const int r = t / A.n_img, img = t - r * A.n_img;
+        if (a0 + r >= A.m) continue;
+        double s = 0.0;
+        for (int sg = 0; sg < A.nseg; sg++)
+            if (A.seg_img[sg] == img) s += segsum[r * A.nseg + sg];
+        A.Tsum_image[(size_t)(a0 + r) * A.n_img + img] = s;
+    }
+}
+
+// ---- per-stamp maps --------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_stamp_maps(const double* __restrict__ kappa, const double* __restrict__ Sigma,
+                                                    const double* __restrict__ UC, int m, int n2f, int fade,
+                                                    int clamp_iter, const double* __restrict__ fade_w,
+                                                    float* __restrict__ kappa32, float* __restrict__ Sigma32,
+                                                    float* __restrict__ UC32, const double* __restrict__ Tsum_image,
+                                                    int n_img, int n2, double* __restrict__ Tsum_stamp,
+                                                    double* __restrict__ Tsum_inpix, double* __restrict__ Neff) {
+    const int fk2 = 2 * fade;
+    for (int a = blockIdx.x * blockDim.x + threadIdx.x; a < m; a += gridDim.x * blockDim.x) {
+        const int iy = a / n2f, ix = a - iy * n2f;
+        float k = (float)kappa[a], s = (float)Sigma[a], u = (float)UC[a];
+        if (clamp_iter) {  // coadd.py:1104-1107
+            u = fmaxf(u, 1e-32f);
+            s = fmaxf(s, 1e-32f);
+        }
+        kappa32[a] = fade32(k, iy, ix, n2f, n2f, fk2, fade_w);
+        Sigma32[a] = fade32(s, iy, ix, n2f, n2f, fk2, fade_w);
+        UC32[a] = fade32(u, iy, ix, n2f, n2f, fk2, fade_w);
+        if (Tsum_image) {
+            double tot = 0.0, tabs = 0.0;
+            for (int g = 0; g < n_img; g++) {
+                const double v = Tsum_image[(size_t)a * n_img + g];
+                tot += v;
+                tabs += fabs(v);
+            }
+            double sq = 0.0;
+            for (int g = 0; g < n_img; g++) {
+                const double v = Tsum_image[(size_t)a * n_img + g] / tabs;
+                sq += v * v;
+            }
+            Tsum_inpix[a] = tot;
+            Neff[a] = fade64(1.0 / sq, iy, ix, n2f, n2f, fk2, fade_w);
+        }
+    }
+    if (Tsum_image && blockIdx.x == 0) {  // Tsum_stamp[img] = sum_a Tsum_image[a][img] / n2^2
+        for (int g = threadIdx.x; g < n_img; g += blockDim.x) {
+            double s = 0.0;
+            for (int a = 0; a < m; a++) s += Tsum_image[(size_t)a * n_img + g];
+            Tsum_stamp[g] = s / ((double)n2 * (double)n2);
+        }
+    }
+}
+
+// ---- overlap-add of one stamp into the block maps (coadd.py:1976-1994) ------------------------------
+__global__ void __launch_bounds__(256) k_accumulate(const float* __restrict__ src, int nlayer, int n2f,
+                                                    float* __restrict__ dst, int side, int y0, int x0) {
+    const int m = n2f * n2f;
+    for (long t = (long)blockIdx.x * blockDim.x + threadIdx.x; t < (long)nlayer * m; t += (long)gridDim.x * blockDim.x) {
+        const int l = (int)(t / m), a = (int)(t - (long)l * m);
+        const int iy = a / n2f, ix = a - iy * n2f;
+        float* d = dst + ((size_t)l * side + (y0 + iy)) * side + x0 + ix;
+        *d = *d + src[t];
+    }
+}
+__global__ void __launch_bounds__(256) k_accumulate64(const double* __restrict__ src, int nlayer, int n2f,
+                                                      float* __restrict__ dst, int side, int y0, int x0) {
+    const int m = n2f * n2f;
+    for (long t = (long)blockIdx.x * blockDim.x + threadIdx.x; t < (long)nlayer * m; t += (long)gridDim.x * blockDim.x) {
+        const int l = (int)(t / m), a = (int)(t - (long)l * m);
+        const int iy = a / n2f, ix = a - iy * n2f;
+        float* d = dst + ((size_t)l * side + (y0 + iy)) * side + x0 + ix;
+        *d = *d + (float)src[t];
+    }
+}
+
+}  // namespace
+
+size_t finalize_smem(int nseg) {
+    return sizeof(double) * ((size_t)ROWS * LDT + 8 * LDT + 8 * 64 + ROWS * 8 * 2 + (size_t)ROWS * (nseg > 0 ? nseg : 1));
+}
+
+int launch_finalize(const FinalizeArgs& a, cudaStream_t s) {
+    if (a.m <= 0 || a.n <= 0) return 0;
+    B200_REQUIRE(a.n_inframe <= 16, "finalize handles at most 16 input layers per launch");
+    B200_REQUIRE(a.nv <= 16 && a.fade <= 32, "finalize: nv <= 16, fade <= 32");
+    const size_t smem = finalize_smem(a.nseg);
+    B200_REQUIRE(smem <= 200 * 1024, "finalize: too many (instamp,image) segments");
+    static bool done = false;
+    if (!done) {
+        B200_CUDA(cudaFuncSetAttribute(k_finalize, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        done = true;
+    }
+    k_finalize<<<(a.m + ROWS - 1) / ROWS, FT, smem, s>>>(a);
+    B200_LAUNCH_CHECK();
+    return 0;
+}
+
+int launch_stamp_maps(const double* kappa, const double* Sigma, const double* UC, int m, int n2f, int fade,
+                      int clamp_iter, const double* fade_w, float* kappa32, float* Sigma32, float* UC32,
+                      const double* Tsum_image, int n_img, int n2, double* Tsum_stamp, double* Tsum_inpix, double* Neff,
+                      cudaStream_t s) {
+    if (m <= 0) return 0;
+    k_stamp_maps<<<(m + 255) / 256, 256, 0, s>>>(kappa, Sigma, UC, m, n2f, fade, clamp_iter, fade_w, kappa32, Sigma32,
+                                                 UC32, Tsum_image, n_img, n2, Tsum_stamp, Tsum_inpix, Neff);
+    B200_LAUNCH_CHECK();
+    return 0;
+}
+
+int launch_accumulate(const void* src, int src_is_f64, int nlayer, int n2f, float* dst, int side, int y0, int x0,
+                      cudaStream_t s) {
+    const long tot = (long)nlayer * n2f * n2f;
+    if (tot <= 0) return 0;
+    B200_REQUIRE(y0 >= 0 && x0 >= 0 && y0 + n2f <= side && x0 + n2f <= side, "stamp outside the block canvas");
+    const int grid = (int)((tot + 255) / 256);
+    if (src_is_f64)
+        k_accumulate64<<<grid, 256, 0, s>>>((const double*)src, nlayer, n2f, dst, side, y0, x0);
+    else
+        k_accumulate<<<grid, 256, 0, s>>>((const float*)src, nlayer, n2f, dst, side, y0, x0);
+    B200_LAUNCH_CHECK();
+    return 0;
+}
+
+}  // namespace b200

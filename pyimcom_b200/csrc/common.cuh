@@ -1,0 +1,63 @@
+// Shared device helpers for the pyimcom_b200 CUDA library (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+namespace b200 {
+
+// ---- error plumbing: every C-ABI entry point returns 0 or a negative/CUDA error code ----------
+void set_error(const char* fmt, ...);
+int check_cuda(cudaError_t e, const char* what, const char* file, int line);
+
+#define B200_CUDA(call)                                                   \
+    do {                                                                  \
+        int _rc = ::b200::check_cuda((call), #call, __FILE__, __LINE__);  \
+        if (_rc) return _rc;                                              \
+    } while (0)
+
+// kernel-launch accounting (b200_launch_count): every launcher reports how many kernels it enqueued
+extern long long g_launches;
+#define B200_LAUNCH_CHECK()              \
+    do {                                 \
+        ::b200::g_launches += 1;         \
+        B200_CUDA(cudaGetLastError());   \
+    } while (0)
+#define B200_LAUNCHED(k) (::b200::g_launches += (k))
+
+#define B200_REQUIRE(cond, msg)                                           \
+    do {                                                                  \
+        if (!(cond)) {                                                    \
+            ::b200::set_error("%s:%d: requirement failed: %s (%s)", __FILE__, __LINE__, #cond, msg); \
+            return -1;                                                    \
+        }                                                                 \
+    } while (0)
+
+// grow-only device scratch used by the host-pointer entry points (function seam)
+int scratch(int slot, size_t bytes, void** out);
+void scratch_release();
+
+// ---- small reductions --------------------------------------------------------------------------
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// deterministic block sum (blockDim.x multiple of 32, <= 1024); result valid in every thread
+__device__ __forceinline__ double block_sum(double v, double* red /* >= 33 doubles of smem */) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    v = warp_sum(v);
+    __syncthreads();
+    if (lane == 0) red[wid] = v;
+    __syncthreads();
+    if (wid == 0) {
+        double t = (lane < nw) ? red[lane] : 0.0;
+        t = warp_sum(t);
+        if (lane == 0) red[32] = t;
+    }
+    __syncthreads();
+    return red[32];
+}
+
+}  // namespace b200

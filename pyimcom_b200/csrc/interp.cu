@@ -1,0 +1,439 @@
+// D5512 interpolation kernels: the furry_parakeet function seam (iD5512C, iD5512C_sym, gridD5512C)
+// and the fused system-matrix assembly kernels that replace the reference's per-image-pair Python
+// loops (psfutil.py:1401-1732, coadd.py:1028-1082).
+//
+// Arithmetic follows routine.py statement by statement (inner sum over x taps then outer over y
+// taps) with fused multiply-adds; see the note at d5512_getw.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace b200 {
+
+__device__ __constant__ double c_d5512_e[5][5] = {
+    {+1.651881673372979740e-05, -3.145538007199505447e-04, +1.793518183780194427e-03, -2.904014557029917318e-03,
+     +6.187591260980151433e-04},
+    {-1.146756217210629335e-04, +2.883845374976550142e-03, -1.857047531896089884e-02, +3.147734488597204311e-02,
+     -6.753293626461192439e-03},
+    {+3.256838096371517067e-04, -9.702063770653997568e-03, +8.678848026470635524e-02, -1.659182651092198924e-01,
+     +3.620560878249733799e-02},
+    {-4.541830837949564726e-04, +1.494862093737218955e-02, -1.668775957435094937e-01, +5.879306056792649171e-01,
+     -1.367845996704077915e-01},
+    {+2.266560930061513573e-04, -7.815848920941316502e-03, +9.686607348538181506e-02, -4.505856722239036105e-01,
+     +6.067135256905490381e-01}};
+__device__ __constant__ double c_d5512_o[5][5] = {
+    {-3.486978652054735998e-06, +6.753750285320532433e-05, -3.871378836550175566e-04, +6.279918076641771273e-04,
+     -1.338434614116611838e-04},
+    {+3.121412120355294799e-05, -8.040343683015897672e-04, +5.209574765466357636e-03, -8.847326408846412429e-03,
+     +1.898674086370833597e-03},
+    {-1.243658986204533102e-04, +3.804930695189636097e-03, -3.434861846914529643e-02, +6.581033749134083954e-02,
+     -1.436476114189205733e-02},
+    {+2.894406669584551734e-04, -9.794291009695265532e-03, +1.104231510875857830e-01, -3.906954914039130755e-01,
+     +9.092432925988773451e-02},
+    {-4.336085507644610966e-04, +1.537862263741893339e-02, -1.925091434770601628e-01, +8.993141455798455697e-01,
+     -1.213035309579723942e+00}};
+
+// ---- D5512 interpolation weights ---------------------------------------------------------------
+// Reference: furry_parakeet iD5512C_getw == pyimcom/routine.py:29-122.  Ten weights from five even
+// and five odd polynomials in fh = frac - 1/2, Horner order as in the reference.  The Horner steps
+// and the tap sums below are fused multiply-adds: each differs from the reference's separately
+// rounded multiply/add by at most one rounding (relative 1e-16 per step; parity tests state 1e-13).
+// The sample COORDINATES are computed with the reference's exact operation sequence (no contraction)
+// so that int(x), the on-grid test and the fractional offset are bit-identical to the CPU statement.
+
+__device__ __forceinline__ void d5512_getw(double* __restrict__ w, double fh) {
+    const double fh2 = fh * fh;
+#pragma unroll
+    for (int k = 0; k < 5; k++) {
+        double e = c_d5512_e[k][0];
+        double o = c_d5512_o[k][0];
+#pragma unroll
+        for (int q = 1; q < 5; q++) {
+            e = fma(e, fh2, c_d5512_e[k][q]);
+            o = fma(o, fh2, c_d5512_o[k][q]);
+        }
+        o *= fh;
+        w[k] = e + o;
+        w[9 - k] = e - o;
+    }
+}
+
+// off-grid test of the reference (routine.py:166): the 10-tap window must fit the grid
+__device__ __forceinline__ bool d5512_on_grid(int xi, int ngx) { return !(xi < 4 || xi >= ngx - 5); }
+
+// 10x10 tap sum at integer corner (yi-4, xi-4) of grid g (row stride ngx).  flip=1 reads the grid
+// mirrored in both axes (np.flip of the table, psfutil.py:1659-1665) without materialising it.
+__device__ __forceinline__ double d5512_taps(const double* __restrict__ g, int ngy, int ngx, int yi, int xi,
+                                             const double* wx, const double* wy, int flip) {
+    double acc = 0.0;
+    if (!flip) {
+        const double* p = g + (size_t)(yi - 4) * ngx + (xi - 4);
+#pragma unroll
+        for (int i = 0; i < 10; i++) {
+            double strip = 0.0;
+#pragma unroll
+            for (int j = 0; j < 10; j++) strip = fma(wx[j], __ldg(p + j), strip);
+            acc = fma(strip, wy[i], acc);
+            p += ngx;
+        }
+    } else {
+        const double* p = g + (size_t)(ngy - 1 - (yi - 4)) * ngx + (ngx - 1 - (xi - 4));
+#pragma unroll
+        for (int i = 0; i < 10; i++) {
+            double strip = 0.0;
+#pragma unroll
+            for (int j = 0; j < 10; j++) strip = fma(wx[j], __ldg(p - j), strip);
+            acc = fma(strip, wy[i], acc);
+            p -= ngx;
+        }
+    }
+    return acc;
+}
+
+// ------------------------------------------------------------------------------------------------
+// iD5512C: routine.py:125-181.  One thread per scattered point, all layers.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_iD5512C(const double* __restrict__ f, int nlayer, int ngy, int ngx,
+                                                 const double* __restrict__ xpos, const double* __restrict__ ypos,
+                                                 long nout, double* __restrict__ out) {
+    long ip = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (ip >= nout) return;
+    const double x = xpos[ip], y = ypos[ip];
+    const int xi = (int)x, yi = (int)y;
+    if (!d5512_on_grid(xi, ngx) || !d5512_on_grid(yi, ngy)) return;  // output untouched
+    double wx[10], wy[10];
+    d5512_getw(wx, x - xi - 0.5);
+    d5512_getw(wy, y - yi - 0.5);
+    for (int l = 0; l < nlayer; l++)
+        out[(size_t)l * nout + ip] = d5512_taps(f + (size_t)l * ngy * ngx, ngy, ngx, yi, xi, wx, wy, 0);
+}
+
+// iD5512C_sym: routine.py:184-253.  Upper triangle of a sq x sq point matrix, mirrored.
+__global__ void __launch_bounds__(128) k_iD5512C_sym(const double* __restrict__ f, int nlayer, int ngy, int ngx,
+                                                     const double* __restrict__ xpos, const double* __restrict__ ypos,
+                                                     long nout, int sq, double* __restrict__ out) {
+    long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (long)sq * sq) return;
+    const int i1 = (int)(t / sq), i2 = (int)(t % sq);
+    if (i2 < i1) return;
+    const long ip = (long)i1 * sq + i2, ipm = (long)i2 * sq + i1;
+    const double x = xpos[ip], y = ypos[ip];
+    const int xi = (int)x, yi = (int)y;
+    if (!d5512_on_grid(xi, ngx) || !d5512_on_grid(yi, ngy)) {
+        // the reference leaves the upper entry untouched and still copies it to the lower triangle
+        if (i1 != i2)
+            for (int l = 0; l < nlayer; l++) out[(size_t)l * nout + ipm] = out[(size_t)l * nout + ip];
+        return;
+    }
+    double wx[10], wy[10];
+    d5512_getw(wx, x - xi - 0.5);
+    d5512_getw(wy, y - yi - 0.5);
+    for (int l = 0; l < nlayer; l++) {
+        double v = d5512_taps(f + (size_t)l * ngy * ngx, ngy, ngx, yi, xi, wx, wy, 0);
+        out[(size_t)l * nout + ip] = v;
+        out[(size_t)l * nout + ipm] = v;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// gridD5512C: routine.py:256-338.  One CTA per input pixel: weights for the nxo columns and nyo rows
+// are computed once into shared memory (off-grid => zero weights, index 4), then the nyo*nxo outputs.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_gridD5512C(const double* __restrict__ f, int ngy, int ngx,
+                                                    const double* __restrict__ xpos, const double* __restrict__ ypos,
+                                                    int nxo, int nyo, double* __restrict__ out) {
+    extern __shared__ double sm[];
+    double* wx = sm;                    // [nxo][10]
+    double* wy = sm + 10 * (size_t)nxo;  // [nyo][10]
+    int* xi = (int*)(wy + 10 * (size_t)nyo);
+    int* yi = xi + nxo;
+    const long p = blockIdx.x;
+    for (int t = threadIdx.x; t < nxo + nyo; t += blockDim.x) {
+        const bool isx = t < nxo;
+        const int k = isx ? t : t - nxo;
+        const double v = isx ? xpos[p * nxo + k] : ypos[p * nyo + k];
+        int vi = (int)v;
+        double w[10];
+        if (!d5512_on_grid(vi, isx ? ngx : ngy)) {
+            vi = 4;
+#pragma unroll
+            for (int q = 0; q < 10; q++) w[q] = 0.0;
+        } else {
+            d5512_getw(w, v - vi - 0.5);
+        }
+        double* dst = (isx ? wx : wy) + 10 * (size_t)k;
+#pragma unroll
+        for (int q = 0; q < 10; q++) dst[q] = w[q];
+        (isx ? xi : yi)[k] = vi;
+    }
+    __syncthreads();
+    const int npt = nxo * nyo;
+    for (int t = threadIdx.x; t < npt; t += blockDim.x) {
+        const int iy = t / nxo, ix = t - iy * nxo;
+        out[p * npt + t] = d5512_taps(f, ngy, ngx, yi[iy], xi[ix], wx + 10 * ix, wy + 10 * iy, 0);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Fused A assembly for one output stamp (stage a; replaces psfutil.py:1401-1495, 1597-1732 and the
+// 9+36 block scatter of coadd.py:1028-1069).
+//
+// The n selected input pixels of the 3x3 InStamp neighbourhood are given in the reference's
+// concatenation order with, per pixel, position (x,y) in output-pixel units and a dense code
+// (local PSF-group id * nimg + image id).  Entry (i,j), i<=j, is the D5512 interpolation of the
+// PSF-overlap table of (group_i,image_i ; group_j,image_j) at ((p_i - p_j)/dscale + nc + 6) -- the
+// reference evaluates exactly these upper-triangle entries (same stamp & image: iD5512C_sym;
+// same stamp, image j<i: block (j,i); stamp a<b: block (a,b)) and mirrors them; so do we.
+// Tables are stored zero-padded by 6 (np.pad(ovl, 6), psfutil.py:1471, 1696).
+// lut[(ci * ncode + cj)] = {table offset (doubles) into `tables`, flip, flat-penalty subtrahend}.
+// Rows/columns n..npad-1 are filled with the identity so the padded matrix stays SPD.
+// One CTA per upper-triangular 32x32 tile; the mirrored tile is written through shared memory so
+// both stores are row-contiguous.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_build_A(const double* __restrict__ px, const double* __restrict__ py,
+                                                 const int* __restrict__ pcode, int n, int npad,
+                                                 const double* __restrict__ tables, const TableRef* __restrict__ lut,
+                                                 int nimg, int ncode, int ngrid, double dscale, double nc,
+                                                 double flat_penalty, double* __restrict__ A, int lda,
+                                                 double diag_add) {
+    __shared__ double tile[32][33];
+    const int nt = npad / 32;
+    int bi, rem = blockIdx.x;
+    {
+        // invert the triangular tile numbering: row bi holds (nt - bi) tiles
+        const double b = 2.0 * nt + 1.0;
+        int guess = (int)((b - sqrt(b * b - 8.0 * rem)) * 0.5);
+        if (guess < 0) guess = 0;
+        if (guess > nt - 1) guess = nt - 1;
+        while (guess > 0 && (long)guess * (2 * nt - guess + 1) / 2 > rem) guess--;
+        while ((long)(guess + 1) * (2 * nt - guess) / 2 <= rem) guess++;
+        bi = guess;
+        rem -= (int)((long)bi * (2 * nt - bi + 1) / 2);
+    }
+    const int bj = bi + rem;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+    const int j = bj * 32 + tx;
+    double xj = 0, yj = 0;
+    int cj = 0;
+    if (j < n) {
+        xj = px[j];
+        yj = py[j];
+        cj = pcode[j];
+    }
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+        const int li = ty + 8 * r;
+        const int i = bi * 32 + li;
+        double v = 0.0;
+        if (i < n && j < n) {
+            if (i <= j) {
+                const int ci = pcode[i];
+                // dd = (p_i - p_j); dd /= dscale; dd += nc; (+6 at the call) -- psfutil.py:1423-1428, 1474
+                const double x = __dadd_rn(__dadd_rn(__ddiv_rn(__dadd_rn(px[i], -xj), dscale), nc), 6.0);
+                const double y = __dadd_rn(__dadd_rn(__ddiv_rn(__dadd_rn(py[i], -yj), dscale), nc), 6.0);
+                const TableRef tr = lut[(size_t)ci * ncode + cj];
+                const int xi = (int)x, yi = (int)y;
+                if (tr.offset >= 0 && d5512_on_grid(xi, ngrid) && d5512_on_grid(yi, ngrid)) {
+                    double wx[10], wy[10];
+                    d5512_getw(wx, x - xi - 0.5);
+                    d5512_getw(wy, y - yi - 0.5);
+                    v = d5512_taps(tables + tr.offset, ngrid, ngrid, yi, xi, wx, wy, tr.flip);
+                }
+                if (flat_penalty != 0.0) {  // psfutil.py:1483-1486, 1705-1708
+                    v = __dadd_rn(v, -tr.penalty_sub);
+                    if (ci % nimg == cj % nimg) v = __dadd_rn(v, flat_penalty);
+                }
+                if (i == j) v += diag_add;
+                A[(size_t)i * lda + j] = v;
+            }
+        } else if (i < npad && j < npad) {
+            v = (i == j) ? 1.0 : 0.0;
+            if (i <= j) A[(size_t)i * lda + j] = v;
+        }
+        tile[li][tx] = v;
+    }
+    __syncthreads();
+    // mirror: A[j][i] = A[i][j] for i<j, written row-contiguously through the shared tile
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+        const int lj = ty + 8 * r;  // local column index of the tile -> output row
+        const int jj = bj * 32 + lj, ii = bi * 32 + tx;
+        if (jj < npad && ii < npad && ii < jj) A[(size_t)jj * lda + ii] = tile[tx][lj];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Fused mBhalf assembly for one output stamp (stage a; replaces psfutil.py:1497-1595 and
+// coadd.py:1075-1082).  mBhalf[o][a=(iy,ix)][i] = gridD5512C of io-table(group_i,image_i,o) at
+// ((x_i - xout[ix])/dscale + nc + 6, (y_i - yout[iy])/dscale + nc + 6).
+// One CTA per tile of TI input pixels: the x/y weight sets of every pixel of the tile are computed
+// once into shared memory, then threads sweep (a, i) with i fastest so that stores are contiguous.
+// Rows m..mpad-1 and columns n..npad-1 are zero-filled (the solver's padding).
+// ------------------------------------------------------------------------------------------------
+template <int TI>
+__global__ void __launch_bounds__(256) k_build_B(const double* __restrict__ px, const double* __restrict__ py,
+                                                 const int* __restrict__ pcode, int n, int npad,
+                                                 const double* __restrict__ tables,
+                                                 const long long* __restrict__ lut_io /* [ncode][n_out] */, int n_out,
+                                                 int ngrid, double dscale, double nc, int n2f, int mpad, double x0out,
+                                                 double y0out, double* __restrict__ B, int ldb, size_t strideB) {
+    extern __shared__ double sm[];
+    double* wx = sm;                               // [TI][n2f][10]
+    double* wy = wx + (size_t)TI * n2f * 10;       // [TI][n2f][10]
+    int* xi = (int*)(wy + (size_t)TI * n2f * 10);  // [TI][n2f]
+    int* yi = xi + TI * n2f;
+    const int i0 = blockIdx.x * TI;
+    for (int t = threadIdx.x; t < TI * n2f * 2; t += blockDim.x) {
+        const int isy = t / (TI * n2f);
+        const int u = t - isy * TI * n2f;
+        const int li = u / n2f, k = u - li * n2f;
+        const int i = i0 + li;
+        double w[10];
+        int vi = 4;
+        bool ok = false;
+        if (i < n) {
+            const double pin = isy ? py[i] : px[i];
+            const double pout = (isy ? y0out : x0out) + (double)k;  // integer output grid (coadd.py:879-882)
+            const double v = __dadd_rn(__dadd_rn(__ddiv_rn(__dadd_rn(pin, -pout), dscale), nc), 6.0);
+            vi = (int)v;
+            if (d5512_on_grid(vi, ngrid)) {
+                d5512_getw(w, v - vi - 0.5);
+                ok = true;
+            } else {
+                vi = 4;
+            }
+        }
+        double* dst = (isy ? wy : wx) + (size_t)u * 10;
+#pragma unroll
+        for (int q = 0; q < 10; q++) dst[q] = ok ? w[q] : 0.0;
+        (isy ? yi : xi)[u] = vi;
+    }
+    __syncthreads();
+    const int m = n2f * n2f;
+    for (int o = 0; o < n_out; o++) {
+        for (int t = threadIdx.x; t < mpad * TI; t += blockDim.x) {
+            const int a = t / TI, li = t - a * TI;
+            const int i = i0 + li;
+            if (i >= npad) continue;
+            double v = 0.0;
+            if (i < n && a < m) {
+                const int iy = a / n2f, ix = a - iy * n2f;
+                const long long off = lut_io[(size_t)pcode[i] * n_out + o];
+                if (off >= 0)
+                    v = d5512_taps(tables + off, ngrid, ngrid, yi[li * n2f + iy], xi[li * n2f + ix],
+                                   wx + (size_t)(li * n2f + ix) * 10, wy + (size_t)(li * n2f + iy) * 10, 0);
+            }
+            B[o * strideB + (size_t)a * ldb + i] = v;
+        }
+    }
+}
+
+// Gather of the selected input pixels of one output stamp (coadd.py:969-977): positions, table codes and
+// the n_inframe float32 layers, in the reference's concatenation order given by idx.  Columns n..npad-1
+// of the layer block are zero-filled (they multiply zero columns of T).
+__global__ void __launch_bounds__(256) k_gather_stamp(const int* __restrict__ idx, int n, int npad,
+                                                      const double* __restrict__ sx, const double* __restrict__ sy,
+                                                      const int* __restrict__ scode, const float* __restrict__ sdata,
+                                                      long src_ld, int n_inframe, double* __restrict__ px,
+                                                      double* __restrict__ py, int* __restrict__ pcode,
+                                                      float* __restrict__ indata, int ldi) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= npad) return;
+    if (k < n) {
+        const int g = idx[k];
+        px[k] = sx[g];
+        py[k] = sy[g];
+        if (scode) pcode[k] = scode[g];
+        for (int f = 0; f < n_inframe; f++) indata[(size_t)f * ldi + k] = sdata[(size_t)f * src_ld + g];
+    } else {
+        for (int f = 0; f < n_inframe; f++) indata[(size_t)f * ldi + k] = 0.0f;
+    }
+}
+
+__global__ void k_getw(double* __restrict__ w, double fh) {
+    double t[10];
+    d5512_getw(t, fh);
+    for (int k = 0; k < 10; k++) w[k] = t[k];
+}
+
+// ---- launchers ---------------------------------------------------------------------------------
+int launch_iD5512C(const double* f, int nlayer, int ngy, int ngx, const double* x, const double* y, long nout,
+                   double* out, cudaStream_t s) {
+    if (nout <= 0) return 0;
+    k_iD5512C<<<(unsigned)((nout + 127) / 128), 128, 0, s>>>(f, nlayer, ngy, ngx, x, y, nout, out);
+    B200_LAUNCH_CHECK();
+    return 0;
+}
+
+int launch_iD5512C_sym(const double* f, int nlayer, int ngy, int ngx, const double* x, const double* y, long nout,
+                       double* out, cudaStream_t s) {
+    if (nout <= 0) return 0;
+    const int sq = (int)sqrt((double)(nout + 1));  // routine.py:214
+    const long nt = (long)sq * sq;
+    if (nt <= 0) return 0;
+    k_iD5512C_sym<<<(unsigned)((nt + 127) / 128), 128, 0, s>>>(f, nlayer, ngy, ngx, x, y, nout, sq, out);
+    B200_LAUNCH_CHECK();
+    return 0;
+}
+
+int launch_gridD5512C(const double* f, int ngy, int ngx, const double* x, const double* y, long npi, int nxo, int nyo,
+                      double* out, cudaStream_t s) {
+    if (npi <= 0 || nxo <= 0 || nyo <= 0) return 0;
+    const size_t smem = sizeof(double) * 10 * ((size_t)nxo + nyo) + sizeof(int) * ((size_t)nxo + nyo);
+    B200_REQUIRE(smem <= 200 * 1024, "gridD5512C: nxo+nyo too large for one CTA's shared memory");
+    if (smem > 48 * 1024)
+        B200_CUDA(cudaFuncSetAttribute(k_gridD5512C, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_gridD5512C<<<(unsigned)npi, 256, smem, s>>>(f, ngy, ngx, x, y, nxo, nyo, out);
+    B200_LAUNCH_CHECK();
+    return 0;
+}
+
+int launch_getw(double* w, double fh, cudaStream_t s) {
+    k_getw<<<1, 1, 0, s>>>(w, fh);
+    B200_LAUNCH_CHECK();
+    return 0;
+}
+
+int launch_gather_stamp(const int* idx, int n, int npad, const double* src_x, const double* src_y, const int* src_code,
+                        const float* src_data, long src_ld, int n_inframe, double* px, double* py, int* pcode,
+                        float* indata, int ldi, cudaStream_t s) {
+    if (npad <= 0) return 0;
+    k_gather_stamp<<<(npad + 255) / 256, 256, 0, s>>>(idx, n, npad, src_x, src_y, src_code, src_data, src_ld,
+                                                      n_inframe, px, py, pcode, indata, ldi);
+    B200_LAUNCH_CHECK();
+    return 0;
+}
+
+int launch_build_A(const double* px, const double* py, const int* pcode, int n, int npad, const double* tables,
+                   const TableRef* lut, int nimg, int ncode, int ngrid, double dscale, double nc, double flat_penalty,
+                   double* A, int lda, double diag_add, cudaStream_t s) {
+    if (npad <= 0) return 0;
+    B200_REQUIRE(npad % 32 == 0 && npad >= n && lda >= npad, "build_A: npad must be a multiple of 32, >= n, <= lda");
+    const long nt = npad / 32;
+    const long ntri = nt * (nt + 1) / 2;
+    k_build_A<<<(unsigned)ntri, 256, 0, s>>>(px, py, pcode, n, npad, tables, lut, nimg, ncode, ngrid, dscale, nc,
+                                             flat_penalty, A, lda, diag_add);
+    B200_LAUNCH_CHECK();
+    return 0;
+}
+
+int launch_build_B(const double* px, const double* py, const int* pcode, int n, int npad, const double* tables,
+                   const long long* lut_io, int n_out, int ngrid, double dscale, double nc, int n2f, int mpad,
+                   double x0out, double y0out, double* B, int ldb, size_t strideB, cudaStream_t s) {
+    if (npad <= 0 || mpad <= 0) return 0;
+    constexpr int TI = 16;
+    B200_REQUIRE(npad >= n && mpad >= n2f * n2f && ldb >= npad, "build_B: padded sizes too small");
+    const size_t smem = (size_t)TI * n2f * 2 * (10 * sizeof(double) + sizeof(int));
+    B200_REQUIRE(smem <= 220 * 1024, "build_B: n2f too large for the shared-memory weight cache");
+    static bool attr_done = false;
+    if (!attr_done) {
+        B200_CUDA(cudaFuncSetAttribute(k_build_B<TI>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+        attr_done = true;
+    }
+    k_build_B<TI><<<(unsigned)((npad + TI - 1) / TI), 256, smem, s>>>(px, py, pcode, n, npad, tables, lut_io, n_out,
+                                                                       ngrid, dscale, nc, n2f, mpad, x0out, y0out, B,
+                                                                       ldb, strideB);
+    B200_LAUNCH_CHECK();
+    return 0;
+}
+
+}  // namespace b200

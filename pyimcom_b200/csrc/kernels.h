@@ -1,0 +1,91 @@
+// Internal launcher declarations shared by the .cu files and capi.cu.
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+#include "../../include/pyimcom_b200.h"
+
+namespace b200 {
+
+// the structs that cross the C ABI are defined once, in include/pyimcom_b200.h
+using TableRef = ::b200_table_ref;
+using SolveSys = ::b200_solve_sys;
+using FinalizeArgs = ::b200_finalize_args;
+
+constexpr int NB = B200_NB;      // Cholesky/TRSM block size == DMMA GEMM tile edge
+constexpr int MAXB = B200_MAXB;  // systems per batched launch (descriptors travel as kernel parameters)
+
+struct SolveBatch {
+    SolveSys s[MAXB];
+};
+
+struct DiagNodes {
+    double v[16];
+};
+
+// interp.cu
+int launch_getw(double* w, double fh, cudaStream_t s);
+int launch_iD5512C(const double* f, int nlayer, int ngy, int ngx, const double* x, const double* y, long nout,
+                   double* out, cudaStream_t s);
+int launch_iD5512C_sym(const double* f, int nlayer, int ngy, int ngx, const double* x, const double* y, long nout,
+                       double* out, cudaStream_t s);
+int launch_gridD5512C(const double* f, int ngy, int ngx, const double* x, const double* y, long npi, int nxo, int nyo,
+                      double* out, cudaStream_t s);
+int launch_gather_stamp(const int* idx, int n, int npad, const double* src_x, const double* src_y, const int* src_code,
+                        const float* src_data, long src_ld, int n_inframe, double* px, double* py, int* pcode,
+                        float* indata, int ldi, cudaStream_t s);
+int launch_build_A(const double* px, const double* py, const int* pcode, int n, int npad, const double* tables,
+                   const TableRef* lut, int nimg, int ncode, int ngrid, double dscale, double nc, double flat_penalty,
+                   double* A, int lda, double diag_add, cudaStream_t s);
+int launch_build_B(const double* px, const double* py, const int* pcode, int n, int npad, const double* tables,
+                   const long long* lut_io, int n_out, int ngrid, double dscale, double nc, int n2f, int mpad,
+                   double x0out, double y0out, double* B, int ldb, size_t strideB, cudaStream_t s);
+
+// linalg.cu
+int launch_chol_solve(const SolveSys* h_sys, int nsys, int do_factor, int do_solve, cudaStream_t s);
+int launch_gemm_nt(const double* A, int lda, const double* B, int ldb, double* C, int ldc, int M, int N, int K,
+                   int accumulate, cudaStream_t s);
+int launch_pad_system(double* W, int ldw, int n, int npad, const double* A, int lda, const double* incs, int ninc,
+                      cudaStream_t s);
+int launch_transpose(const double* A, int lda, double* At, int ldat, int rows, int cols, cudaStream_t s);
+
+// kappa.cu
+int launch_lakernel1(const double* lam, const double* mPhalf, int ldp, int m, int n, double C, double targetleak,
+                     double kCmin, double kCmax, int nbis, double* kappa, double* Sigma, double* UC, double* T, int ldt,
+                     double smax, cudaStream_t s);
+int launch_eigen_single(const double* lam, const double* mPhalf, int ldp, int m, int n, double C, double kappa,
+                        double* Sigma, double* UC, double* T, int ldt, cudaStream_t s);
+int launch_lsolve_sps(int N, double* A, double* x, const double* b, double* work, cudaStream_t s);
+int launch_build_reduced_T(const double* Nflat, const double* Dflat, const double* Eflat, const double* kappa, int nv,
+                           int m, double ucmin, double smax, double* out_kappa, double* out_Sigma, double* out_UC,
+                           double* out_w, int* out_iv, int* out_branch, cudaStream_t s);
+int launch_node_stats(const double* mB, int ldb, const double* Tpi, int ldt, size_t strideT, int nv, int m, int n,
+                      const double* kappa_nodes, double Cnorm, double* Dp, double* Npq, double* Epq, double* DpC,
+                      double* EpqC, const double* Epq_in, cudaStream_t s);
+int launch_rowdot(const double* X, int ldx, const double* Y, int ldy, int m, int n, double* out, int ostride,
+                  cudaStream_t s);
+
+int launch_single_kappa_maps(const double* D, const double* N, const double* E, int m, double kappa, double C,
+                             double* kappa_out, double* Sigma_out, double* UC_out, cudaStream_t s);
+int launch_scale(const double* in, double scale, int m, double* out, cudaStream_t s);
+
+// iter.cu
+int launch_iter_cg(const double* AA, int lda, double diag_add, const double* mB, int ldb, int m, int n,
+                   const double* inx, const double* iny, const double* outx, const double* outy, double rho_acc,
+                   double rtol, int maxiter, double* Ti, int ldt, int* niter, int* nsel, cudaStream_t s);
+
+// eigen.cu
+int launch_jacobi_eigh(double* A, int lda, int n, double* Vt, int ldv, double* lam, int max_sweeps, int* sweeps_done,
+                       cudaStream_t s);
+
+// coadd.cu
+int launch_finalize(const FinalizeArgs& a, cudaStream_t s);
+int launch_stamp_maps(const double* kappa, const double* Sigma, const double* UC, int m, int n2f, int fade,
+                      int clamp_iter, const double* fade_w, float* kappa32, float* Sigma32, float* UC32,
+                      const double* Tsum_image, int n_img, int n2, double* Tsum_stamp, double* Tsum_inpix, double* Neff,
+                      cudaStream_t s);
+int launch_accumulate(const void* src, int src_is_f64, int nlayer, int n2f, float* dst, int side, int y0, int x0,
+                      cudaStream_t s);
+
+}  // namespace b200

@@ -1,0 +1,506 @@
+// FP64 dense linear algebra for the CholKernel path: a DMMA (mma.sync m8n8k4 f64)
+// tile GEMM, a shared-memory Cholesky + triangular inverse of one 128x128 diagonal block, and the
+// batched right-looking driver that factors  W = A + kappa*I = L L^T  and solves
+// Ti (L L^T) = mBhalf  for all m right-hand-side rows.
+//
+// Replaces scipy.linalg.cholesky / cho_solve at lakernel.py:263, 276, 304, 358.
+//
+// Data layout (all row-major, leading dimensions and padded sizes multiples of NB = 128):
+//   W (npad, ldw)  in: A + kappa*I (lower triangle read, identity in the padding)
+//                  out: L in the lower triangle (diagonal blocks included), L^T in the strictly upper
+//                       block triangle (written by the panel step so that every product below is "NT").
+//   X (mpad, ldx)  in: mBhalf rows; out: Ti rows.
+//   Dinv (2*nb, 128, 128): inv(L_kk) for k < nb, then inv(L_kk)^T.
+//
+// With rows as right-hand sides the solve is   Z = X L^-T  (forward, fused into the factorisation:
+// the X rows are simply extra panel rows below the matrix) followed by  Ti = Z L^-1  (backward).
+// Every product is  C (+)= A[.,K] * B[.,K]^T  with both operands K-contiguous, so one tile kernel
+// (128x128x16 stages, 4-stage cp.async ring, 8 warps of 64x32, DMMA.8x8x4) serves all phases.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace b200 {
+
+namespace {
+
+constexpr int KT = 16;           // K extent of one pipeline stage
+constexpr int LDSM = KT + 4;     // smem row stride in doubles: 20 = 4 mod 16 -> conflict-free fragment loads
+constexpr int STAGES = 4;
+constexpr int GT = 256;          // threads per GEMM CTA
+constexpr int STAGE_DOUBLES = 2 * NB * LDSM;
+constexpr size_t GEMM_SMEM = (size_t)STAGES * STAGE_DOUBLES * sizeof(double);  // 163840 B
+
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+
+__device__ __forceinline__ void cp_async16(double* smem, const double* gmem) {
+    unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+enum TileMode { TILE_ASSIGN = 0, TILE_SUB = 1, TILE_ADD = 2 };
+
+// One 128x128 output tile:  C = op(C, A[128,K] * B[128,K]^T).
+//   TILE_ASSIGN: C = A B^T       (C may alias A: every A chunk is in shared memory before C is written)
+//   TILE_SUB   : C = C - A B^T   (accumulators start at -C, result is the negated accumulator)
+//   TILE_ADD   : C = C + A B^T
+// Ct != nullptr additionally stores the tile transposed: Ct[c * ldct + r] = C[r][c].
+template <int MODE>
+__device__ __forceinline__ void gemm_tile_nt(const double* A, int lda, const double* B,
+                                             int ldb, double* C, int ldc, int K, double* Ct, int ldct,
+                                             double* smem) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int wm = warp >> 2, wn = warp & 3;  // 2 x 4 warps, warp tile 64 x 32
+    const int g = lane >> 2, q = lane & 3;
+
+    double acc[8][4][2];
+    if (MODE == TILE_ASSIGN) {
+#pragma unroll
+        for (int mi = 0; mi < 8; mi++)
+#pragma unroll
+            for (int ni = 0; ni < 4; ni++) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
+    }
+
+    const int nk = K / KT;
+    // loader mapping: 1024 16-byte chunks per operand per stage; thread handles chunks tid + 256*r
+    auto load_stage = [&](int slot, int kt) {
+        double* As = smem + (size_t)slot * STAGE_DOUBLES;
+        double* Bs = As + NB * LDSM;
+        const int k0 = kt * KT;
+#pragma unroll
+        for (int r = 0; r < 4; r++) {
+            const int c = tid + GT * r;
+            const int row = c >> 3, kc = (c & 7) * 2;
+            cp_async16(As + row * LDSM + kc, A + (size_t)row * lda + k0 + kc);
+            cp_async16(Bs + row * LDSM + kc, B + (size_t)row * ldb + k0 + kc);
+        }
+    };
+#pragma unroll
+    for (int s = 0; s < STAGES - 1; s++) {
+        if (s < nk) load_stage(s, s);
+        cp_async_commit();
+    }
+    if (MODE != TILE_ASSIGN) {  // overlaps with the pipeline fill
+#pragma unroll
+        for (int mi = 0; mi < 8; mi++)
+#pragma unroll
+            for (int ni = 0; ni < 4; ni++) {
+                const double2 v = *reinterpret_cast<const double2*>(
+                    C + (size_t)(wm * 64 + mi * 8 + g) * ldc + wn * 32 + ni * 8 + q * 2);
+                acc[mi][ni][0] = (MODE == TILE_SUB) ? -v.x : v.x;
+                acc[mi][ni][1] = (MODE == TILE_SUB) ? -v.y : v.y;
+            }
+    }
+    for (int kt = 0; kt < nk; kt++) {
+        cp_async_wait<STAGES - 2>();
+        __syncthreads();
+        if (kt + STAGES - 1 < nk) load_stage((kt + STAGES - 1) % STAGES, kt + STAGES - 1);
+        cp_async_commit();
+        const double* As = smem + (size_t)(kt % STAGES) * STAGE_DOUBLES + (wm * 64 + g) * LDSM + q;
+        const double* Bs = smem + (size_t)(kt % STAGES) * STAGE_DOUBLES + NB * LDSM + (wn * 32 + g) * LDSM + q;
+#pragma unroll
+        for (int kk = 0; kk < KT / 4; kk++) {
+            double a[8], b[4];
+#pragma unroll
+            for (int mi = 0; mi < 8; mi++) a[mi] = As[mi * 8 * LDSM + kk * 4];
+#pragma unroll
+            for (int ni = 0; ni < 4; ni++) b[ni] = Bs[ni * 8 * LDSM + kk * 4];
+#pragma unroll
+            for (int mi = 0; mi < 8; mi++)
+#pragma unroll
+                for (int ni = 0; ni < 4; ni++) dmma884(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
+        }
+    }
+    cp_async_wait<0>();
+#pragma unroll
+    for (int mi = 0; mi < 8; mi++)
+#pragma unroll
+        for (int ni = 0; ni < 4; ni++) {
+            const int r = wm * 64 + mi * 8 + g, c = wn * 32 + ni * 8 + q * 2;
+            double2 v;
+            v.x = (MODE == TILE_SUB) ? -acc[mi][ni][0] : acc[mi][ni][0];
+            v.y = (MODE == TILE_SUB) ? -acc[mi][ni][1] : acc[mi][ni][1];
+            *reinterpret_cast<double2*>(C + (size_t)r * ldc + c) = v;
+            if (Ct) {
+                Ct[(size_t)c * ldct + r] = v.x;
+                Ct[(size_t)(c + 1) * ldct + r] = v.y;
+            }
+        }
+}
+
+// ---- generic C (+)= A B^T over a grid of tiles (also the public DGEMM of the library) ----------
+template <int MODE>
+__global__ void __launch_bounds__(GT, 1) k_gemm_nt(const double* __restrict__ A, int lda,
+                                                   const double* __restrict__ B, int ldb, double* C, int ldc, int K) {
+    extern __shared__ __align__(16) double smem[];
+    const int tn = blockIdx.x, tm = blockIdx.y;
+    gemm_tile_nt<MODE>(A + (size_t)tm * NB * lda, lda, B + (size_t)tn * NB * ldb, ldb,
+                       C + (size_t)tm * NB * ldc + (size_t)tn * NB, ldc, K, nullptr, 0, smem);
+}
+
+// ---- factorisation phases ----------------------------------------------------------------------
+// Panel step k: rows below the diagonal block (and all X rows) times inv(L_kk)^T; the W part is also
+// stored transposed into the upper block triangle.
+__global__ void __launch_bounds__(GT, 1) k_chol_panel(SolveBatch bt, int k) {
+    extern __shared__ __align__(16) double smem[];
+    const SolveSys& s = bt.s[blockIdx.y];
+    const int nb = s.npad / NB, mb = s.mpad / NB;
+    const int nrow = nb - 1 - k;
+    const int t = blockIdx.x;
+    if (k >= nb || t >= nrow + mb) return;
+    const double* Dk = s.Dinv + (size_t)k * NB * NB;
+    if (t < nrow) {
+        const int i = k + 1 + t;
+        double* Cp = s.W + (size_t)i * NB * s.ldw + (size_t)k * NB;
+        gemm_tile_nt<TILE_ASSIGN>(Cp, s.ldw, Dk, NB, Cp, s.ldw, NB, s.W + (size_t)k * NB * s.ldw + (size_t)i * NB,
+                                  s.ldw, smem);
+    } else {
+        double* Cp = s.X + (size_t)(t - nrow) * NB * s.ldx + (size_t)k * NB;
+        gemm_tile_nt<TILE_ASSIGN>(Cp, s.ldx, Dk, NB, Cp, s.ldx, NB, nullptr, 0, smem);
+    }
+}
+
+// Trailing update after panel k:  W[i][j] -= W[i][k] W[j][k]^T (k < j <= i)  and  X[t][j] -= X[t][k] W[j][k]^T.
+__global__ void __launch_bounds__(GT, 1) k_chol_update(SolveBatch bt, int k) {
+    extern __shared__ __align__(16) double smem[];
+    const SolveSys& s = bt.s[blockIdx.z];
+    const int nb = s.npad / NB, mb = s.mpad / NB;
+    const int nrow = nb - 1 - k;
+    const int jj = blockIdx.x, t = blockIdx.y;
+    if (k >= nb || jj >= nrow || t >= nrow + mb) return;
+    const int j = k + 1 + jj;
+    const double* Bp = s.W + (size_t)j * NB * s.ldw + (size_t)k * NB;
+    if (t < nrow) {
+        const int i = k + 1 + t;
+        if (j > i) return;
+        gemm_tile_nt<TILE_SUB>(s.W + (size_t)i * NB * s.ldw + (size_t)k * NB, s.ldw, Bp, s.ldw,
+                               s.W + (size_t)i * NB * s.ldw + (size_t)j * NB, s.ldw, NB, nullptr, 0, smem);
+    } else {
+        const int r = t - nrow;
+        gemm_tile_nt<TILE_SUB>(s.X + (size_t)r * NB * s.ldx + (size_t)k * NB, s.ldx, Bp, s.ldw,
+                               s.X + (size_t)r * NB * s.ldx + (size_t)j * NB, s.ldx, NB, nullptr, 0, smem);
+    }
+}
+
+// Backward step k, part 1:  X[t][k] = X[t][k] inv(L_kk)   (B operand = inv(L_kk)^T)
+__global__ void __launch_bounds__(GT, 1) k_back_diag(SolveBatch bt, int kfromtop) {
+    extern __shared__ __align__(16) double smem[];
+    const SolveSys& s = bt.s[blockIdx.y];
+    const int nb = s.npad / NB, mb = s.mpad / NB;
+    const int k = nb - 1 - kfromtop;
+    if (k < 0 || (int)blockIdx.x >= mb) return;
+    double* Cp = s.X + (size_t)blockIdx.x * NB * s.ldx + (size_t)k * NB;
+    gemm_tile_nt<TILE_ASSIGN>(Cp, s.ldx, s.Dinv + (size_t)(nb + k) * NB * NB, NB, Cp, s.ldx, NB, nullptr, 0, smem);
+}
+
+// Backward step k, part 2:  X[t][j] -= X[t][k] L[k][j]  (j < k); L[k][j]^T lives at W[j][k] (upper triangle)
+__global__ void __launch_bounds__(GT, 1) k_back_update(SolveBatch bt, int kfromtop) {
+    extern __shared__ __align__(16) double smem[];
+    const SolveSys& s = bt.s[blockIdx.z];
+    const int nb = s.npad / NB, mb = s.mpad / NB;
+    const int k = nb - 1 - kfromtop;
+    const int j = blockIdx.x, t = blockIdx.y;
+    if (k < 0 || j >= k || t >= mb) return;
+    gemm_tile_nt<TILE_SUB>(s.X + (size_t)t * NB * s.ldx + (size_t)k * NB, s.ldx,
+                           s.W + (size_t)j * NB * s.ldw + (size_t)k * NB, s.ldw,
+                           s.X + (size_t)t * NB * s.ldx + (size_t)j * NB, s.ldx, NB, nullptr, 0, smem);
+}
+
+// ---- 128x128 diagonal block: Cholesky in shared memory + explicit triangular inverse -------------
+// One CTA (256 threads) per system.  info follows LAPACK dpotrf: 0, or 1 + index of the first
+// non-positive (or NaN) pivot; the block is still completed with that pivot replaced by 1 so that
+// everything stays finite -- the host checks info and takes the repair branch (lakernel.py:262-279).
+//
+// Factorisation: right-looking over 8-column panels.  Every thread factors the 8x8 diagonal block of
+// the panel redundantly in registers (no barrier inside a panel), threads owning a row below it
+// forward-substitute their 8 entries, then all threads apply the rank-8 update to the trailing block
+// in 4x4 micro-tiles.  Two barriers per panel.
+// Inverse: thread pair per column, x_c = L^-1 e_c by forward substitution; x_c[r] is parked in the
+// unused upper triangle (S[c][r+1]) so one 128x129 array holds both L and L^-1.
+constexpr int PD = NB + 1;
+constexpr size_t POTRF_SMEM = (size_t)NB * PD * sizeof(double);
+
+__global__ void __launch_bounds__(256, 1) k_potrf_diag(SolveBatch bt, int k) {
+    extern __shared__ __align__(16) double S[];  // [128][129]
+    const SolveSys& s = bt.s[blockIdx.x];
+    const int nb = s.npad / NB;
+    if (k >= nb) return;
+    const int tid = threadIdx.x;
+    double* Wkk = s.W + (size_t)k * NB * s.ldw + (size_t)k * NB;
+    for (int e = tid; e < NB * NB; e += 256) {
+        const int r = e >> 7, c = e & 127;
+        S[r * PD + c] = (c <= r) ? Wkk[(size_t)r * s.ldw + c] : 0.0;
+    }
+    __syncthreads();
+    int bad = 0;
+    for (int j0 = 0; j0 < NB; j0 += 8) {
+        double D[8][8], rinv[8];
+#pragma unroll
+        for (int a = 0; a < 8; a++)
+#pragma unroll
+            for (int b = 0; b <= a; b++) D[a][b] = S[(j0 + a) * PD + j0 + b];
+#pragma unroll
+        for (int c = 0; c < 8; c++) {
+            double d = D[c][c];
+            if (!(d > 0.0)) {
+                if (!bad) bad = k * NB + j0 + c + 1;
+                d = 1.0;
+            }
+            const double l = sqrt(d);
+            D[c][c] = l;
+            rinv[c] = 1.0 / l;
+#pragma unroll
+            for (int a = c + 1; a < 8; a++) D[a][c] *= rinv[c];
+#pragma unroll
+            for (int a = c + 1; a < 8; a++)
+#pragma unroll
+                for (int b = c + 1; b <= a; b++) D[a][b] -= D[a][c] * D[b][c];
+        }
+        if (tid < NB) {
+            const int r = tid;
+            if (r >= j0 + 8) {
+                double row[8];
+#pragma unroll
+                for (int c = 0; c < 8; c++) row[c] = S[r * PD + j0 + c];
+#pragma unroll
+                for (int c = 0; c < 8; c++) {
+                    double v = row[c];
+#pragma unroll
+                    for (int q = 0; q < c; q++) v -= row[q] * D[c][q];
+                    row[c] = v * rinv[c];
+                }
+#pragma unroll
+                for (int c = 0; c < 8; c++) S[r * PD + j0 + c] = row[c];
+            } else if (r >= j0) {
+#pragma unroll
+                for (int a = 0; a < 8; a++)
+                    if (a == r - j0) {
+#pragma unroll
+                        for (int b = 0; b <= a; b++) S[r * PD + j0 + b] = D[a][b];
+                    }
+            }
+        }
+        __syncthreads();
+        const int T0 = j0 + 8;
+        const int nt4 = (NB - T0) >> 2;
+        const int cnt = nt4 * (nt4 + 1) / 2;
+        for (int t = tid; t < cnt; t += 256) {
+            int bi = (int)((sqrtf(8.0f * (float)t + 1.0f) - 1.0f) * 0.5f);
+            while (bi * (bi + 1) / 2 > t) bi--;
+            while ((bi + 1) * (bi + 2) / 2 <= t) bi++;
+            const int bj = t - bi * (bi + 1) / 2;
+            const double* pa = S + (T0 + 4 * bi) * PD + j0;
+            const double* pb = S + (T0 + 4 * bj) * PD + j0;
+            double* pc = S + (T0 + 4 * bi) * PD + T0 + 4 * bj;
+            double c4[4][4];
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+#pragma unroll
+                for (int j = 0; j < 4; j++) c4[i][j] = pc[i * PD + j];
+#pragma unroll
+            for (int q = 0; q < 8; q++) {
+                double av[4], bv[4];
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    av[i] = pa[i * PD + q];
+                    bv[i] = pb[i * PD + q];
+                }
+#pragma unroll
+                for (int i = 0; i < 4; i++)
+#pragma unroll
+                    for (int j = 0; j < 4; j++) c4[i][j] -= av[i] * bv[j];
+            }
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+#pragma unroll
+                for (int j = 0; j < 4; j++) pc[i * PD + j] = c4[i][j];
+        }
+        __syncthreads();
+    }
+    if (tid == 0 && bad && *s.info == 0) *s.info = bad;
+    // L back to global (lower triangle of the diagonal block)
+    for (int e = tid; e < NB * NB; e += 256) {
+        const int r = e >> 7, c = e & 127;
+        if (c <= r) Wkk[(size_t)r * s.ldw + c] = S[r * PD + c];
+    }
+    // inverse: columns c = tid/2, the two threads of a pair split the dot product over q
+    {
+        const int c = tid >> 1, h = tid & 1;
+        double* xc = S + c * PD + 1;  // xc[r] = (L^-1)[r][c], r >= c
+        for (int r = 0; r < NB; r++) {
+            if (r >= c) {
+                const double* Lr = S + r * PD;
+                double s0 = 0.0, s1 = 0.0;
+                int q = c + h;
+                for (; q + 2 < r; q += 4) {
+                    s0 += Lr[q] * xc[q];
+                    s1 += Lr[q + 2] * xc[q + 2];
+                }
+                if (q < r) s0 += Lr[q] * xc[q];
+                double sum = s0 + s1;
+                sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+                const double x = ((r == c ? 1.0 : 0.0) - sum) / Lr[r];
+                if (h == 0) xc[r] = x;
+            } else {
+                (void)__shfl_xor_sync(0xffffffffu, 0.0, 1);
+            }
+            __syncwarp();
+        }
+    }
+    __syncthreads();
+    double* Di = s.Dinv + (size_t)k * NB * NB;
+    double* Dt = s.Dinv + (size_t)(nb + k) * NB * NB;
+    for (int e = tid; e < NB * NB; e += 256) {
+        const int r = e >> 7, c = e & 127;
+        Di[e] = (c <= r) ? S[c * PD + r + 1] : 0.0;  // inv(L)[r][c]
+        Dt[e] = (r <= c) ? S[r * PD + c + 1] : 0.0;  // inv(L)^T[r][c] = inv(L)[c][r]
+    }
+}
+
+// W <- A (n x n, lda) + running sum of diagonal increments, identity in the padding (lakernel.py:295-299, 356)
+struct DiagIncs {
+    double v[16];
+    int n;
+};
+__global__ void k_pad_system(double* __restrict__ W, int ldw, int n, int npad, const double* __restrict__ A, int lda,
+                             DiagIncs incs) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x, r = blockIdx.y;
+    if (c >= npad) return;
+    double v;
+    if (r < n && c < n) {
+        v = A[(size_t)r * lda + c];
+        if (r == c)
+            for (int q = 0; q < incs.n; q++) v += incs.v[q];
+    } else {
+        v = (r == c) ? 1.0 : 0.0;
+    }
+    W[(size_t)r * ldw + c] = v;
+}
+
+__global__ void k_transpose(const double* __restrict__ A, int lda, double* __restrict__ At, int ldat, int rows,
+                            int cols) {
+    __shared__ double tile[32][33];
+    const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+    for (int i = threadIdx.y; i < 32; i += 8) {
+        const int r = r0 + i, c = c0 + threadIdx.x;
+        tile[i][threadIdx.x] = (r < rows && c < cols) ? A[(size_t)r * lda + c] : 0.0;
+    }
+    __syncthreads();
+    for (int i = threadIdx.y; i < 32; i += 8) {
+        const int c = c0 + i, r = r0 + threadIdx.x;
+        if (c < cols && r < rows) At[(size_t)c * ldat + r] = tile[threadIdx.x][i];
+    }
+}
+
+bool g_attr_done = false;
+int gemm_attrs() {
+    if (g_attr_done) return 0;
+    B200_CUDA(cudaFuncSetAttribute(k_gemm_nt<TILE_ASSIGN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM));
+    B200_CUDA(cudaFuncSetAttribute(k_gemm_nt<TILE_SUB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM));
+    B200_CUDA(cudaFuncSetAttribute(k_gemm_nt<TILE_ADD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM));
+    B200_CUDA(cudaFuncSetAttribute(k_chol_panel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM));
+    B200_CUDA(cudaFuncSetAttribute(k_chol_update, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM));
+    B200_CUDA(cudaFuncSetAttribute(k_back_diag, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM));
+    B200_CUDA(cudaFuncSetAttribute(k_back_update, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM));
+    B200_CUDA(cudaFuncSetAttribute(k_potrf_diag, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)POTRF_SMEM));
+    g_attr_done = true;
+    return 0;
+}
+
+}  // namespace
+
+// ---- launchers ---------------------------------------------------------------------------------
+int launch_chol_solve(const SolveSys* h_sys, int nsys, int do_factor, int do_solve, cudaStream_t st) {
+    if (nsys <= 0) return 0;
+    B200_REQUIRE(nsys <= MAXB, "at most MAXB systems per batched call");
+    if (int rc = gemm_attrs()) return rc;
+    SolveBatch bt;
+    int nbmax = 0, mbmax = 0;
+    for (int i = 0; i < nsys; i++) {
+        bt.s[i] = h_sys[i];
+        if (!do_solve) bt.s[i].mpad = 0;
+        const SolveSys& s = bt.s[i];
+        B200_REQUIRE(s.npad > 0 && s.npad % NB == 0 && s.mpad % NB == 0 && s.ldw % 2 == 0 && s.ldx % 2 == 0 &&
+                         s.ldw >= s.npad && (s.mpad == 0 || s.ldx >= s.npad),
+                     "padded sizes must be multiples of 128");
+        nbmax = s.npad / NB > nbmax ? s.npad / NB : nbmax;
+        mbmax = s.mpad / NB > mbmax ? s.mpad / NB : mbmax;
+    }
+    for (int i = nsys; i < MAXB; i++) bt.s[i] = bt.s[0];
+    if (do_factor) {
+        for (int k = 0; k < nbmax; k++) {
+            k_potrf_diag<<<nsys, 256, POTRF_SMEM, st>>>(bt, k);
+            B200_LAUNCHED(1);
+            const int nrow = nbmax - 1 - k;
+            if (nrow + mbmax > 0) {
+                k_chol_panel<<<dim3(nrow + mbmax, nsys), GT, GEMM_SMEM, st>>>(bt, k);
+                B200_LAUNCHED(1);
+            }
+            if (nrow > 0) {
+                k_chol_update<<<dim3(nrow, nrow + mbmax, nsys), GT, GEMM_SMEM, st>>>(bt, k);
+                B200_LAUNCHED(1);
+            }
+        }
+        B200_CUDA(cudaGetLastError());
+    }
+    if (do_solve && mbmax > 0) {
+        for (int kk = 0; kk < nbmax; kk++) {
+            k_back_diag<<<dim3(mbmax, nsys), GT, GEMM_SMEM, st>>>(bt, kk);
+            B200_LAUNCHED(1);
+            const int kmax = nbmax - 1 - kk;
+            if (kmax > 0) {
+                k_back_update<<<dim3(kmax, mbmax, nsys), GT, GEMM_SMEM, st>>>(bt, kk);
+                B200_LAUNCHED(1);
+            }
+        }
+        B200_CUDA(cudaGetLastError());
+    }
+    return 0;
+}
+
+// C (M x N) = [C +/-] A (M x K) * B (N x K)^T ; M, N multiples of 128, K multiple of 16.
+// accumulate: 0 assign, 1 add, -1 subtract.
+int launch_gemm_nt(const double* A, int lda, const double* B, int ldb, double* C, int ldc, int M, int N, int K,
+                   int accumulate, cudaStream_t st) {
+    if (M <= 0 || N <= 0) return 0;
+    B200_REQUIRE(M % NB == 0 && N % NB == 0 && K % KT == 0 && K > 0 && lda % 2 == 0 && ldb % 2 == 0 && ldc % 2 == 0,
+                 "gemm_nt wants M,N multiples of 128, K multiple of 16, even leading dimensions");
+    if (int rc = gemm_attrs()) return rc;
+    dim3 grid(N / NB, M / NB);
+    if (accumulate == 0)
+        k_gemm_nt<TILE_ASSIGN><<<grid, GT, GEMM_SMEM, st>>>(A, lda, B, ldb, C, ldc, K);
+    else if (accumulate > 0)
+        k_gemm_nt<TILE_ADD><<<grid, GT, GEMM_SMEM, st>>>(A, lda, B, ldb, C, ldc, K);
+    else
+        k_gemm_nt<TILE_SUB><<<grid, GT, GEMM_SMEM, st>>>(A, lda, B, ldb, C, ldc, K);
+    B200_LAUNCH_CHECK();
+    return 0;
+}
+
+int launch_pad_system(double* W, int ldw, int n, int npad, const double* A, int lda, const double* incs, int ninc,
+                      cudaStream_t st) {
+    B200_REQUIRE(ninc <= 16, "at most 16 diagonal increments");
+    DiagIncs di;
+    di.n = ninc;
+    for (int i = 0; i < 16; i++) di.v[i] = i < ninc ? incs[i] : 0.0;
+    k_pad_system<<<dim3((npad + 255) / 256, npad), 256, 0, st>>>(W, ldw, n, npad, A, lda, di);
+    B200_LAUNCH_CHECK();
+    return 0;
+}
+
+int launch_transpose(const double* A, int lda, double* At, int ldat, int rows, int cols, cudaStream_t st) {
+    if (rows <= 0 || cols <= 0) return 0;
+    k_transpose<<<dim3((cols + 31) / 32, (rows + 31) / 32), dim3(32, 8), 0, st>>>(A, lda, At, ldat, rows, cols);
+    B200_LAUNCH_CHECK();
+    return 0;
+}
+
+}  // namespace b200

@@ -181,8 +181,8 @@ class PSFTables:
         """idx_blk2grp (psfutil.py:821-829)."""
         return self.grp_imgs[G].index(k_img)
 
-    def table_ii(self, Ga, ka, Gb, kb):
-        """(table, flip) giving psf(ka@Ga) (*) psf(kb@Gb) as a function of (p_a - p_b).
+    def table_ii_ref(self, Ga, ka, Gb, kb):
+        """(table set, index into its leading axes, flip) for psf(ka@Ga) (*) psf(kb@Gb) as a function of (p_a - p_b).
 
         Same group: triangle entry, flipped in both axes when group index a > b (psfutil.py:1652-1665).
         Different groups: dense table of the ordered pair; the reversed order is the flipped table
@@ -192,12 +192,17 @@ class PSFTables:
             t = self.get_self(Ga)
             n_psf = len(self.grp_imgs[Ga])
             a, b = self.grp_index(Ga, ka), self.grp_index(Ga, kb)
-            return (t[tri_index(n_psf, a, b)], False) if a <= b else (t[tri_index(n_psf, b, a)], True)
+            return (t, (tri_index(n_psf, a, b),), False) if a <= b else (t, (tri_index(n_psf, b, a),), True)
         if Ga < Gb:
             t = self.get_cross(Ga, Gb)
-            return t[self.grp_index(Ga, ka), self.grp_index(Gb, kb)], False
+            return t, (self.grp_index(Ga, ka), self.grp_index(Gb, kb)), False
         t = self.get_cross(Gb, Ga)
-        return t[self.grp_index(Gb, kb), self.grp_index(Ga, ka)], True
+        return t, (self.grp_index(Gb, kb), self.grp_index(Ga, ka)), True
+
+    def table_ii(self, Ga, ka, Gb, kb):
+        """(table, flip): the 2-D table selected by table_ii_ref."""
+        t, idx, flip = self.table_ii_ref(Ga, ka, Gb, kb)
+        return t[idx], flip
 
 
 def anchor(ji):

@@ -13,6 +13,15 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
 
 
+def pytest_sessionstart(session):
+    """Make sure the native pieces exist (both are git-ignored build products; nvcc cross-compiles without a GPU)."""
+    from oracle import build as ob
+    from pyimcom_b200 import build as pb
+
+    pb.build()
+    ob.build()
+
+
 @pytest.fixture(scope="session")
 def golden_dir():
     return os.path.join(ROOT, "tests", "golden")
