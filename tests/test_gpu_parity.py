@@ -131,7 +131,14 @@ def test_lakernel1_and_lsolve(gr):
     assert np.abs(kappa - gr["lk1_kappa"]).max() < 1e-12
     assert np.abs(Sigma - gr["lk1_Sigma"]).max() < 1e-7
     assert np.abs(UC - gr["lk1_UC"]).max() < 1e-14
-    assert np.abs(T[::25, ::33] - gr["lk1_T_sub"]).max() < 1e-8
+    # T is expressed in the eigenbasis, whose gauge (signs, rotations inside degenerate subspaces) depends on the
+    # host's LAPACK build: compare it with the oracle on the SAME (lam, Q), and with the reference through the
+    # gauge-invariant product T @ Q^T (lakernel.py:223)
+    rk, rS, rU, rT = np.zeros(m), np.zeros(m), np.zeros(m), np.zeros((m, n))
+    R.lakernel1(lam, Q, mPhalf, Cn, 1e-8, 1e-16, 1e16, 53, rk, rS, rU, rT, 0.5)
+    assert np.array_equal(kappa, rk)  # P-discrete: same 53 bisection branches
+    assert np.abs(T - rT).max() < 1e-8 * np.abs(rT).max()
+    assert np.abs((T @ Q.T)[::25, ::33] - gr["lk1_TQt_sub"]).max() < 1e-8
     # float32 outputs, as lakernel.py:216-218 passes them
     k32, S32, U32 = (np.zeros(m, dtype=np.float32) for _ in range(3))
     G.lakernel1(lam, Q, mPhalf, Cn, 1e-8, 1e-16, 1e16, 53, k32, S32, U32, T, 0.5)
@@ -217,10 +224,10 @@ def test_eigh_device():
     ds = GL.upload_system(A, np.zeros((1, 4, n)), [1.0], 2)
     lam, Vt, sweeps = GL.eigh_device(ds.A.clone(), n)
     lam, V = lam[:n].cpu().numpy(), Vt[:n, :n].cpu().numpy().T
-    assert 0 < sweeps < 30
     assert np.abs(np.sort(lam) - np.linalg.eigvalsh(A)).max() < 1e-13
     assert np.abs(V.T @ V - np.eye(n)).max() < 1e-12
     assert np.abs(A @ V - V * lam).max() < 1e-13
+    assert 0 < sweeps < 25
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -251,7 +258,7 @@ def test_la_kernels(name, golden_dir):
         for j in range(16):
             assert (UC[j] < 1e-4 and 2e-3 < kap[j] < 4e-3) if j % 5 == 0 else (0.05 < UC[j] < 0.2 and 2e-4 < kap[j] < 4e-4)
     if kern == "IterKernel":
-        assert np.array_equal(K.f64[0]["niter"], KO.f64[0]["niter"])  # P-discrete
+        assert np.array_equal(K.f64[0]["niter"].ravel(), KO.f64[0]["niter"].ravel())  # P-discrete
 
 
 def test_incr_repair():
@@ -313,7 +320,7 @@ def test_block_vs_oracle_and_reference(name, golden_dir):
             assert np.array_equal(s.extras[0]["iv"], k.f64[0]["iv"])  # P-discrete
             assert np.array_equal(s.extras[0]["branch"], k.f64[0]["branch"])
         if kern == "Iterative":
-            assert np.array_equal(s.extras[0]["niter"], k.f64[0]["niter"])  # P-discrete: CG iteration counts
+            assert np.array_equal(s.extras[0]["niter"].ravel(), k.f64[0]["niter"].ravel())  # P-discrete: CG iterations
         o.post_kernel()
         o.perform_coaddition()
         tol = P32

@@ -70,7 +70,8 @@ def test_lakernel1_and_lsolve(gr):
     assert np.abs(kappa - gr["lk1_kappa"]).max() < 1e-12
     assert np.abs(Sigma - gr["lk1_Sigma"]).max() < 1e-7
     assert np.abs(UC - gr["lk1_UC"]).max() < 1e-14
-    assert np.abs(T[::25, ::33] - gr["lk1_T_sub"]).max() < 1e-8
+    # T lives in the eigenbasis, whose gauge depends on the host's LAPACK build: compare through T @ Q^T
+    assert np.abs((T @ Q.T)[::25, ::33] - gr["lk1_TQt_sub"]).max() < 1e-8
     A_ = A + np.identity(n)
     x = np.zeros(n)
     R.lsolve_sps(n, A_.copy(), x, mBhalf[0].copy())
