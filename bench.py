@@ -1,0 +1,333 @@
+#!/usr/bin/env python
+"""bench.py -- coadd output pixels/sec of the per-postage-stamp coaddition hot path on B200.
+
+    python bench.py --gpus N --steps K --warmup W           (N > 1: launched by torchrun, one rank per GPU)
+    python bench.py --impl reference ...                     (the CPU path on the host cores, same config)
+
+Workload (BASELINE.json configs[3], the configuration the metric is quoted on): a paper4-shaped synthetic
+block -- n2 = 32, FADE = 3 (m = 1444 output px per stamp incl. fade), dtheta = 0.0390625", NPIXPSF = 48,
+oversamp = 8 (395^2-entry padded PSF-overlap tables), INPAD = 1.24", KAPPAC = [6e-4], 6 input images,
+n_inframe = 6 layers, CholKernel; n ~ 6.5 k selected input pixels per stamp -- reduced to n1P x n1P = 4 x 4
+output stamps per block so that a step takes a fraction of a second.  One STEP = one block (16 OutStamps):
+gather -> A / mBhalf assembly -> batched FP64 Cholesky + triangular solves -> T apply -> overlap-add.
+Every rank owns its own block (weak scaling, seed = 1000 + rank); the only collective is the final gather of
+the output cube to rank 0 (NCCL).
+
+value : stamps * n2^2 / time with the block inputs already resident in HBM (prepare() done before the clock)
+e2e   : the same through the public API from HOST buffers: GpuBlock(blk, tables).prepare().run().download()
+        (host planning, pinned H2D of pixels/tables/plans, the stamp loop, D2H of the block maps) + gather.
+"""
+
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+from pyimcom_b200.synth import StampConfig, SynthBlock  # noqa: E402
+
+METRIC = "coadd_output_pixels_per_sec"
+UNIT = "output px/s"
+SEED0 = 1000
+
+
+def workload_cfg(kernel="Cholesky"):
+    return StampConfig(n1=2, n2=32, dtheta_arcsec=0.0390625, fade_kernel=3, postage_pad=1, npixpsf=48, oversamp=8,
+                       instamp_pad_arcsec=1.24, n_out=1, n_inframe=6, linear_algebra=kernel,
+                       kappaC_arr=np.array([6e-4]), uctarget=1e-6, sigmamax=0.5)
+
+
+def make_block(rank):
+    cfg = workload_cfg()
+    return SynthBlock(cfg, n_image=6, seed=SEED0 + rank, psf_sigmas=(0.85, 0.9, 0.95, 1.0, 1.05, 1.1), star=True)
+
+
+def config_dict(cfg, n_stamps, extra=None):
+    d = {"workload": "paper4-shaped synthetic block (BASELINE.json configs[3]), CholKernel, reduced to n1P=4",
+         "n2": cfg.n2, "fade": cfg.fade_kernel, "n2f": cfg.n2f, "m": cfg.n2f**2, "stamps_per_block": n_stamps,
+         "n_images": 6, "n_inframe": cfg.n_inframe, "kappaC": [6e-4], "npixpsf": cfg.npixpsf, "oversamp": cfg.oversamp,
+         "inpad_arcsec": 1.24, "dtheta_arcsec": cfg.dtheta_arcsec, "blocks_per_gpu_per_step": 1,
+         "l2_policy": "per-stamp working set (A 0.35 GB + mBhalf 0.08 GB, fresh buffers every stamp) exceeds the 126 MB L2"}
+    if extra:
+        d.update(extra)
+    return d
+
+
+# ---------------------------------------------------------------------------------------------------
+# clocks
+# ---------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index, self.lines, self.proc = index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def __exit__(self, *a):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except subprocess.TimeoutExpired:
+                self.proc.kill()
+
+    def summary(self):
+        sm, mx, reasons = [], 0, set()
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx = max(mx, float(f[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------------
+# CPU arm: the oracle (port of the reference's algorithm) on the host cores
+# ---------------------------------------------------------------------------------------------------
+def cpu_stamps(blk, n_stamps, threads):
+    """Time the oracle's OutStamp path for the first n_stamps of the block; returns seconds."""
+    import warnings
+
+    from oracle import lakernel as OL
+    from oracle import routines as R
+    from oracle.sysmat import OracleOutStamp
+    from pyimcom_b200.psfovl_host import PSFTables
+
+    R.set_threads(threads)
+    tab = PSFTables(blk, R.iD5512C, R.gridD5512C, dedup=True)
+    order = list(blk.stamp_order())[:n_stamps]
+    for (j, i) in order[:1]:  # builds the PSF-overlap tables outside the clock, as on the GPU arm
+        OracleOutStamp(blk, tab, j, i).build_system_matrices()
+    t0 = time.perf_counter()
+    for (j, i) in order:
+        o = OracleOutStamp(blk, tab, j, i)
+        o.build_system_matrices()
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            OL.CholKernel(o)()
+        o.post_kernel()
+        o.perform_coaddition()
+    return time.perf_counter() - t0
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    blk = make_block(0)
+    cfg = blk.cfg
+    sample = 1
+    for _ in range(args.warmup if args.warmup < 2 else 1):
+        cpu_stamps(blk, 1, cores)
+    times = [cpu_stamps(blk, sample, cores) for _ in range(args.steps)]
+    t = float(np.mean(times))
+    val = sample * cfg.n2**2 / t
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * t, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": config_dict(cfg, sample, {"note": "each step = a bounded sample of 1 OutStamp of the same block"}),
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
+                             "sample": f"{sample} OutStamp per step, oracle/ (C + OpenMP interpolation, SciPy/OpenBLAS Cholesky)"},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------------------
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+
+    from pyimcom_b200 import _lib
+    from pyimcom_b200 import pyimcom_croutines as G
+    from pyimcom_b200.coadd import GpuBlock
+    from pyimcom_b200.psfovl_host import PSFTables
+    from pyimcom_b200.shard import gather_cube
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    blk = make_block(rank)
+    cfg = blk.cfg
+    tab = PSFTables(blk, G.iD5512C, G.gridD5512C, dedup=True)  # PSF-overlap tables (row f1): built once, outside the clock
+    gb = GpuBlock(blk, tab)
+    gb.prepare()
+    n_stamps = len(gb.order)
+    px_per_step = n_stamps * cfg.n2**2
+
+    # FP64 peak of this GPU: cuBLAS DGEMM through torch (MEASURED_PEAKS.json carries no FP64 entry)
+    N = 6144
+    a = torch.randn(N, N, dtype=torch.float64, device="cuda")
+    b = torch.randn(N, N, dtype=torch.float64, device="cuda")
+    c = torch.empty_like(a)
+    best = 1e9
+    for it in range(6):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        torch.matmul(a, b, out=c)
+        e1.record()
+        torch.cuda.synchronize()
+        if it:
+            best = min(best, e0.elapsed_time(e1) * 1e-3)
+    fp64_peak = 2 * N**3 / best / 1e12
+    del a, b, c
+
+    def step_resident():
+        gb.reset_maps()
+        gb.run()
+        return gather_cube(gb.out_map, world, rank)
+
+    def step_e2e():
+        g2 = GpuBlock(blk, tab)
+        g2.prepare()
+        g2.run()
+        maps = g2.download()
+        gather_cube(g2.out_map, world, rank)
+        return g2, maps
+
+    for _ in range(max(args.warmup, 3)):
+        step_resident()
+    # ---- timed: resident inputs ----
+    barrier()
+    _lib.profile(1)
+    n0 = _lib.launch_count()
+    with ClockSampler(local) as clk:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            step_resident()
+        e1.record()
+        barrier()
+    launches = _lib.launch_count() - n0
+    t_res = e0.elapsed_time(e1) * 1e-3
+    prof = _lib.profile_read()
+    _lib.profile(0)
+    # ---- timed: end to end from host buffers ----
+    step_e2e()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        g2, maps = step_e2e()
+    e1.record()
+    barrier()
+    t_e2e = e0.elapsed_time(e1) * 1e-3
+    h2d = int(g2.h2d_bytes)
+    d2h = int(sum(v.nbytes for v in maps.values()))
+    if world > 1:
+        tt = torch.tensor([t_res, t_e2e], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        t_res, t_e2e = float(tt[0]), float(tt[1])
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except OSError:
+            pass
+        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        hbm_src = "MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+        stages = {}
+        for name, (ms, work, cnt) in prof.items():
+            tensor = name in ("chol_super_update", "chol_panel", "chol_inner_update", "back_super_update", "back_diag",
+                              "back_inner_update", "gemm_nt", "potrf_diag")
+            rate = work / (ms * 1e-3) / (1e12 if tensor else 1e9) if ms > 0 else 0.0
+            stages[name] = {"launches": cnt, "ms_total": round(ms, 3), "share_of_step": round(ms * 1e-3 / t_res, 4),
+                            "achieved": round(rate, 3), "unit": "TFLOP/s" if tensor else "GB/s",
+                            "frac": round(rate / (fp64_peak if tensor else hbm_peak), 4)}
+        dom = "chol_super_update"
+        ms, work, cnt = prof.get(dom, (0.0, 0.0, 0))
+        ach = work / (ms * 1e-3) / 1e12 if ms > 0 else 0.0
+        tensor_ms = sum(prof[k][0] for k in prof if k.startswith(("chol_", "back_")))
+        tensor_fl = sum(prof[k][1] for k in prof if k.startswith(("chol_", "back_")))
+        roofline = {"bound": "tensor", "kernel": "k_chol_super_update (FP64 DMMA m8n8k4 tile GEMM, long-K)",
+                    "achieved": round(ach, 3), "peak": round(fp64_peak, 3), "unit": "TFLOP/s",
+                    "frac": round(ach / fp64_peak, 4), "traffic": None,
+                    "peak_source": f"cuBLAS DGEMM {N}^3 through torch.matmul, best of 5, measured in this run "
+                                   "(MEASURED_PEAKS.json has no FP64 entry)",
+                    "launches": cnt, "avg_launch_ms": round(ms / max(cnt, 1), 4),
+                    "flops_per_launch": work / max(cnt, 1),
+                    "all_dmma_kernels": {"achieved": round(tensor_fl / (tensor_ms * 1e-3) / 1e12, 3) if tensor_ms else 0,
+                                         "share_of_step": round(tensor_ms * 1e-3 / t_res, 4)},
+                    "hbm_peak_gbs": hbm_peak, "hbm_peak_source": hbm_src, "stages": stages}
+        cores = os.cpu_count() or 1
+        cpu = None
+        if world == 1 and not args.no_cpu:
+            tcpu = cpu_stamps(blk, 2, cores)
+            cpu = {"value": 2 * cfg.n2**2 / tcpu, "unit": UNIT, "cores": cores, "kind": "port",
+                   "sample": "first 2 OutStamps of the same block, oracle/ (C + OpenMP interpolation on all cores, "
+                             "SciPy/OpenBLAS Cholesky)", "seconds_per_stamp": tcpu / 2}
+        n_in = int(np.mean([gb.plans[ji].n for ji in gb.order]))
+        line = {"metric": METRIC, "value": world * px_per_step * args.steps / t_res, "unit": UNIT, "n_gpus": world,
+                "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": 1e3 * t_res / args.steps,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": config_dict(cfg, n_stamps, {"n_input_px_per_stamp": n_in, "parallelism": f"blocks x{world}"}),
+                "e2e": {"value": world * px_per_step * args.steps / t_e2e, "unit": UNIT, "h2d_bytes_per_step": h2d,
+                        "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * t_e2e / args.steps},
+                "gpu_launches": int(launches), "stamps_per_sec": world * n_stamps * args.steps / t_res,
+                "clocks": clk.summary(), "roofline": roofline, "cpu_baseline": cpu}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=("b200", "reference"))
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -32,6 +32,18 @@ long long b200_launch_count(void);
 /* frees the grow-only device scratch used by the host-seam functions */
 int b200_release_scratch(void);
 
+/* Per-launch device timing for bench.py's roofline: b200_profile(1) starts recording CUDA events around the
+ * launches of the kinds below (b200_profile(0) stops and clears); b200_profile_read synchronises the device and
+ * returns the summed duration (ms), the summed algorithmic work (flops for the DMMA kinds, bytes for the HBM
+ * kinds) and the number of launches of one kind. */
+enum b200_prof_kind {
+    B200_PROF_CHOL_SUPER = 0, B200_PROF_POTRF_DIAG, B200_PROF_CHOL_PANEL, B200_PROF_CHOL_INNER,
+    B200_PROF_BACK_SUPER, B200_PROF_BACK_DIAG, B200_PROF_BACK_INNER, B200_PROF_BUILD_A, B200_PROF_BUILD_B,
+    B200_PROF_FINALIZE, B200_PROF_GEMM, B200_PROF_ITER_CG, B200_PROF_LAKERNEL1, B200_PROF_EIGH, B200_PROF_NKINDS
+};
+int b200_profile(int on);
+int b200_profile_read(int kind, double* ms, double* work, long long* count);
+
 /* ---- 1. host seam: furry_parakeet.pyimcom_croutines / pyimcom.routine ------------------------- */
 /* routine.py:125-181  iD5512C(infunc (nlayer,ngy,ngx), xpos (nout), ypos (nout), fhatout (nlayer,nout));
  * off-grid points leave fhatout untouched (routine.py:166-167). */

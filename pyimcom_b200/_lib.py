@@ -61,6 +61,8 @@ class FinalizeArgs(C.Structure):
 # name -> argtypes, exactly the declarations of include/pyimcom_b200.h (checked by tests/test_abi.py)
 PROTOTYPES = {
     "b200_release_scratch": [],
+    "b200_profile": [i32],
+    "b200_profile_read": [i32, C.POINTER(f64), C.POINTER(f64), C.POINTER(C.c_longlong)],
     "b200_iD5512C": [vp, i32, i32, i32, vp, vp, i64, vp],
     "b200_iD5512C_sym": [vp, i32, i32, i32, vp, vp, i64, vp],
     "b200_gridD5512C": [vp, i32, i32, vp, vp, i64, i32, i32, vp],
@@ -117,6 +119,22 @@ def _wrap(name, argtypes):
 
 for _n, _a in PROTOTYPES.items():
     globals()[_n[len("b200_"):]] = _wrap(_n, _a)
+profile_read_raw = globals()["profile_read"]
+
+
+PROF_KINDS = ("chol_super_update", "potrf_diag", "chol_panel", "chol_inner_update", "back_super_update", "back_diag",
+              "back_inner_update", "build_A", "build_B", "finalize", "gemm_nt", "iter_cg", "lakernel1", "eigh")
+
+
+def profile_read():
+    """{kind: (total ms, total algorithmic work, launches)} for every kind with at least one recorded launch."""
+    out = {}
+    for k, name in enumerate(PROF_KINDS):
+        ms, work, cnt = f64(0), f64(0), C.c_longlong(0)
+        globals()["profile_read_raw"](k, C.byref(ms), C.byref(work), C.byref(cnt))
+        if cnt.value:
+            out[name] = (ms.value, work.value, cnt.value)
+    return out
 
 
 def launch_count() -> int:

@@ -34,6 +34,14 @@ TABLEREF_DTYPE = np.dtype([("offset", "<i8"), ("flip", "<i4"), ("pad_", "<i4"), 
 assert TABLEREF_DTYPE.itemsize == C.sizeof(_lib.TableRef)
 
 
+def h2d(a: np.ndarray) -> torch.Tensor:
+    """Host array -> device tensor through pinned memory, asynchronous on the current stream."""
+    t = torch.from_numpy(np.ascontiguousarray(a))
+    if t.numel() == 0:
+        return t.cuda()
+    return t.pin_memory().to("cuda", non_blocking=True)
+
+
 class _Arena:
     """PSF-overlap tables in HBM: each table set is stored once, zero-padded by 6 (np.pad(ovl, 6), psfutil.py:1471)."""
 
@@ -61,8 +69,7 @@ class _Arena:
     def upload(self):
         if not self.chunks:
             return torch.zeros(1, dtype=torch.float64, device="cuda")
-        host = np.concatenate(self.chunks)
-        return torch.from_numpy(host).cuda()
+        return h2d(np.concatenate(self.chunks))
 
 
 class StampPlan:
@@ -191,28 +198,33 @@ class GpuBlock:
     def upload(self):
         cfg = self.cfg
         dev = "cuda"
-        self.d_x = torch.from_numpy(self.h_x).to(dev)
-        self.d_y = torch.from_numpy(self.h_y).to(dev)
-        self.d_data = torch.from_numpy(self.h_data).to(dev)
+        self.d_x = h2d(self.h_x)
+        self.d_y = h2d(self.h_y)
+        self.d_data = h2d(self.h_data)
         self.d_tables = self.arena.upload()
         plans = [self.plans[ji] for ji in self.order]
         # per-stamp metadata packed into a few arrays, one H2D copy each
         self.off_pix = np.concatenate([[0], np.cumsum([p.n for p in plans])]).astype(np.int64)
         self.off_seg = np.concatenate([[0], np.cumsum([p.seg_end.size for p in plans])]).astype(np.int64)
         cat = lambda arrs, dt: np.concatenate(arrs).astype(dt) if arrs else np.zeros(0, dtype=dt)  # noqa: E731
-        self.d_idx = torch.from_numpy(cat([p.idx for p in plans], np.int32)).to(dev)
-        self.d_pcode_all = torch.from_numpy(cat([p.pcode for p in plans], np.int32)).to(dev)
-        self.d_seg_end = torch.from_numpy(cat([p.seg_end for p in plans], np.int32)).to(dev)
-        self.d_seg_img = torch.from_numpy(cat([p.seg_img for p in plans], np.int32)).to(dev)
+        self.d_idx = h2d(cat([p.idx for p in plans], np.int32))
+        self.d_pcode_all = h2d(cat([p.pcode for p in plans], np.int32))
+        self.d_seg_end = h2d(cat([p.seg_end for p in plans], np.int32))
+        self.d_seg_img = h2d(cat([p.seg_img for p in plans], np.int32))
         lut = np.stack([p.lut for p in plans]) if plans else np.zeros((0, 1, 1), dtype=TABLEREF_DTYPE)
-        self.d_lut = torch.from_numpy(lut.view(np.uint8).reshape(len(plans), -1)).to(dev)
+        self.d_lut = h2d(lut.view(np.uint8).reshape(len(plans), -1))
         lut_io = np.stack([p.lut_io for p in plans]) if plans else np.zeros((0, 1, 1), dtype=np.int64)
-        self.d_lut_io = torch.from_numpy(np.ascontiguousarray(lut_io)).to(dev)
-        self.d_fade_w = torch.from_numpy(trapezoid_weights(cfg.fade_kernel)).to(dev) if cfg.fade_kernel > 0 else None
+        self.d_lut_io = h2d(np.ascontiguousarray(lut_io))
+        self.d_fade_w = h2d(trapezoid_weights(cfg.fade_kernel)) if cfg.fade_kernel > 0 else None
         self.h2d_bytes = sum(t.numel() * t.element_size() for t in (self.d_x, self.d_y, self.d_data, self.d_tables,
                                                                      self.d_idx, self.d_pcode_all, self.d_seg_end,
                                                                      self.d_seg_img, self.d_lut, self.d_lut_io))
-        # block maps (coadd.py:2028-2047)
+        self.reset_maps()
+        self._uploaded = True
+
+    def reset_maps(self):
+        """Zero-initialised block maps (coadd.py:2028-2047)."""
+        cfg, dev = self.cfg, "cuda"
         side = cfg.NsideP + 2 * cfg.fade_kernel
         self.side = side
         n_out = cfg.n_out
@@ -223,7 +235,6 @@ class GpuBlock:
         self.kappa_map = torch.zeros_like(self.UC_map)
         self.Tsum_map = torch.zeros_like(self.UC_map)
         self.Neff_map = torch.zeros_like(self.UC_map)
-        self._uploaded = True
 
     # ---------------------------------------------------------------------------------------------
     # device pipeline of one OutStamp

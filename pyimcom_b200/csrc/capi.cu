@@ -3,6 +3,8 @@
 #include <stdarg.h>
 #include <string.h>
 
+#include <vector>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -56,6 +58,40 @@ void scratch_release() {
     }
 }
 
+// ---- per-launch profiling -------------------------------------------------------------------------
+struct ProfRec {
+    cudaEvent_t a, b;
+    double work;
+    int kind;
+};
+static int g_prof_on = 0;
+static std::vector<ProfRec> g_prof;
+
+void prof_begin(int kind, cudaStream_t st) {
+    if (!g_prof_on) return;
+    ProfRec r;
+    r.kind = kind;
+    r.work = 0.0;
+    if (cudaEventCreate(&r.a) != cudaSuccess || cudaEventCreate(&r.b) != cudaSuccess) return;
+    cudaEventRecord(r.a, st);
+    g_prof.push_back(r);
+}
+
+void prof_end(double work, cudaStream_t st) {
+    if (!g_prof_on || g_prof.empty()) return;
+    ProfRec& r = g_prof.back();
+    r.work = work;
+    cudaEventRecord(r.b, st);
+}
+
+static void prof_reset() {
+    for (auto& r : g_prof) {
+        cudaEventDestroy(r.a);
+        cudaEventDestroy(r.b);
+    }
+    g_prof.clear();
+}
+
 }  // namespace b200
 
 using namespace b200;
@@ -94,6 +130,28 @@ int b200_version(void) { return 100; }
 long long b200_launch_count(void) { return g_launches; }
 int b200_release_scratch(void) {
     scratch_release();
+    return 0;
+}
+int b200_profile(int on) {
+    prof_reset();
+    g_prof_on = on;
+    return 0;
+}
+int b200_profile_read(int kind, double* ms, double* work, long long* count) {
+    B200_CUDA(cudaDeviceSynchronize());
+    double t = 0.0, w = 0.0;
+    long long c = 0;
+    for (auto& r : g_prof) {
+        if (r.kind != kind) continue;
+        float e = 0.f;
+        if (cudaEventElapsedTime(&e, r.a, r.b) != cudaSuccess) continue;
+        t += e;
+        w += r.work;
+        c++;
+    }
+    if (ms) *ms = t;
+    if (work) *work = w;
+    if (count) *count = c;
     return 0;
 }
 

@@ -251,7 +251,12 @@ int launch_finalize(const FinalizeArgs& a, cudaStream_t s) {
         B200_CUDA(cudaFuncSetAttribute(k_finalize, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         done = true;
     }
+    prof_begin(PROF_FINALIZE, s);
     k_finalize<<<(a.m + ROWS - 1) / ROWS, FT, smem, s>>>(a);
+    // bytes: node solutions + (-B/2) read once, float32 T written once, layers read once
+    prof_end((double)a.m * a.n * (8.0 * a.nv + (a.mB ? 8.0 : 0.0) + (a.T32 ? 4.0 : 0.0) + (a.Ti64 ? 8.0 : 0.0)) +
+                 4.0 * a.n_inframe * (double)a.n,
+             s);
     B200_LAUNCH_CHECK();
     return 0;
 }

@@ -410,8 +410,10 @@ int launch_build_A(const double* px, const double* py, const int* pcode, int n, 
     B200_REQUIRE(npad % 32 == 0 && npad >= n && lda >= npad, "build_A: npad must be a multiple of 32, >= n, <= lda");
     const long nt = npad / 32;
     const long ntri = nt * (nt + 1) / 2;
+    prof_begin(PROF_BUILD_A, s);
     k_build_A<<<(unsigned)ntri, 256, 0, s>>>(px, py, pcode, n, npad, tables, lut, nimg, ncode, ngrid, dscale, nc,
                                              flat_penalty, A, lda, diag_add);
+    prof_end(8.0 * npad * (double)npad + 20.0 * n, s);  // bytes: the matrix written once + positions/codes read
     B200_LAUNCH_CHECK();
     return 0;
 }
@@ -429,9 +431,11 @@ int launch_build_B(const double* px, const double* py, const int* pcode, int n, 
         B200_CUDA(cudaFuncSetAttribute(k_build_B<TI>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
         attr_done = true;
     }
+    prof_begin(PROF_BUILD_B, s);
     k_build_B<TI><<<(unsigned)((npad + TI - 1) / TI), 256, smem, s>>>(px, py, pcode, n, npad, tables, lut_io, n_out,
                                                                        ngrid, dscale, nc, n2f, mpad, x0out, y0out, B,
                                                                        ldb, strideB);
+    prof_end(8.0 * n_out * (double)mpad * npad + 20.0 * n, s);
     B200_LAUNCH_CHECK();
     return 0;
 }

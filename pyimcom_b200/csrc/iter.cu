@@ -140,8 +140,10 @@ int launch_iter_cg(const double* AA, int lda, double diag_add, const double* mB,
         B200_CUDA(cudaFuncSetAttribute(k_iter_cg, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
         done = true;
     }
+    prof_begin(PROF_ITER_CG, s);
     k_iter_cg<<<m, CT, smem, s>>>(AA, lda, diag_add, mB, ldb, m, n, inx, iny, outx, outy, rho_acc, rtol,
                                   maxiter, Ti, ldt, niter, nsel);
+    prof_end(8.0 * m * (double)n * 2.0, s);  // bytes: mBhalf rows read + Ti rows written (A_sel gathers hit L2)
     B200_LAUNCH_CHECK();
     return 0;
 }

@@ -319,6 +319,7 @@ int launch_lakernel1(const double* lam, const double* mPhalf, int ldp, int m, in
                      double kCmin, double kCmax, int nbis, double* kappa, double* Sigma, double* UC, double* T, int ldt,
                      double smax, cudaStream_t s) {
     if (m <= 0) return 0;
+    prof_begin(PROF_LAKERNEL1, s);
     const size_t smem_row = (40 + (size_t)n) * sizeof(double);
     if (smem_row <= 200 * 1024) {
         static bool done = false;
@@ -332,6 +333,7 @@ int launch_lakernel1(const double* lam, const double* mPhalf, int ldp, int m, in
         k_lakernel1<false><<<m, KT_THREADS, 40 * sizeof(double), s>>>(lam, mPhalf, ldp, m, n, C, targetleak, kCmin,
                                                                        kCmax, nbis, kappa, Sigma, UC, T, ldt, smax);
     }
+    prof_end(8.0 * m * (double)n * 2.0, s);  // bytes: mPhalf read once (row kept on chip), T written once
     B200_LAUNCH_CHECK();
     return 0;
 }

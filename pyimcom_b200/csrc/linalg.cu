@@ -27,6 +27,7 @@ constexpr int KT = 16;           // K extent of one pipeline stage
 constexpr int LDSM = KT + 4;     // smem row stride in doubles: 20 = 4 mod 16 -> conflict-free fragment loads
 constexpr int STAGES = 4;
 constexpr int GT = 256;          // threads per GEMM CTA
+constexpr int SP = 4;            // block columns per super-panel (512 matrix columns)
 constexpr int STAGE_DOUBLES = 2 * NB * LDSM;
 constexpr size_t GEMM_SMEM = (size_t)STAGES * STAGE_DOUBLES * sizeof(double);  // 163840 B
 
@@ -147,6 +148,32 @@ __global__ void __launch_bounds__(GT, 1) k_gemm_nt(const double* __restrict__ A,
 }
 
 // ---- factorisation phases ----------------------------------------------------------------------
+// The driver works on SUPER-PANELS of SP block columns [c0, c1): left-looking between super-panels (one
+// long-K GEMM launch brings the whole super-panel up to date: every output tile is read and written once
+// per super-panel, so the tile kernel runs at its large-K rate), right-looking with K = 128 inside.
+//
+// Super-panel update:  W[i][j] -= W[i][0:c0] W[j][0:c0]^T  (c0 <= j < c1, j <= i)  and the same for the X rows.
+__global__ void __launch_bounds__(GT, 1) k_chol_super_update(SolveBatch bt, int c0, int c1) {
+    extern __shared__ __align__(16) double smem[];
+    const SolveSys& s = bt.s[blockIdx.z];
+    const int nb = s.npad / NB, mb = s.mpad / NB;
+    const int j = c0 + blockIdx.x, t = blockIdx.y;
+    const int nrow = nb - c0;
+    if (j >= nb || j >= c1 || t >= nrow + mb) return;
+    const double* Bp = s.W + (size_t)j * NB * s.ldw;
+    const int K = c0 * NB;
+    if (t < nrow) {
+        const int i = c0 + t;
+        if (j > i) return;
+        gemm_tile_nt<TILE_SUB>(s.W + (size_t)i * NB * s.ldw, s.ldw, Bp, s.ldw,
+                               s.W + (size_t)i * NB * s.ldw + (size_t)j * NB, s.ldw, K, nullptr, 0, smem);
+    } else {
+        const int r = t - nrow;
+        gemm_tile_nt<TILE_SUB>(s.X + (size_t)r * NB * s.ldx, s.ldx, Bp, s.ldw,
+                               s.X + (size_t)r * NB * s.ldx + (size_t)j * NB, s.ldx, K, nullptr, 0, smem);
+    }
+}
+
 // Panel step k: rows below the diagonal block (and all X rows) times inv(L_kk)^T; the W part is also
 // stored transposed into the upper block triangle.
 __global__ void __launch_bounds__(GT, 1) k_chol_panel(SolveBatch bt, int k) {
@@ -168,15 +195,16 @@ __global__ void __launch_bounds__(GT, 1) k_chol_panel(SolveBatch bt, int k) {
     }
 }
 
-// Trailing update after panel k:  W[i][j] -= W[i][k] W[j][k]^T (k < j <= i)  and  X[t][j] -= X[t][k] W[j][k]^T.
-__global__ void __launch_bounds__(GT, 1) k_chol_update(SolveBatch bt, int k) {
+// Update inside the super-panel after panel k:  W[i][j] -= W[i][k] W[j][k]^T (k < j < c1, j <= i)  and
+// X[t][j] -= X[t][k] W[j][k]^T.
+__global__ void __launch_bounds__(GT, 1) k_chol_update(SolveBatch bt, int k, int c1) {
     extern __shared__ __align__(16) double smem[];
     const SolveSys& s = bt.s[blockIdx.z];
     const int nb = s.npad / NB, mb = s.mpad / NB;
     const int nrow = nb - 1 - k;
     const int jj = blockIdx.x, t = blockIdx.y;
-    if (k >= nb || jj >= nrow || t >= nrow + mb) return;
     const int j = k + 1 + jj;
+    if (k >= nb || j >= nb || j >= c1 || t >= nrow + mb) return;
     const double* Bp = s.W + (size_t)j * NB * s.ldw + (size_t)k * NB;
     if (t < nrow) {
         const int i = k + 1 + t;
@@ -190,6 +218,21 @@ __global__ void __launch_bounds__(GT, 1) k_chol_update(SolveBatch bt, int k) {
     }
 }
 
+// Backward substitution Ti = Z L^-1, super-panels taken from the right.  In "from the end" coordinates
+// [e0, e1) the super-panel of a system with nb blocks is lo = max(0, nb - e1) <= k < hi = nb - e0.
+// Super-panel update:  X[t][j] -= X[t][hi:nb] L[hi:nb][j]  (lo <= j < hi); L[k][j]^T lives at W[j][k] (upper triangle).
+__global__ void __launch_bounds__(GT, 1) k_back_super_update(SolveBatch bt, int e0, int e1) {
+    extern __shared__ __align__(16) double smem[];
+    const SolveSys& s = bt.s[blockIdx.z];
+    const int nb = s.npad / NB, mb = s.mpad / NB;
+    const int hi = nb - e0;
+    const int j = hi - 1 - (int)blockIdx.x, t = blockIdx.y;
+    if (hi <= 0 || j < 0 || j < nb - e1 || t >= mb) return;
+    gemm_tile_nt<TILE_SUB>(s.X + (size_t)t * NB * s.ldx + (size_t)hi * NB, s.ldx,
+                           s.W + (size_t)j * NB * s.ldw + (size_t)hi * NB, s.ldw,
+                           s.X + (size_t)t * NB * s.ldx + (size_t)j * NB, s.ldx, e0 * NB, nullptr, 0, smem);
+}
+
 // Backward step k, part 1:  X[t][k] = X[t][k] inv(L_kk)   (B operand = inv(L_kk)^T)
 __global__ void __launch_bounds__(GT, 1) k_back_diag(SolveBatch bt, int kfromtop) {
     extern __shared__ __align__(16) double smem[];
@@ -201,14 +244,14 @@ __global__ void __launch_bounds__(GT, 1) k_back_diag(SolveBatch bt, int kfromtop
     gemm_tile_nt<TILE_ASSIGN>(Cp, s.ldx, s.Dinv + (size_t)(nb + k) * NB * NB, NB, Cp, s.ldx, NB, nullptr, 0, smem);
 }
 
-// Backward step k, part 2:  X[t][j] -= X[t][k] L[k][j]  (j < k); L[k][j]^T lives at W[j][k] (upper triangle)
-__global__ void __launch_bounds__(GT, 1) k_back_update(SolveBatch bt, int kfromtop) {
+// Backward step k, part 2, inside the super-panel:  X[t][j] -= X[t][k] L[k][j]  (lo <= j < k)
+__global__ void __launch_bounds__(GT, 1) k_back_update(SolveBatch bt, int kfromtop, int e1) {
     extern __shared__ __align__(16) double smem[];
     const SolveSys& s = bt.s[blockIdx.z];
     const int nb = s.npad / NB, mb = s.mpad / NB;
     const int k = nb - 1 - kfromtop;
-    const int j = blockIdx.x, t = blockIdx.y;
-    if (k < 0 || j >= k || t >= mb) return;
+    const int j = k - 1 - (int)blockIdx.x, t = blockIdx.y;
+    if (k < 0 || j < 0 || j < nb - e1 || t >= mb) return;
     gemm_tile_nt<TILE_SUB>(s.X + (size_t)t * NB * s.ldx + (size_t)k * NB, s.ldx,
                            s.W + (size_t)j * NB * s.ldw + (size_t)k * NB, s.ldw,
                            s.X + (size_t)t * NB * s.ldx + (size_t)j * NB, s.ldx, NB, nullptr, 0, smem);
@@ -408,6 +451,8 @@ int gemm_attrs() {
     B200_CUDA(cudaFuncSetAttribute(k_gemm_nt<TILE_ADD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM));
     B200_CUDA(cudaFuncSetAttribute(k_chol_panel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM));
     B200_CUDA(cudaFuncSetAttribute(k_chol_update, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM));
+    B200_CUDA(cudaFuncSetAttribute(k_chol_super_update, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM));
+    B200_CUDA(cudaFuncSetAttribute(k_back_super_update, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM));
     B200_CUDA(cudaFuncSetAttribute(k_back_diag, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM));
     B200_CUDA(cudaFuncSetAttribute(k_back_update, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM));
     B200_CUDA(cudaFuncSetAttribute(k_potrf_diag, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)POTRF_SMEM));
@@ -435,30 +480,78 @@ int launch_chol_solve(const SolveSys* h_sys, int nsys, int do_factor, int do_sol
         mbmax = s.mpad / NB > mbmax ? s.mpad / NB : mbmax;
     }
     for (int i = nsys; i < MAXB; i++) bt.s[i] = bt.s[0];
+    // algorithmic flop counts of the launches (profiling only): tiles actually computed x 2*128^2*K
+    auto tiles_fwd = [&](int c0, int c1, int rows_from) {  // W tiles (j <= i) + X tiles over all systems
+        double t = 0;
+        for (int q = 0; q < nsys; q++) {
+            const int nb = bt.s[q].npad / NB, mb = bt.s[q].mpad / NB;
+            for (int j = c0; j < c1 && j < nb; j++) {
+                const int ifrom = rows_from > j ? rows_from : j;
+                t += (nb - ifrom > 0 ? nb - ifrom : 0) + mb;
+            }
+        }
+        return t;
+    };
+    const double tile_flops = 2.0 * NB * NB;
     if (do_factor) {
-        for (int k = 0; k < nbmax; k++) {
-            k_potrf_diag<<<nsys, 256, POTRF_SMEM, st>>>(bt, k);
-            B200_LAUNCHED(1);
-            const int nrow = nbmax - 1 - k;
-            if (nrow + mbmax > 0) {
-                k_chol_panel<<<dim3(nrow + mbmax, nsys), GT, GEMM_SMEM, st>>>(bt, k);
+        for (int c0 = 0; c0 < nbmax; c0 += SP) {
+            const int c1 = c0 + SP < nbmax ? c0 + SP : nbmax;
+            if (c0 > 0) {
+                prof_begin(PROF_CHOL_SUPER, st);
+                k_chol_super_update<<<dim3(c1 - c0, nbmax - c0 + mbmax, nsys), GT, GEMM_SMEM, st>>>(bt, c0, c1);
+                prof_end(tiles_fwd(c0, c1, c0) * tile_flops * c0 * NB, st);
                 B200_LAUNCHED(1);
             }
-            if (nrow > 0) {
-                k_chol_update<<<dim3(nrow, nrow + mbmax, nsys), GT, GEMM_SMEM, st>>>(bt, k);
+            for (int k = c0; k < c1; k++) {
+                prof_begin(PROF_POTRF_DIAG, st);
+                k_potrf_diag<<<nsys, 256, POTRF_SMEM, st>>>(bt, k);
+                prof_end(nsys * (NB * (double)NB * NB), st);
                 B200_LAUNCHED(1);
+                const int nrow = nbmax - 1 - k;
+                if (nrow + mbmax > 0) {
+                    prof_begin(PROF_CHOL_PANEL, st);
+                    k_chol_panel<<<dim3(nrow + mbmax, nsys), GT, GEMM_SMEM, st>>>(bt, k);
+                    prof_end(tiles_fwd(k, k + 1, k + 1) * tile_flops * NB, st);
+                    B200_LAUNCHED(1);
+                }
+                if (c1 - 1 - k > 0) {
+                    prof_begin(PROF_CHOL_INNER, st);
+                    k_chol_update<<<dim3(c1 - 1 - k, nrow + mbmax, nsys), GT, GEMM_SMEM, st>>>(bt, k, c1);
+                    prof_end(tiles_fwd(k + 1, c1, k + 1) * tile_flops * NB, st);
+                    B200_LAUNCHED(1);
+                }
             }
         }
         B200_CUDA(cudaGetLastError());
     }
     if (do_solve && mbmax > 0) {
-        for (int kk = 0; kk < nbmax; kk++) {
-            k_back_diag<<<dim3(mbmax, nsys), GT, GEMM_SMEM, st>>>(bt, kk);
-            B200_LAUNCHED(1);
-            const int kmax = nbmax - 1 - kk;
-            if (kmax > 0) {
-                k_back_update<<<dim3(kmax, mbmax, nsys), GT, GEMM_SMEM, st>>>(bt, kk);
+        double mbsum = 0;
+        for (int q = 0; q < nsys; q++) mbsum += bt.s[q].mpad / NB;
+        for (int e0 = 0; e0 < nbmax; e0 += SP) {
+            const int e1 = e0 + SP < nbmax ? e0 + SP : nbmax;
+            if (e0 > 0) {
+                prof_begin(PROF_BACK_SUPER, st);
+                k_back_super_update<<<dim3(e1 - e0, mbmax, nsys), GT, GEMM_SMEM, st>>>(bt, e0, e1);
+                double t = 0;
+                for (int q = 0; q < nsys; q++) {
+                    const int nb = bt.s[q].npad / NB;
+                    const int hi = nb - e0, lo = nb - e1 > 0 ? nb - e1 : 0;
+                    if (hi > lo) t += (double)(hi - lo) * (bt.s[q].mpad / NB);
+                }
+                prof_end(t * tile_flops * e0 * NB, st);
                 B200_LAUNCHED(1);
+            }
+            for (int kk = e0; kk < e1; kk++) {
+                prof_begin(PROF_BACK_DIAG, st);
+                k_back_diag<<<dim3(mbmax, nsys), GT, GEMM_SMEM, st>>>(bt, kk);
+                prof_end(mbsum * tile_flops * NB, st);
+                B200_LAUNCHED(1);
+                if (e1 - 1 - kk > 0) {
+                    prof_begin(PROF_BACK_INNER, st);
+                    k_back_update<<<dim3(e1 - 1 - kk, mbmax, nsys), GT, GEMM_SMEM, st>>>(bt, kk, e1);
+                    prof_end(mbsum * (e1 - 1 - kk) * tile_flops * NB, st);
+                    B200_LAUNCHED(1);
+                }
             }
         }
         B200_CUDA(cudaGetLastError());
