@@ -26,7 +26,8 @@ import numpy as np
 import torch
 
 from . import _lib
-from .lakernel import SOLVERS, ApplySpec, DeviceSystem, apply_T, eigen_decompose, ptr, rup, solve_eigen, stream_handle
+from .lakernel import SOLVERS, ApplySpec, DeviceSystem, apply_T, eigen_decompose, ptr, rup, solve_chol_batch, solve_eigen
+from .lakernel import stream_handle
 from .lakernel import trapezoid_weights
 from .psfovl_host import anchor
 
@@ -285,36 +286,62 @@ class GpuBlock:
         """OutStamp.__call__ (coadd.py:979-1000) + overlap-add (coadd.py:1976-1994) for stamp k of self.order.
 
         keep=True returns the per-stamp device results (parity tests); otherwise nothing is retained."""
+        return self.coadd_batch([k], keep=keep)[0]
+
+    def coadd_batch(self, ks, keep: bool = False):
+        """The OutStamps ks (positions in self.order) together: stage (a) per stamp, then ONE batched solve across
+        the stamps (CholKernel: every (stamp, kappa node) system shares the factorisation launches; the other
+        kernels run stamp by stamp), then T-apply and overlap-add per stamp.  Stamps are independent given their
+        3x3 InStamp neighbourhoods (coadd.py:2056-2060), so the order inside a batch does not matter."""
         cfg = self.cfg
-        p = self.plans[self.order[k]]
-        st = stream_handle()
-        kept = {}
-        if p.n == 0:  # lakernel.py:110-119 and coadd.py:1094-1100: nothing to add except UC = kappa = 1
-            return self._empty_stamp(p, keep)
-        ds, indata = self.build_system(k)
-        spec = self.apply_spec(k, indata, want_T32=keep, want_Ti64=keep)
-        eig = eigen_decompose(ds) if self.kernel == "Eigen" else None
-        y0, x0 = (p.j_st - 1) * cfg.n2, (p.i_st - 1) * cfg.n2
+        kept = [dict() for _ in ks]
+        live = []
+        for q, k in enumerate(ks):
+            p = self.plans[self.order[k]]
+            if p.n == 0:  # lakernel.py:110-119 and coadd.py:1094-1100: nothing to add except UC = kappa = 1
+                self._empty_stamp(p, keep)
+                continue
+            ds, indata = self.build_system(k)
+            live.append((q, k, p, ds, indata))
         for j_out in range(cfg.n_out):
-            if self.kernel == "Eigen":
-                ko = solve_eigen(ds, cfg, j_out, eig=eig)
-            else:
-                ko = SOLVERS[self.kernel](ds, cfg, j_out)
-            res = apply_T(ds, ko, j_out, spec)
-            acc = lambda src, f64, nl, dst: _lib.dev_accumulate(ptr(src), int(f64), nl, cfg.n2f, ptr(dst), self.side, y0,  # noqa: E731
-                                                                x0, st)
-            acc(res["outimage"], False, cfg.n_inframe, self.out_map[j_out])
-            acc(res["UC"], False, 1, self.UC_map[j_out])
-            acc(res["Sigma"], False, 1, self.Sigma_map[j_out])
-            acc(res["kappa"], False, 1, self.kappa_map[j_out])
-            acc(res["Tsum_inpix"], True, 1, self.Tsum_map[j_out])
-            acc(res["Neff"], True, 1, self.Neff_map[j_out])
-            self.T_weightmap[j_out, :, p.j_st - 1, p.i_st - 1] = res["Tsum_stamp"][: self.blk.n_inimage].float()
+            if self.kernel == "Cholesky":
+                kos = solve_chol_batch([t[3] for t in live], cfg, j_out) if live else []
+            for u, (q, k, p, ds, indata) in enumerate(live):
+                if self.kernel == "Cholesky":
+                    ko = kos[u]
+                elif self.kernel == "Eigen":
+                    if j_out == 0:
+                        kept[q]["_eig"] = eigen_decompose(ds)
+                    ko = solve_eigen(ds, cfg, j_out, eig=kept[q]["_eig"])
+                else:
+                    ko = SOLVERS[self.kernel](ds, cfg, j_out)
+                spec = self.apply_spec(k, indata, want_T32=keep, want_Ti64=keep)
+                res = apply_T(ds, ko, j_out, spec)
+                self._overlap_add(p, j_out, res)
+                if keep:
+                    kept[q][j_out] = dict(res=res, ko=ko)
+            if self.kernel == "Cholesky":
+                del kos
+        for (q, k, p, ds, indata) in live:
+            kept[q].pop("_eig", None)
             if keep:
-                kept[j_out] = dict(res=res, ko=ko)
-        if keep:
-            kept["ds"], kept["indata"], kept["plan"] = ds, indata, p
+                kept[q]["ds"], kept[q]["indata"], kept[q]["plan"] = ds, indata, p
         return kept
+
+    def _overlap_add(self, p, j_out, res):
+        """coadd.py:1976-1994: add one stamp's faded results into the block maps."""
+        cfg = self.cfg
+        st = stream_handle()
+        y0, x0 = (p.j_st - 1) * cfg.n2, (p.i_st - 1) * cfg.n2
+        acc = lambda src, f64, nl, dst: _lib.dev_accumulate(ptr(src), int(f64), nl, cfg.n2f, ptr(dst), self.side, y0,  # noqa: E731
+                                                            x0, st)
+        acc(res["outimage"], False, cfg.n_inframe, self.out_map[j_out])
+        acc(res["UC"], False, 1, self.UC_map[j_out])
+        acc(res["Sigma"], False, 1, self.Sigma_map[j_out])
+        acc(res["kappa"], False, 1, self.kappa_map[j_out])
+        acc(res["Tsum_inpix"], True, 1, self.Tsum_map[j_out])
+        acc(res["Neff"], True, 1, self.Neff_map[j_out])
+        self.T_weightmap[j_out, :, p.j_st - 1, p.i_st - 1] = res["Tsum_stamp"][: self.blk.n_inimage].float()
 
     def _empty_stamp(self, p, keep):
         cfg = self.cfg
@@ -334,11 +361,28 @@ class GpuBlock:
         self.kappa_map[sl] += t
         return {}
 
-    def run(self):
-        """coadd_output_stamps(sim_mode=False) (coadd.py:2056-2069): every planned stamp, in order."""
+    def batch_size(self) -> int:
+        """OutStamps solved together: as many as MAXB systems allow, within an HBM budget (A, W, mBhalf and X of
+        every stamp of the batch are live at once: ~(2 npad^2 + 2 n_out mpad npad) * 8 bytes per kappa node)."""
+        if self.kernel != "Cholesky" or not self.order:
+            return 1
+        cfg = self.cfg
+        nv = max(1, len(np.atleast_1d(cfg.kappaC_arr)))
+        nmax = max(self.plans[ji].n for ji in self.order)
+        npad, mpad = rup(nmax), rup(cfg.n2f**2)
+        per = 8.0 * ((1 + nv) * npad * npad + (cfg.n_out + nv) * mpad * npad)
+        free = torch.cuda.mem_get_info()[0] + torch.cuda.memory_reserved() - torch.cuda.memory_allocated()
+        return int(max(1, min(0.5 * free // per, self.max_batch)))
+
+    max_batch = 16
+
+    def run(self, batch: int | None = None):
+        """coadd_output_stamps(sim_mode=False) (coadd.py:2056-2069): every planned stamp, in batches of
+        independent stamps (order inside the block is the reference's)."""
         assert self._uploaded, "call prepare() first"
-        for k in range(len(self.order)):
-            self.coadd_stamp(k)
+        nb = batch or self.batch_size()
+        for k0 in range(0, len(self.order), nb):
+            self.coadd_batch(list(range(k0, min(k0 + nb, len(self.order)))))
         return self
 
     def download(self):

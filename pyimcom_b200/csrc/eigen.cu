@@ -1,15 +1,17 @@
 // Symmetric eigendecomposition for EigenKernel and the Cholesky repair branch:
 // replaces np.linalg.eigh at lakernel.py:162, 201, 266.
 //
-// Parallel one-sided (Hestenes) Jacobi on the rows of G = V^T A, V = I initially.  A rotation of rows
-// (p, q) is chosen so that g_p . g_q = 0; the same rotation is applied to the rows of V^T.  At
-// convergence the rows of G are mutually orthogonal, G G^T = V^T A^2 V is diagonal, so the rows of V^T
-// are eigenvectors of A (A is symmetric positive semi-definite up to rounding here) and
-// lam_k = g_k . v_k keeps the sign.  Pairs are scheduled by the round-robin ("circle") tournament:
-// npl/2 disjoint pairs per round, npl - 1 rounds per sweep, one kernel launch per round, one CTA per pair.
-// The pair (p,q) is skipped when |g_p.g_q| <= tol |g_p||g_q| (relative criterion, tol = max(1e-15, sqrt(n) eps))
-// or when both rows are numerically null (|g_p||g_q| <= (4 eps |A|_F)^2): any orthonormal basis of the null
-// space serves the callers (T, Sigma and U/C are invariant to it).
+// Parallel two-sided (classical) Jacobi in implicit form: the kernel keeps G = V^T A and V^T (V = I
+// initially) and never stores H = V^T A V; the three entries a rotation of the pair (p, q) needs are dot
+// products of rows, h_pp = g_p . v_p, h_qq = g_q . v_q, h_pq = g_p . v_q, and the rotation that zeroes h_pq
+// is applied to rows p, q of both G and V^T (which is H <- J^T H J).  Working on H rather than on the Gram
+// matrix G G^T = V^T A^2 V (one-sided Hestenes) keeps the absolute accuracy at eps |A|_F for the small
+// eigenvalues too, which is what LAPACK's eigh delivers and what 1/(lam + kappa) in EigenKernel needs.
+// Pairs are scheduled by the round-robin ("circle") tournament: npl/2 disjoint pairs per round, npl - 1
+// rounds per sweep, one kernel launch per round, one CTA per pair.
+// The pair (p,q) is skipped when |h_pq| <= tol sqrt|h_pp h_qq| (tol = max(1e-15, sqrt(n) eps)) or when
+// |h_pq| <= 2 sqrt(n) eps |A|_F (the rounding floor of the implicit dot products): any orthonormal basis of a
+// numerically degenerate subspace serves the callers (T, Sigma and U/C are invariant to it).
 // Every reduction uses a fixed thread -> element mapping and a fixed tree: the result is deterministic.
 #include <math.h>
 
@@ -92,29 +94,23 @@ __global__ void __launch_bounds__(JT) k_jacobi_round(double* __restrict__ G, int
     if (q >= n) return;  // dummy player of an odd-sized problem
     double* gp = G + (size_t)p * lda;
     double* gq = G + (size_t)q * lda;
+    double* vp = Vt + (size_t)p * ldv;
+    double* vq = Vt + (size_t)q * ldv;
     double a = 0.0, b = 0.0, g = 0.0;
     for (int c = threadIdx.x; c < n; c += JT) {
-        const double x = gp[c], y = gq[c];
-        a += x * x;
-        b += y * y;
-        g += x * y;
+        const double x = gp[c], y = gq[c], u = vp[c], w = vq[c];
+        a += x * u;
+        b += y * w;
+        g += x * w;
     }
     block_sum3(a, b, g, red);
-    const double ab = sqrt(a) * sqrt(b);
-    const double floor2 = 16.0 * 4.930380657631324e-32 * state[0];  // (4 eps |A|_F)^2
-    if (!(fabs(g) > tol * ab) || ab <= floor2) return;
+    const double ab = sqrt(fabs(a)) * sqrt(fabs(b));
+    const double floor1 = 2.0 * 2.220446049250313e-16 * sqrt((double)n * state[0]);  // 2 sqrt(n) eps |A|_F
+    if (!(fabs(g) > tol * ab) || fabs(g) <= floor1) return;
     const double zeta = (b - a) / (2.0 * g);
     const double t = (zeta >= 0.0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
     const double cs = 1.0 / sqrt(1.0 + t * t), sn = cs * t;
-    double* vp = Vt + (size_t)p * ldv;
-    double* vq = Vt + (size_t)q * ldv;
-    // de Rijk ordering: the row with the larger norm after the rotation goes to the lower index, which sorts the
-    // norms as the sweeps proceed and speeds convergence up markedly on wide spectra
-    const bool swap = (a - t * g) < (b + t * g);
-    double* op = swap ? gq : gp;
-    double* oq = swap ? gp : gq;
-    double* wp = swap ? vq : vp;
-    double* wq = swap ? vp : vq;
+    double *op = gp, *oq = gq, *wp = vp, *wq = vq;
     for (int c = threadIdx.x; c < n; c += JT) {
         const double x = gp[c], y = gq[c];
         op[c] = cs * x - sn * y;

@@ -327,6 +327,119 @@ __global__ void __launch_bounds__(256) k_build_B(const double* __restrict__ px, 
     }
 }
 
+// Separable form of the same assembly (the production kernel).  gridD5512C's sum is
+//   out[iy][ix] = sum_i wy[iy][i] * ( sum_j wx[ix][j] f[yi[iy]-4+i][xi[ix]-4+j] )        (routine.py:313-336)
+// and the inner strip depends on the table row and on ix only.  Output pixels are 1/dscale < 3 table samples
+// apart, so the 10-row windows of consecutive iy overlap heavily: per input pixel the CTA first forms the strips
+// S[r][ix] for every table row r its output column needs (phase 1: ~(n2f/dscale + 10) * n2f strips, global
+// gathers with lanes along ix), then every output is ten fused multiply-adds on S (phase 2, shared memory only).
+// Both phases keep the reference's operation order (strip: j = 0..9, then i = 0..9), so the result is bit-identical
+// to the direct form above while doing ~2.5x fewer loads and multiply-adds, none of them redundant gathers.
+// TI input pixels per CTA so that each output row receives TI contiguous doubles (a full 32-byte sector for TI=4).
+template <int TI>
+__global__ void __launch_bounds__(512) k_build_B_sep(const double* __restrict__ px, const double* __restrict__ py,
+                                                     const int* __restrict__ pcode, int n, int npad,
+                                                     const double* __restrict__ tables,
+                                                     const long long* __restrict__ lut_io, int n_out, int ngrid,
+                                                     double dscale, double nc, int n2f, int mpad, double x0out,
+                                                     double y0out, double* __restrict__ B, int ldb, size_t strideB,
+                                                     int rmax) {
+    extern __shared__ double sm[];
+    double* wx = sm;                                // [TI][n2f][10]
+    double* wy = wx + (size_t)TI * n2f * 10;        // [TI][n2f][10]
+    double* S = wy + (size_t)TI * n2f * 10;         // [TI][rmax][n2f]
+    int* xi = (int*)(S + (size_t)TI * rmax * n2f);  // [TI][n2f], -1 = off grid
+    int* yi = xi + TI * n2f;
+    int* r0 = yi + TI * n2f;  // [TI] first table row of the strip cache
+    int* nr = r0 + TI;        // [TI] rows held (0: nothing to do, > rmax: direct evaluation)
+    const int i0 = blockIdx.x * TI;
+    for (int t = threadIdx.x; t < TI * n2f * 2; t += blockDim.x) {
+        const int isy = t / (TI * n2f);
+        const int u = t - isy * TI * n2f;
+        const int li = u / n2f, k = u - li * n2f;
+        const int i = i0 + li;
+        double w[10];
+        int vi = -1;
+        if (i < n) {
+            const double pin = isy ? py[i] : px[i];
+            const double pout = (isy ? y0out : x0out) + (double)k;  // integer output grid (coadd.py:879-882)
+            const double v = __dadd_rn(__dadd_rn(__ddiv_rn(__dadd_rn(pin, -pout), dscale), nc), 6.0);
+            vi = (int)v;
+            if (d5512_on_grid(vi, ngrid))
+                d5512_getw(w, v - vi - 0.5);
+            else
+                vi = -1;
+        }
+        double* dst = (isy ? wy : wx) + (size_t)u * 10;
+#pragma unroll
+        for (int q = 0; q < 10; q++) dst[q] = vi >= 0 ? w[q] : 0.0;
+        (isy ? yi : xi)[u] = vi;
+    }
+    __syncthreads();
+    if (threadIdx.x < TI) {
+        const int li = threadIdx.x;
+        int lo = 1 << 30, hi = -1;
+        for (int k = 0; k < n2f; k++) {
+            const int v = yi[li * n2f + k];
+            if (v >= 0) {
+                lo = min(lo, v - 4);
+                hi = max(hi, v + 5);
+            }
+        }
+        r0[li] = lo;
+        nr[li] = hi >= 0 ? hi - lo + 1 : 0;
+    }
+    __syncthreads();
+    const int m = n2f * n2f;
+    for (int o = 0; o < n_out; o++) {
+        // phase 1: strips
+        for (int t = threadIdx.x; t < TI * rmax * n2f; t += blockDim.x) {
+            const int li = t / (rmax * n2f);
+            const int u = t - li * rmax * n2f;
+            const int r = u / n2f, ix = u - r * n2f;
+            const int i = i0 + li;
+            if (i >= n || r >= nr[li] || nr[li] > rmax) continue;
+            const int x = xi[li * n2f + ix];
+            const long long off = lut_io[(size_t)pcode[i] * n_out + o];
+            double strip = 0.0;
+            if (x >= 0 && off >= 0) {
+                const double* p = tables + off + (size_t)(r0[li] + r) * ngrid + (x - 4);
+                const double* w = wx + (size_t)(li * n2f + ix) * 10;
+#pragma unroll
+                for (int j = 0; j < 10; j++) strip = fma(w[j], __ldg(p + j), strip);
+            }
+            S[t] = strip;
+        }
+        __syncthreads();
+        // phase 2: outputs, TI contiguous doubles per output row
+        for (int t = threadIdx.x; t < mpad * TI; t += blockDim.x) {
+            const int a = t / TI, li = t - a * TI;
+            const int i = i0 + li;
+            if (i >= npad) continue;
+            double v = 0.0;
+            if (i < n && a < m) {
+                const int iy = a / n2f, ix = a - iy * n2f;
+                const int y = yi[li * n2f + iy], x = xi[li * n2f + ix];
+                if (y >= 0 && x >= 0) {
+                    if (nr[li] <= rmax) {
+                        const double* sp = S + ((size_t)li * rmax + (y - 4 - r0[li])) * n2f + ix;
+                        const double* w = wy + (size_t)(li * n2f + iy) * 10;
+#pragma unroll
+                        for (int q = 0; q < 10; q++) v = fma(sp[q * n2f], w[q], v);
+                    } else {
+                        const long long off = lut_io[(size_t)pcode[i] * n_out + o];
+                        if (off >= 0)
+                            v = d5512_taps(tables + off, ngrid, ngrid, y, x, wx + (size_t)(li * n2f + ix) * 10,
+                                           wy + (size_t)(li * n2f + iy) * 10, 0);
+                    }
+                }
+            }
+            B[o * strideB + (size_t)a * ldb + i] = v;
+        }
+        __syncthreads();
+    }
+}
+
 // Gather of the selected input pixels of one output stamp (coadd.py:969-977): positions, table codes and
 // the n_inframe float32 layers, in the reference's concatenation order given by idx.  Columns n..npad-1
 // of the layer block are zero-filled (they multiply zero columns of T).
@@ -422,19 +535,37 @@ int launch_build_B(const double* px, const double* py, const int* pcode, int n, 
                    const long long* lut_io, int n_out, int ngrid, double dscale, double nc, int n2f, int mpad,
                    double x0out, double y0out, double* B, int ldb, size_t strideB, cudaStream_t s) {
     if (npad <= 0 || mpad <= 0) return 0;
-    constexpr int TI = 16;
     B200_REQUIRE(npad >= n && mpad >= n2f * n2f && ldb >= npad, "build_B: padded sizes too small");
-    const size_t smem = (size_t)TI * n2f * 2 * (10 * sizeof(double) + sizeof(int));
-    B200_REQUIRE(smem <= 220 * 1024, "build_B: n2f too large for the shared-memory weight cache");
     static bool attr_done = false;
     if (!attr_done) {
-        B200_CUDA(cudaFuncSetAttribute(k_build_B<TI>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+        B200_CUDA(cudaFuncSetAttribute(k_build_B<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+        B200_CUDA(cudaFuncSetAttribute(k_build_B_sep<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+        B200_CUDA(cudaFuncSetAttribute(k_build_B_sep<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
         attr_done = true;
     }
+    // rows of the strip cache: the n2f output rows span (n2f - 1) / dscale table rows, plus the 10-row window
+    const int rmax = (int)ceil((n2f - 1) / dscale) + 12;
+    auto sep_smem = [&](int ti) {
+        return (size_t)ti * n2f * 2 * 10 * sizeof(double) + (size_t)ti * rmax * n2f * sizeof(double) +
+               (size_t)(2 * ti * n2f + 2 * ti) * sizeof(int);
+    };
     prof_begin(PROF_BUILD_B, s);
-    k_build_B<TI><<<(unsigned)((npad + TI - 1) / TI), 256, smem, s>>>(px, py, pcode, n, npad, tables, lut_io, n_out,
-                                                                       ngrid, dscale, nc, n2f, mpad, x0out, y0out, B,
-                                                                       ldb, strideB);
+    if (dscale > 0 && sep_smem(4) <= 200 * 1024 && npad % 4 == 0) {
+        k_build_B_sep<4><<<(unsigned)((npad + 3) / 4), 512, sep_smem(4), s>>>(px, py, pcode, n, npad, tables, lut_io, n_out,
+                                                                             ngrid, dscale, nc, n2f, mpad, x0out, y0out,
+                                                                             B, ldb, strideB, rmax);
+    } else if (dscale > 0 && sep_smem(2) <= 200 * 1024 && npad % 2 == 0) {
+        k_build_B_sep<2><<<(unsigned)((npad + 1) / 2), 512, sep_smem(2), s>>>(px, py, pcode, n, npad, tables, lut_io, n_out,
+                                                                             ngrid, dscale, nc, n2f, mpad, x0out, y0out,
+                                                                             B, ldb, strideB, rmax);
+    } else {
+        constexpr int TI = 16;
+        const size_t smem = (size_t)TI * n2f * 2 * (10 * sizeof(double) + sizeof(int));
+        B200_REQUIRE(smem <= 220 * 1024, "build_B: n2f too large for the shared-memory weight cache");
+        k_build_B<TI><<<(unsigned)((npad + TI - 1) / TI), 256, smem, s>>>(px, py, pcode, n, npad, tables, lut_io, n_out,
+                                                                           ngrid, dscale, nc, n2f, mpad, x0out, y0out, B,
+                                                                           ldb, strideB);
+    }
     prof_end(8.0 * n_out * (double)mpad * npad + 20.0 * n, s);
     B200_LAUNCH_CHECK();
     return 0;

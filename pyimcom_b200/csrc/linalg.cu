@@ -262,12 +262,15 @@ __global__ void __launch_bounds__(GT, 1) k_back_update(SolveBatch bt, int kfromt
 // non-positive (or NaN) pivot; the block is still completed with that pivot replaced by 1 so that
 // everything stays finite -- the host checks info and takes the repair branch (lakernel.py:262-279).
 //
-// Factorisation: right-looking over 8-column panels.  Every thread factors the 8x8 diagonal block of
-// the panel redundantly in registers (no barrier inside a panel), threads owning a row below it
-// forward-substitute their 8 entries, then all threads apply the rank-8 update to the trailing block
-// in 4x4 micro-tiles.  Two barriers per panel.
-// Inverse: thread pair per column, x_c = L^-1 e_c by forward substitution; x_c[r] is parked in the
-// unused upper triangle (S[c][r+1]) so one 128x129 array holds both L and L^-1.
+// Right-looking over 8-column panels on the AUGMENTED block [A_kk ; I]: the 128 rows of the identity are
+// carried along as extra right-hand-side rows, so that Z = I L^-T (upper triangular) -- the inverse the
+// panel GEMMs need -- is complete when the factorisation is, with no separate serial substitution phase.
+// Z[r][c] (c >= r) is parked at S[r][c+1], the unused strict upper triangle of the 128x129 array holding A/L.
+// Per panel: every thread factors the 8x8 diagonal block redundantly in registers (rsqrt, no barrier);
+// threads 0..127 forward-substitute the 8 panel entries of the A rows below the panel, threads 128..255
+// those of the Z rows that are non-zero there (rows <= j0+7); then all threads apply the rank-8 update to
+// the trailing A block (lower triangle) and to the trailing columns of those Z rows in 4x4 micro-tiles.
+// Two barriers per panel.
 constexpr int PD = NB + 1;
 constexpr size_t POTRF_SMEM = (size_t)NB * PD * sizeof(double);
 
@@ -280,7 +283,8 @@ __global__ void __launch_bounds__(256, 1) k_potrf_diag(SolveBatch bt, int k) {
     double* Wkk = s.W + (size_t)k * NB * s.ldw + (size_t)k * NB;
     for (int e = tid; e < NB * NB; e += 256) {
         const int r = e >> 7, c = e & 127;
-        S[r * PD + c] = (c <= r) ? Wkk[(size_t)r * s.ldw + c] : 0.0;
+        if (c <= r) S[r * PD + c] = Wkk[(size_t)r * s.ldw + c];
+        if (c >= r) S[r * PD + c + 1] = (c == r) ? 1.0 : 0.0;  // Z = I
     }
     __syncthreads();
     int bad = 0;
@@ -297,9 +301,8 @@ __global__ void __launch_bounds__(256, 1) k_potrf_diag(SolveBatch bt, int k) {
                 if (!bad) bad = k * NB + j0 + c + 1;
                 d = 1.0;
             }
-            const double l = sqrt(d);
-            D[c][c] = l;
-            rinv[c] = 1.0 / l;
+            rinv[c] = rsqrt(d);
+            D[c][c] = d * rinv[c];
 #pragma unroll
             for (int a = c + 1; a < 8; a++) D[a][c] *= rinv[c];
 #pragma unroll
@@ -307,12 +310,15 @@ __global__ void __launch_bounds__(256, 1) k_potrf_diag(SolveBatch bt, int k) {
 #pragma unroll
                 for (int b = c + 1; b <= a; b++) D[a][b] -= D[a][c] * D[b][c];
         }
-        if (tid < NB) {
-            const int r = tid;
-            if (r >= j0 + 8) {
+        {
+            // row (r of A for tid < 128, r of Z otherwise): x[c] = (x[c] - sum_{q<c} x[q] L[c][q]) / L[c][c]
+            const bool isz = tid >= NB;
+            const int r = isz ? tid - NB : tid;
+            double* rowp = S + r * PD + j0 + (isz ? 1 : 0);
+            if (isz ? (r < j0 + 8) : (r >= j0 + 8)) {
                 double row[8];
 #pragma unroll
-                for (int c = 0; c < 8; c++) row[c] = S[r * PD + j0 + c];
+                for (int c = 0; c < 8; c++) row[c] = (!isz || j0 + c >= r) ? rowp[c] : 0.0;  // Z is upper triangular
 #pragma unroll
                 for (int c = 0; c < 8; c++) {
                     double v = row[c];
@@ -320,29 +326,53 @@ __global__ void __launch_bounds__(256, 1) k_potrf_diag(SolveBatch bt, int k) {
                     for (int q = 0; q < c; q++) v -= row[q] * D[c][q];
                     row[c] = v * rinv[c];
                 }
+                if (isz) {
+                    // entries left of the diagonal of Z stay zero by construction; only c >= r is storage of Z
 #pragma unroll
-                for (int c = 0; c < 8; c++) S[r * PD + j0 + c] = row[c];
-            } else if (r >= j0) {
+                    for (int c = 0; c < 8; c++)
+                        if (j0 + c >= r) rowp[c] = row[c];
+                } else {
 #pragma unroll
-                for (int a = 0; a < 8; a++)
-                    if (a == r - j0) {
-#pragma unroll
-                        for (int b = 0; b <= a; b++) S[r * PD + j0 + b] = D[a][b];
-                    }
+                    for (int c = 0; c < 8; c++) rowp[c] = row[c];
+                }
             }
         }
         __syncthreads();
+        if (tid == 255) {
+            // the factored 8x8 block goes back only now: before the barrier slower threads may still be loading
+            // the unfactored block.  One thread, static register indices (a per-thread row select would push D
+            // into local memory); nothing reads these entries again before the final write-out.
+#pragma unroll
+            for (int a = 0; a < 8; a++)
+#pragma unroll
+                for (int b = 0; b <= a; b++) S[(j0 + a) * PD + j0 + b] = D[a][b];
+        }
         const int T0 = j0 + 8;
         const int nt4 = (NB - T0) >> 2;
-        const int cnt = nt4 * (nt4 + 1) / 2;
+        const int cntA = nt4 * (nt4 + 1) / 2;
+        const int cnt = cntA + (T0 >> 2) * nt4;
         for (int t = tid; t < cnt; t += 256) {
-            int bi = (int)((sqrtf(8.0f * (float)t + 1.0f) - 1.0f) * 0.5f);
-            while (bi * (bi + 1) / 2 > t) bi--;
-            while ((bi + 1) * (bi + 2) / 2 <= t) bi++;
-            const int bj = t - bi * (bi + 1) / 2;
-            const double* pa = S + (T0 + 4 * bi) * PD + j0;
-            const double* pb = S + (T0 + 4 * bj) * PD + j0;
-            double* pc = S + (T0 + 4 * bi) * PD + T0 + 4 * bj;
+            const double *pa, *pb;
+            double* pc;
+            int zrow = -1;  // first Z row of the tile (entries left of Z's diagonal are storage of A/L: read as 0)
+            bool diag = false;  // diagonal A tile: only its lower triangle is A's storage (the rest belongs to Z)
+            if (t < cntA) {
+                int bi = (int)((sqrtf(8.0f * (float)t + 1.0f) - 1.0f) * 0.5f);
+                while (bi * (bi + 1) / 2 > t) bi--;
+                while ((bi + 1) * (bi + 2) / 2 <= t) bi++;
+                const int bj = t - bi * (bi + 1) / 2;
+                diag = bi == bj;
+                pa = S + (T0 + 4 * bi) * PD + j0;
+                pb = S + (T0 + 4 * bj) * PD + j0;
+                pc = S + (T0 + 4 * bi) * PD + T0 + 4 * bj;
+            } else {
+                const int u = t - cntA;
+                const int zi = u / nt4, bj = u - zi * nt4;
+                zrow = 4 * zi;
+                pa = S + (4 * zi) * PD + j0 + 1;  // Z rows 4 zi .. 4 zi + 3, panel columns
+                pb = S + (T0 + 4 * bj) * PD + j0;
+                pc = S + (4 * zi) * PD + T0 + 4 * bj + 1;
+            }
             double c4[4][4];
 #pragma unroll
             for (int i = 0; i < 4; i++)
@@ -353,7 +383,7 @@ __global__ void __launch_bounds__(256, 1) k_potrf_diag(SolveBatch bt, int k) {
                 double av[4], bv[4];
 #pragma unroll
                 for (int i = 0; i < 4; i++) {
-                    av[i] = pa[i * PD + q];
+                    av[i] = (zrow < 0 || j0 + q >= zrow + i) ? pa[i * PD + q] : 0.0;
                     bv[i] = pb[i * PD + q];
                 }
 #pragma unroll
@@ -364,47 +394,19 @@ __global__ void __launch_bounds__(256, 1) k_potrf_diag(SolveBatch bt, int k) {
 #pragma unroll
             for (int i = 0; i < 4; i++)
 #pragma unroll
-                for (int j = 0; j < 4; j++) pc[i * PD + j] = c4[i][j];
+                for (int j = 0; j < 4; j++)
+                    if (!diag || j <= i) pc[i * PD + j] = c4[i][j];
         }
         __syncthreads();
     }
     if (tid == 0 && bad && *s.info == 0) *s.info = bad;
-    // L back to global (lower triangle of the diagonal block)
-    for (int e = tid; e < NB * NB; e += 256) {
-        const int r = e >> 7, c = e & 127;
-        if (c <= r) Wkk[(size_t)r * s.ldw + c] = S[r * PD + c];
-    }
-    // inverse: columns c = tid/2, the two threads of a pair split the dot product over q
-    {
-        const int c = tid >> 1, h = tid & 1;
-        double* xc = S + c * PD + 1;  // xc[r] = (L^-1)[r][c], r >= c
-        for (int r = 0; r < NB; r++) {
-            if (r >= c) {
-                const double* Lr = S + r * PD;
-                double s0 = 0.0, s1 = 0.0;
-                int q = c + h;
-                for (; q + 2 < r; q += 4) {
-                    s0 += Lr[q] * xc[q];
-                    s1 += Lr[q + 2] * xc[q + 2];
-                }
-                if (q < r) s0 += Lr[q] * xc[q];
-                double sum = s0 + s1;
-                sum += __shfl_xor_sync(0xffffffffu, sum, 1);
-                const double x = ((r == c ? 1.0 : 0.0) - sum) / Lr[r];
-                if (h == 0) xc[r] = x;
-            } else {
-                (void)__shfl_xor_sync(0xffffffffu, 0.0, 1);
-            }
-            __syncwarp();
-        }
-    }
-    __syncthreads();
     double* Di = s.Dinv + (size_t)k * NB * NB;
     double* Dt = s.Dinv + (size_t)(nb + k) * NB * NB;
     for (int e = tid; e < NB * NB; e += 256) {
         const int r = e >> 7, c = e & 127;
-        Di[e] = (c <= r) ? S[c * PD + r + 1] : 0.0;  // inv(L)[r][c]
-        Dt[e] = (r <= c) ? S[r * PD + c + 1] : 0.0;  // inv(L)^T[r][c] = inv(L)[c][r]
+        if (c <= r) Wkk[(size_t)r * s.ldw + c] = S[r * PD + c];  // L, lower triangle of the diagonal block
+        Dt[e] = (r <= c) ? S[r * PD + c + 1] : 0.0;              // inv(L)^T[r][c] = Z[r][c]
+        Di[e] = (c <= r) ? S[c * PD + r + 1] : 0.0;              // inv(L)[r][c] = Z[c][r]
     }
 }
 

@@ -161,25 +161,39 @@ def _padded_system(ds: DeviceSystem, incs):
     return W
 
 
-def _chol_with_repair(ds: DeviceSystem, inc_lists, j_out):
-    """Factor + solve the systems A + sum(incs) for every increment list; repair branch of
-    CholKernel._cholesky_wrapper (lakernel.py:262-279) on failure.  Returns the list of solutions X_k."""
-    Ws = [_padded_system(ds, incs) for incs in inc_lists]
-    Xs = [ds.mB[j_out].clone() for _ in inc_lists]
-    info, _keep = chol_solve_batch(Ws, Xs)
-    bad = info.cpu().numpy()
+def _chol_solve_items(items):
+    """Factor + solve A_k + sum(incs_k) for every item (ds, incs, j_out); the systems of all items go through
+    the batched factorisation together (up to MAXB per launch sequence) and the LAPACK-style info codes are read
+    back once.  Failing items take the repair branch of CholKernel._cholesky_wrapper (lakernel.py:262-279).
+    Returns the list of solutions X_k (mpad, npad), rows = Ti."""
+    Ws = [_padded_system(ds, incs) for ds, incs, _ in items]
+    Xs = [ds.mB[j].clone() for ds, _, j in items]
+    infos = []
+    for c0 in range(0, len(items), _lib.MAXB):
+        info, _keep = chol_solve_batch(Ws[c0:c0 + _lib.MAXB], Xs[c0:c0 + _lib.MAXB])
+        infos.append(info)
+    del Ws
+    bad = torch.cat(infos).cpu().numpy()
     if bad.any():
-        lam, _, _ = eigh_device(ds.A.clone(), ds.n)
-        w0 = float(lam[: ds.n].min().item())
-        shift = abs(w0) + 1e-16
+        shifts = {}
         for k in np.nonzero(bad)[0]:
+            ds, incs, j = items[k]
+            if id(ds) not in shifts:  # one eigh per stamp serves all of its failing nodes
+                lam, _, _ = eigh_device(ds.A.clone(), ds.n)
+                shifts[id(ds)] = float(lam[: ds.n].min().item())
+            w0 = shifts[id(ds)]
             warnings.warn(f"CholKernel: repaired negative eigenvalue {w0:19.12e}", stacklevel=3)
-            Ws[k] = _padded_system(ds, list(inc_lists[k]) + [shift])
-            Xs[k] = ds.mB[j_out].clone()
-            info2, _keep2 = chol_solve_batch([Ws[k]], [Xs[k]])
+            W = _padded_system(ds, list(incs) + [abs(w0) + 1e-16])
+            Xs[k] = ds.mB[j].clone()
+            info2, _keep2 = chol_solve_batch([W], [Xs[k]])
             if int(info2.item()) != 0:
                 raise np.linalg.LinAlgError("Cholesky failed after the eigenvalue repair")
     return Xs
+
+
+def _chol_with_repair(ds: DeviceSystem, inc_lists, j_out):
+    """Single-stamp form of _chol_solve_items: the systems A + sum(incs) for every increment list."""
+    return _chol_solve_items([(ds, incs, j_out) for incs in inc_lists])
 
 
 def _node_reduce(ds, j_out, Tpi, kappa_arr, kappaC_arr, ucmin, smax, Epq_in=None):
@@ -205,25 +219,36 @@ def _node_reduce(ds, j_out, Tpi, kappa_arr, kappaC_arr, ucmin, smax, Epq_in=None
                         extras=dict(Dp=Dp, Npq=Npq, Epq=Epq, out_w=ow, iv=iv, branch=br))
 
 
+def solve_chol_batch(dss, cfg, j_out: int):
+    """CholKernel for one output PSF of several output stamps at once (lakernel.py:281-394): the nv systems of
+    every stamp share one batched factorisation.  Returns one KernelOutput per stamp."""
+    kappaC = np.asarray(cfg.kappaC_arr, dtype=np.float64)
+    nv = kappaC.size
+    items = []
+    for ds in dss:
+        kappa_arr = kappaC * float(ds.C[j_out])
+        if nv == 1:
+            items.append((ds, [float(kappa_arr[0])] if kappa_arr[0] else [], j_out))
+            continue
+        run = []
+        for p in range(nv):  # cumulative diagonal increments (lakernel.py:356)
+            run.append(float(kappa_arr[p] - (kappa_arr[p - 1] if p > 0 else 0)))
+            items.append((ds, list(run), j_out))
+    Xs = _chol_solve_items(items)
+    outs = []
+    for q, ds in enumerate(dss):
+        kappa_arr = kappaC * float(ds.C[j_out])
+        if nv == 1:
+            outs.append(KernelOutput(Tpi=Xs[q].unsqueeze(0), w=None, kappa_scalar=float(kappa_arr[0])))
+        else:
+            Tpi = torch.stack(Xs[q * nv:(q + 1) * nv])
+            outs.append(_node_reduce(ds, j_out, Tpi, kappa_arr, kappaC, cfg.uctarget, cfg.sigmamax))
+    return outs
+
+
 def solve_chol(ds: DeviceSystem, cfg, j_out: int) -> KernelOutput:
     """CholKernel for one output PSF (lakernel.py:281-394)."""
-    kappaC = np.asarray(cfg.kappaC_arr, dtype=np.float64)
-    Cj = float(ds.C[j_out])
-    if kappaC.size == 1:
-        kap = float(kappaC[0] * Cj)
-        (X,) = _chol_with_repair(ds, [[kap] if kap else []], j_out)
-        return KernelOutput(Tpi=X.unsqueeze(0), w=None, kappa_scalar=kap)
-    kappa_arr = kappaC * Cj
-    inc_lists = []
-    run = []
-    for p in range(kappaC.size):  # cumulative diagonal increments (lakernel.py:356)
-        run.append(float(kappa_arr[p] - (kappa_arr[p - 1] if p > 0 else 0)))
-        inc_lists.append(list(run))
-    Xs = []
-    for c0 in range(0, len(inc_lists), _lib.MAXB):
-        Xs += _chol_with_repair(ds, inc_lists[c0:c0 + _lib.MAXB], j_out)
-    Tpi = torch.stack(Xs)
-    return _node_reduce(ds, j_out, Tpi, kappa_arr, kappaC, cfg.uctarget, cfg.sigmamax)
+    return solve_chol_batch([ds], cfg, j_out)[0]
 
 
 def eigen_decompose(ds: DeviceSystem):

@@ -136,8 +136,18 @@ def test_lakernel1_and_lsolve(gr):
     # gauge-invariant product T @ Q^T (lakernel.py:223)
     rk, rS, rU, rT = np.zeros(m), np.zeros(m), np.zeros(m), np.zeros((m, n))
     R.lakernel1(lam, Q, mPhalf, Cn, 1e-8, 1e-16, 1e16, 53, rk, rS, rU, rT, 0.5)
-    assert np.array_equal(kappa, rk)  # P-discrete: same 53 bisection branches
-    assert np.abs(T - rT).max() < 1e-8 * np.abs(rT).max()
+    # 53 halvings of log(factor) end below float64 resolution, where the last branches are decided by the rounding
+    # of the n-term sums: the GPU's tree reduction and the serial CPU sum may then part ways at the 1e-8 level
+    assert np.abs(kappa - rk).max() < 1e-7 * rk.max()
+    # P-discrete at the production depth (nbis = 13, lakernel.py:174): kappa sits on the lattice
+    # sqrt(kmin kmax) * factor^(+-1/2 +-1/4 ...), so equal branch words <=> equal kappa up to rounding of the products
+    k13, r13 = np.zeros(m), np.zeros(m)
+    S_, U_, T13, rT13 = np.zeros(m), np.zeros(m), np.zeros((m, n)), np.zeros((m, n))
+    G.lakernel1(lam, Q, mPhalf, Cn, 1e-8, 1e-16, 1e16, 13, k13, S_, U_, T13, 0.5)
+    R.lakernel1(lam, Q, mPhalf, Cn, 1e-8, 1e-16, 1e16, 13, r13, S_, U_, rT13, 0.5)
+    assert np.abs(k13 / r13 - 1).max() < 1e-13
+    assert np.abs(T13 - rT13).max() < 1e-12 * np.abs(rT13).max()  # same kappa => T = P/(lam+kappa) to rounding
+    assert np.abs(T - rT).max() < 1e-7 * np.abs(rT).max()  # nbis = 53: follows the 1e-8 kappa wobble above
     assert np.abs((T @ Q.T)[::25, ::33] - gr["lk1_TQt_sub"]).max() < 1e-8
     # float32 outputs, as lakernel.py:216-218 passes them
     k32, S32, U32 = (np.zeros(m, dtype=np.float32) for _ in range(3))
@@ -224,10 +234,11 @@ def test_eigh_device():
     ds = GL.upload_system(A, np.zeros((1, 4, n)), [1.0], 2)
     lam, Vt, sweeps = GL.eigh_device(ds.A.clone(), n)
     lam, V = lam[:n].cpu().numpy(), Vt[:n, :n].cpu().numpy().T
-    assert np.abs(np.sort(lam) - np.linalg.eigvalsh(A)).max() < 1e-13
+    # absolute accuracy class of LAPACK's eigh: a small multiple of sqrt(n) eps |A|_F (|A|_F ~ 5 here)
+    assert np.abs(np.sort(lam) - np.linalg.eigvalsh(A)).max() < 5e-13
     assert np.abs(V.T @ V - np.eye(n)).max() < 1e-12
-    assert np.abs(A @ V - V * lam).max() < 1e-13
-    assert 0 < sweeps < 25
+    assert np.abs(A @ V - V * lam).max() < 5e-13
+    assert 0 < sweeps < 40
 
 
 # ---------------------------------------------------------------------------------------------------
