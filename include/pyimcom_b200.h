@@ -98,10 +98,14 @@ int b200_dev_gather_stamp(const int* idx, int n, int npad, const double* src_x, 
 /* A (npad x lda) for one output stamp: replaces PSFOvl._call_ii_self/_call_ii_cross (psfutil.py:1401-1495,
  * 1597-1732) and the 9+36 block scatter of OutStamp._build_system_matrices (coadd.py:1028-1069).
  * px,py (n): positions in output pixels; pcode (n): local_group*nimg + image; lut (ncode*ncode).
- * Entries with index >= n form an identity block; diag_add is added to the first n diagonal entries. */
+ * Entries with index >= n form an identity block; diag_add is added to the first n diagonal entries.
+ * poly == 0: the tables referenced by lut are row-major (ngrid x ngrid).  poly == P > 0 (P = oversamp, the native
+ * pixel pitch in table samples): they are stored polyphase, T'[y % P][x % P][y / P][x / P] with planes of
+ * ncell x ncell doubles, ncell = ceil(ngrid / P), i.e. P*P*ncell*ncell doubles per table -- neighbouring input
+ * pixels then read neighbouring doubles.  Same values, same arithmetic order, bit-identical results. */
 int b200_dev_build_A(const double* px, const double* py, const int* pcode, int n, int npad, const double* tables,
                      const b200_table_ref* lut, int nimg, int ncode, int ngrid, double dscale, double nc,
-                     double flat_penalty, double* A, int lda, double diag_add, void* stream);
+                     double flat_penalty, double* A, int lda, double diag_add, int poly, void* stream);
 /* mBhalf (n_out, mpad, ldb) for one output stamp: replaces PSFOvl._call_io_cross (psfutil.py:1497-1595) and
  * coadd.py:1075-1082.  lut_io (ncode*n_out) table offsets (<0 absent); output pixel (iy,ix) sits at
  * (x0out + ix, y0out + iy) (coadd.py:879-882).  Padding rows/columns are zero-filled. */

@@ -43,29 +43,48 @@ def h2d(a: np.ndarray) -> torch.Tensor:
     return t.pin_memory().to("cuda", non_blocking=True)
 
 
-class _Arena:
-    """PSF-overlap tables in HBM: each table set is stored once, zero-padded by 6 (np.pad(ovl, 6), psfutil.py:1471)."""
+POLY_PERIODS = (2, 3, 4, 5, 6, 8, 10, 12, 16)  # instantiations of the polyphase A-assembly kernel
 
-    def __init__(self, nsamp_ovl):
+
+class _Arena:
+    """PSF-overlap tables in HBM: each table set is stored once, zero-padded by 6 (np.pad(ovl, 6), psfutil.py:1471).
+
+    In-out tables (read by the mBhalf kernel along the dense output grid) stay row-major.  In-in tables (read by
+    the A kernel at positions one native pixel = ``poly`` table samples apart) are stored polyphase,
+    ``T'[y % P][x % P][y // P][x // P]``, so that a warp's 32 neighbouring input pixels read neighbouring doubles
+    (include/pyimcom_b200.h, b200_dev_build_A)."""
+
+    def __init__(self, nsamp_ovl, poly=0):
         self.ngrid = nsamp_ovl + 12
+        self.poly = int(poly) if int(poly) in POLY_PERIODS else 0
+        self.ncell = -(-self.ngrid // self.poly) if self.poly else 0
         self.chunks = []
         self.base = {}
+        self.stride = {}
         self.size = 0
         self._keep = []
 
-    def offset(self, arr, idx):
+    def offset(self, arr, idx, poly=False):
         """Offset (in doubles) of table arr[idx] inside the arena; registers arr on first use."""
-        key = id(arr)
+        poly = bool(poly and self.poly)
+        key = (id(arr), poly)
         if key not in self.base:
             self.base[key] = self.size
             self._keep.append(arr)  # ids stay unique while the arrays are alive
             lead = int(np.prod(arr.shape[:-2]))
-            pad = np.zeros((lead, self.ngrid, self.ngrid))
-            pad[:, 6:-6, 6:-6] = arr.reshape(lead, arr.shape[-2], arr.shape[-1])
+            if poly:
+                P, nc = self.poly, self.ncell
+                pad = np.zeros((lead, nc * P, nc * P))
+                pad[:, 6:6 + arr.shape[-2], 6:6 + arr.shape[-1]] = arr.reshape(lead, arr.shape[-2], arr.shape[-1])
+                pad = np.ascontiguousarray(pad.reshape(lead, nc, P, nc, P).transpose(0, 2, 4, 1, 3))
+            else:
+                pad = np.zeros((lead, self.ngrid, self.ngrid))
+                pad[:, 6:-6, 6:-6] = arr.reshape(lead, arr.shape[-2], arr.shape[-1])
+            self.stride[key] = pad.size // lead
             self.chunks.append(pad.reshape(-1))
             self.size += pad.size
         flat = int(np.ravel_multi_index(idx, arr.shape[:-2]))
-        return self.base[key] + flat * self.ngrid * self.ngrid
+        return self.base[key] + flat * self.stride[key]
 
     def upload(self):
         if not self.chunks:
@@ -94,6 +113,8 @@ class GpuBlock:
         self.plans = {}
         self.order = []
         self._uploaded = False
+        # period of the polyphase in-in tables = native pixel pitch in table samples = oversamp (psfutil.py:610)
+        self.poly = int(getattr(self.cfg, "oversamp", 0))
 
     # ---------------------------------------------------------------------------------------------
     # host-side planning (coadd.py:846-977)
@@ -183,14 +204,14 @@ class GpuBlock:
                 tab.group(Gb)
                 t, tidx, flip = tab.table_ii_ref(Ga, ka, Gb, kb)
                 n_in = len(tab.grp_imgs[Ga]) if Ga == Gb else (len(tab.grp_imgs[Ga]) * len(tab.grp_imgs[Gb])) ** 0.5
-                lut[ca, cb] = (self.arena.offset(t, tidx), int(flip), 0, cfg.flat_penalty / n_in)
+                lut[ca, cb] = (self.arena.offset(t, tidx, poly=True), int(flip), 0, cfg.flat_penalty / n_in)
         p.lut, p.lut_io = lut, lut_io
         return p
 
     def prepare(self, stamps=None):
         """Plan the requested OutStamps (default: the whole block in the reference's 2x2-group order) and upload."""
         self._global_pixels()
-        self.arena = _Arena(self.cfg.nsamp_ovl)
+        self.arena = _Arena(self.cfg.nsamp_ovl, poly=self.poly)
         self.order = list(stamps) if stamps is not None else list(self.blk.stamp_order())
         self.plans = {ji: self.plan_stamp(*ji) for ji in self.order}
         self.upload()
@@ -262,7 +283,7 @@ class GpuBlock:
         ncode = 4 * nimg
         _lib.dev_build_A(ptr(px), ptr(py), ptr(pcode), n, npad, ptr(self.d_tables), ptr(self.d_lut[k]), nimg, ncode,
                          self.arena.ngrid, float(cfg.dscale), float(cfg.nc_ovl), float(cfg.flat_penalty), ptr(A),
-                         A.stride(0), 0.0, st)
+                         A.stride(0), 0.0, self.arena.poly, st)
         mB = torch.empty((cfg.n_out, mpad, npad), dtype=torch.float64, device="cuda")
         _lib.dev_build_B(ptr(px), ptr(py), ptr(pcode), n, npad, ptr(self.d_tables), ptr(self.d_lut_io[k]), cfg.n_out,
                          self.arena.ngrid, float(cfg.dscale), float(cfg.nc_ovl), cfg.n2f, mpad, p.x0out, p.y0out, ptr(mB),

@@ -286,9 +286,9 @@ int b200_dev_gather_stamp(const int* idx, int n, int npad, const double* sx, con
 }
 int b200_dev_build_A(const double* px, const double* py, const int* pcode, int n, int npad, const double* tables,
                      const b200_table_ref* lut, int nimg, int ncode, int ngrid, double dscale, double nc,
-                     double flat_penalty, double* A, int lda, double diag_add, void* s) {
+                     double flat_penalty, double* A, int lda, double diag_add, int poly, void* s) {
     return launch_build_A(px, py, pcode, n, npad, tables, lut, nimg, ncode, ngrid, dscale, nc, flat_penalty, A, lda,
-                          diag_add, ST(s));
+                          diag_add, poly, ST(s));
 }
 int b200_dev_build_B(const double* px, const double* py, const int* pcode, int n, int npad, const double* tables,
                      const long long* lut_io, int n_out, int ngrid, double dscale, double nc, int n2f, int mpad,

@@ -89,6 +89,45 @@ __device__ __forceinline__ double d5512_taps(const double* __restrict__ g, int n
     return acc;
 }
 
+// ---- polyphase table layout (A assembly) -------------------------------------------------------------------------
+// The native pixel pitch of the input images is exactly P = oversamp table samples (dscale = pitch / P,
+// psfutil.py:610), so the 32 consecutive input pixels a warp handles read table positions that are ~P samples
+// apart: in the row-major table every lane touches its own cache line.  The assembly kernel therefore reads the
+// PSF-overlap tables in a polyphase layout  T'[y mod P][x mod P][y / P][x / P]  (planes of ncell x ncell doubles,
+// ncell = ceil(ngrid / P)): lanes whose positions differ by P samples now read neighbouring doubles of one plane.
+// The re-layout is done once per table when the arena is built; values and the order of the arithmetic are
+// untouched, so the result is bit-identical to the row-major path.
+template <int P>
+struct PolyOff {
+    int ox[10], oy[10];
+    // integer corner (yi-4, xi-4); flip mirrors both axes (np.flip of the table, psfutil.py:1659-1665)
+    __device__ __forceinline__ PolyOff(int yi, int xi, int ngrid, int ncell, int flip) {
+        const int plane = ncell * ncell;
+#pragma unroll
+        for (int j = 0; j < 10; j++) {
+            const int x = flip ? ngrid - 1 - (xi - 4 + j) : xi - 4 + j;
+            const int y = flip ? ngrid - 1 - (yi - 4 + j) : yi - 4 + j;
+            ox[j] = (x % P) * plane + x / P;
+            oy[j] = (y % P) * (P * plane) + (y / P) * ncell;
+        }
+    }
+};
+
+template <int P>
+__device__ __forceinline__ double d5512_taps_poly(const double* __restrict__ g, const PolyOff<P>& o, const double* wx,
+                                                  const double* wy) {
+    double acc = 0.0;
+#pragma unroll
+    for (int i = 0; i < 10; i++) {
+        const double* p = g + o.oy[i];
+        double strip = 0.0;
+#pragma unroll
+        for (int j = 0; j < 10; j++) strip = fma(wx[j], __ldg(p + o.ox[j]), strip);
+        acc = fma(strip, wy[i], acc);
+    }
+    return acc;
+}
+
 // ------------------------------------------------------------------------------------------------
 // iD5512C: routine.py:125-181.  One thread per scattered point, all layers.
 // ------------------------------------------------------------------------------------------------
@@ -189,6 +228,7 @@ __global__ void __launch_bounds__(256) k_gridD5512C(const double* __restrict__ f
 // One CTA per upper-triangular 32x32 tile; the mirrored tile is written through shared memory so
 // both stores are row-contiguous.
 // ------------------------------------------------------------------------------------------------
+template <int P>  // P == 0: row-major tables; P > 0: polyphase tables of period P
 __global__ void __launch_bounds__(256) k_build_A(const double* __restrict__ px, const double* __restrict__ py,
                                                  const int* __restrict__ pcode, int n, int npad,
                                                  const double* __restrict__ tables, const TableRef* __restrict__ lut,
@@ -236,7 +276,12 @@ __global__ void __launch_bounds__(256) k_build_A(const double* __restrict__ px, 
                     double wx[10], wy[10];
                     d5512_getw(wx, x - xi - 0.5);
                     d5512_getw(wy, y - yi - 0.5);
-                    v = d5512_taps(tables + tr.offset, ngrid, ngrid, yi, xi, wx, wy, tr.flip);
+                    if (P > 0) {
+                        const PolyOff<(P > 0 ? P : 1)> po(yi, xi, ngrid, (ngrid + P - 1) / (P > 0 ? P : 1), tr.flip);
+                        v = d5512_taps_poly(tables + tr.offset, po, wx, wy);
+                    } else {
+                        v = d5512_taps(tables + tr.offset, ngrid, ngrid, yi, xi, wx, wy, tr.flip);
+                    }
                 }
                 if (flat_penalty != 0.0) {  // psfutil.py:1483-1486, 1705-1708
                     v = __dadd_rn(v, -tr.penalty_sub);
@@ -518,14 +563,31 @@ int launch_gather_stamp(const int* idx, int n, int npad, const double* src_x, co
 
 int launch_build_A(const double* px, const double* py, const int* pcode, int n, int npad, const double* tables,
                    const TableRef* lut, int nimg, int ncode, int ngrid, double dscale, double nc, double flat_penalty,
-                   double* A, int lda, double diag_add, cudaStream_t s) {
+                   double* A, int lda, double diag_add, int poly, cudaStream_t s) {
     if (npad <= 0) return 0;
     B200_REQUIRE(npad % 32 == 0 && npad >= n && lda >= npad, "build_A: npad must be a multiple of 32, >= n, <= lda");
     const long nt = npad / 32;
     const long ntri = nt * (nt + 1) / 2;
     prof_begin(PROF_BUILD_A, s);
-    k_build_A<<<(unsigned)ntri, 256, 0, s>>>(px, py, pcode, n, npad, tables, lut, nimg, ncode, ngrid, dscale, nc,
-                                             flat_penalty, A, lda, diag_add);
+#define B200_BUILD_A(PP)                                                                                           \
+    k_build_A<PP><<<(unsigned)ntri, 256, 0, s>>>(px, py, pcode, n, npad, tables, lut, nimg, ncode, ngrid, dscale, nc, \
+                                                 flat_penalty, A, lda, diag_add)
+    switch (poly) {
+        case 0: B200_BUILD_A(0); break;
+        case 2: B200_BUILD_A(2); break;
+        case 3: B200_BUILD_A(3); break;
+        case 4: B200_BUILD_A(4); break;
+        case 5: B200_BUILD_A(5); break;
+        case 6: B200_BUILD_A(6); break;
+        case 8: B200_BUILD_A(8); break;
+        case 10: B200_BUILD_A(10); break;
+        case 12: B200_BUILD_A(12); break;
+        case 16: B200_BUILD_A(16); break;
+        default:
+            set_error("build_A: no polyphase instantiation for period %d (0, 2-6, 8, 10, 12, 16)", poly);
+            return -1;
+    }
+#undef B200_BUILD_A
     prof_end(8.0 * npad * (double)npad + 20.0 * n, s);  // bytes: the matrix written once + positions/codes read
     B200_LAUNCH_CHECK();
     return 0;

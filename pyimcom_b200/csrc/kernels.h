@@ -37,7 +37,7 @@ int launch_gather_stamp(const int* idx, int n, int npad, const double* src_x, co
                         float* indata, int ldi, cudaStream_t s);
 int launch_build_A(const double* px, const double* py, const int* pcode, int n, int npad, const double* tables,
                    const TableRef* lut, int nimg, int ncode, int ngrid, double dscale, double nc, double flat_penalty,
-                   double* A, int lda, double diag_add, cudaStream_t s);
+                   double* A, int lda, double diag_add, int poly, cudaStream_t s);
 int launch_build_B(const double* px, const double* py, const int* pcode, int n, int npad, const double* tables,
                    const long long* lut_io, int n_out, int ngrid, double dscale, double nc, int n2f, int mpad,
                    double x0out, double y0out, double* B, int ldb, size_t strideB, cudaStream_t s);
