@@ -88,6 +88,13 @@ typedef struct b200_table_ref {
     double penalty_sub; /* flat_penalty / n_in of this PSF-group pair (psfutil.py:1484, 1706) */
 } b200_table_ref;
 
+/* PSF-overlap tables as the host holds them, src (ntab, ns, ns), into the layout the assembly kernels read: each
+ * table zero-padded by pad on every side (np.pad(ovl, 6), psfutil.py:1471, 1580, 1696) to ngrid = ns + 2 pad,
+ * row-major (poly == 0: ngrid*ngrid doubles per table) or polyphase of period poly (see b200_dev_build_A:
+ * poly*poly*ncell*ncell doubles per table, ncell = ceil(ngrid / poly)). */
+int b200_dev_layout_tables(const double* src, int ntab, int ns, int pad, int ngrid, int poly, double* dst,
+                           void* stream);
+
 /* Gather the selected input pixels of one output stamp (coadd.py:969-977): out[k] = src[idx[k]] for positions,
  * codes (src_code/pcode may both be NULL) and the n_inframe float32 layers (src_data (n_inframe, src_ld) ->
  * indata (n_inframe, ldi), zero padded). */

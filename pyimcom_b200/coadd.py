@@ -55,41 +55,39 @@ class _Arena:
     (include/pyimcom_b200.h, b200_dev_build_A)."""
 
     def __init__(self, nsamp_ovl, poly=0):
+        self.ns = nsamp_ovl
         self.ngrid = nsamp_ovl + 12
         self.poly = int(poly) if int(poly) in POLY_PERIODS else 0
         self.ncell = -(-self.ngrid // self.poly) if self.poly else 0
-        self.chunks = []
+        self.sets = []  # (array, lead, poly period, base offset)
         self.base = {}
         self.stride = {}
         self.size = 0
-        self._keep = []
 
     def offset(self, arr, idx, poly=False):
         """Offset (in doubles) of table arr[idx] inside the arena; registers arr on first use."""
-        poly = bool(poly and self.poly)
-        key = (id(arr), poly)
+        P = self.poly if poly else 0
+        key = (id(arr), P)
         if key not in self.base:
-            self.base[key] = self.size
-            self._keep.append(arr)  # ids stay unique while the arrays are alive
+            assert arr.shape[-1] == self.ns and arr.shape[-2] == self.ns
             lead = int(np.prod(arr.shape[:-2]))
-            if poly:
-                P, nc = self.poly, self.ncell
-                pad = np.zeros((lead, nc * P, nc * P))
-                pad[:, 6:6 + arr.shape[-2], 6:6 + arr.shape[-1]] = arr.reshape(lead, arr.shape[-2], arr.shape[-1])
-                pad = np.ascontiguousarray(pad.reshape(lead, nc, P, nc, P).transpose(0, 2, 4, 1, 3))
-            else:
-                pad = np.zeros((lead, self.ngrid, self.ngrid))
-                pad[:, 6:-6, 6:-6] = arr.reshape(lead, arr.shape[-2], arr.shape[-1])
-            self.stride[key] = pad.size // lead
-            self.chunks.append(pad.reshape(-1))
-            self.size += pad.size
+            self.base[key] = self.size
+            self.stride[key] = P * P * self.ncell * self.ncell if P else self.ngrid * self.ngrid
+            self.sets.append((arr, lead, P, self.size))  # keeps arr alive: ids stay unique
+            self.size += lead * self.stride[key]
         flat = int(np.ravel_multi_index(idx, arr.shape[:-2]))
         return self.base[key] + flat * self.stride[key]
 
     def upload(self):
-        if not self.chunks:
-            return torch.zeros(1, dtype=torch.float64, device="cuda")
-        return h2d(np.concatenate(self.chunks))
+        """Raw tables go up as they are (one pinned copy per table set); padding and re-layout happen on the device."""
+        dst = torch.empty(max(1, self.size), dtype=torch.float64, device="cuda")
+        self.h2d_bytes = 0
+        st = stream_handle()
+        for arr, lead, P, base in self.sets:
+            src = h2d(np.asarray(arr, dtype=np.float64).reshape(lead, self.ns, self.ns))
+            self.h2d_bytes += src.numel() * 8
+            _lib.dev_layout_tables(ptr(src), lead, self.ns, 6, self.ngrid, P, C.c_void_p(dst.data_ptr() + 8 * base), st)
+        return dst
 
 
 class StampPlan:
@@ -193,28 +191,41 @@ class GpuBlock:
         lut["offset"] = -1
         lut_io = np.full((ncode, cfg.n_out), -1, dtype=np.int64)
         present = np.unique(p.pcode)
-        for ca in present:
-            Ga, ka = groups[ca // nimg], int(ca % nimg)
-            tab.group(Ga)
-            io = tab.get_io(Ga)
-            for o in range(cfg.n_out):
-                lut_io[ca, o] = self.arena.offset(io, (tab.grp_index(Ga, ka), o))
-            for cb in present:
-                Gb, kb = groups[cb // nimg], int(cb % nimg)
-                tab.group(Gb)
-                t, tidx, flip = tab.table_ii_ref(Ga, ka, Gb, kb)
-                n_in = len(tab.grp_imgs[Ga]) if Ga == Gb else (len(tab.grp_imgs[Ga]) * len(tab.grp_imgs[Gb])) ** 0.5
-                lut[ca, cb] = (self.arena.offset(t, tidx, poly=True), int(flip), 0, cfg.flat_penalty / n_in)
+        pair, io_c = self._pair_cache, self._io_cache  # (group, image) look-ups are shared by neighbouring stamps
+        gk = [(groups[c // nimg], int(c % nimg)) for c in present]
+        rows = []
+        for ca, (Ga, ka) in zip(present, gk):
+            if (Ga, ka) not in io_c:
+                tab.group(Ga)
+                io = tab.get_io(Ga)
+                io_c[(Ga, ka)] = [self.arena.offset(io, (tab.grp_index(Ga, ka), o)) for o in range(cfg.n_out)]
+            lut_io[ca, :] = io_c[(Ga, ka)]
+            for (Gb, kb) in gk:
+                key = (Ga, ka, Gb, kb)
+                if key not in pair:
+                    tab.group(Gb)
+                    t, tidx, flip = tab.table_ii_ref(Ga, ka, Gb, kb)
+                    n_in = len(tab.grp_imgs[Ga]) if Ga == Gb else (len(tab.grp_imgs[Ga]) * len(tab.grp_imgs[Gb])) ** 0.5
+                    pair[key] = (self.arena.offset(t, tidx, poly=True), int(flip), 0, cfg.flat_penalty / n_in)
+                rows.append(pair[key])
+        if rows:
+            lut[np.ix_(present, present)] = np.array(rows, dtype=TABLEREF_DTYPE).reshape(len(present), len(present))
         p.lut, p.lut_io = lut, lut_io
         return p
 
     def prepare(self, stamps=None):
         """Plan the requested OutStamps (default: the whole block in the reference's 2x2-group order) and upload."""
+        import time
+
+        t0 = time.perf_counter()
         self._global_pixels()
         self.arena = _Arena(self.cfg.nsamp_ovl, poly=self.poly)
+        self._pair_cache, self._io_cache = {}, {}
         self.order = list(stamps) if stamps is not None else list(self.blk.stamp_order())
         self.plans = {ji: self.plan_stamp(*ji) for ji in self.order}
+        t1 = time.perf_counter()
         self.upload()
+        self.host_seconds = {"plan": t1 - t0, "upload_enqueue": time.perf_counter() - t1}
         return self
 
     def upload(self):
@@ -238,9 +249,9 @@ class GpuBlock:
         lut_io = np.stack([p.lut_io for p in plans]) if plans else np.zeros((0, 1, 1), dtype=np.int64)
         self.d_lut_io = h2d(np.ascontiguousarray(lut_io))
         self.d_fade_w = h2d(trapezoid_weights(cfg.fade_kernel)) if cfg.fade_kernel > 0 else None
-        self.h2d_bytes = sum(t.numel() * t.element_size() for t in (self.d_x, self.d_y, self.d_data, self.d_tables,
-                                                                     self.d_idx, self.d_pcode_all, self.d_seg_end,
-                                                                     self.d_seg_img, self.d_lut, self.d_lut_io))
+        self.h2d_bytes = self.arena.h2d_bytes + sum(
+            t.numel() * t.element_size() for t in (self.d_x, self.d_y, self.d_data, self.d_idx, self.d_pcode_all,
+                                                   self.d_seg_end, self.d_seg_img, self.d_lut, self.d_lut_io))
         self.reset_maps()
         self._uploaded = True
 

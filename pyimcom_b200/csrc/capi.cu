@@ -279,6 +279,9 @@ int b200_dev_gridD5512C(const double* f, int ngy, int ngx, const double* x, cons
                         double* out, void* s) {
     return launch_gridD5512C(f, ngy, ngx, x, y, npi, nxo, nyo, out, ST(s));
 }
+int b200_dev_layout_tables(const double* src, int ntab, int ns, int pad, int ngrid, int poly, double* dst, void* s) {
+    return launch_layout_tables(src, ntab, ns, pad, ngrid, poly, dst, ST(s));
+}
 int b200_dev_gather_stamp(const int* idx, int n, int npad, const double* sx, const double* sy, const int* scode,
                           const float* sdata, long src_ld, int n_inframe, double* px, double* py, int* pcode,
                           float* indata, int ldi, void* s) {

@@ -507,6 +507,33 @@ __global__ void __launch_bounds__(256) k_gather_stamp(const int* __restrict__ id
     }
 }
 
+// PSF-overlap tables as uploaded (ntab, ns, ns) -> the arena layout: zero-padded by `pad` on every side
+// (np.pad(ovl, 6), psfutil.py:1471, 1580, 1696) to ngrid = ns + 2 pad, row-major (P == 0) or polyphase of period P.
+__global__ void __launch_bounds__(256) k_layout_tables(const double* __restrict__ src, int ntab, int ns, int pad,
+                                                       int ngrid, int P, double* __restrict__ dst) {
+    const int ncell = P > 0 ? (ngrid + P - 1) / P : 0;
+    const long long per = P > 0 ? (long long)P * P * ncell * ncell : (long long)ngrid * ngrid;
+    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= per * ntab) return;
+    const int t = (int)(e / per);
+    long long r = e - (long long)t * per;
+    int y, x;
+    if (P > 0) {
+        const int cx = (int)(r % ncell);
+        r /= ncell;
+        const int cy = (int)(r % ncell);
+        r /= ncell;
+        const int pxx = (int)(r % P), pyy = (int)(r / P);
+        y = cy * P + pyy;
+        x = cx * P + pxx;
+    } else {
+        y = (int)(r / ngrid);
+        x = (int)(r - (long long)y * ngrid);
+    }
+    const int sy = y - pad, sx = x - pad;
+    dst[e] = (sy >= 0 && sy < ns && sx >= 0 && sx < ns) ? src[((size_t)t * ns + sy) * ns + sx] : 0.0;
+}
+
 __global__ void k_getw(double* __restrict__ w, double fh) {
     double t[10];
     d5512_getw(t, fh);
@@ -541,6 +568,18 @@ int launch_gridD5512C(const double* f, int ngy, int ngx, const double* x, const 
     if (smem > 48 * 1024)
         B200_CUDA(cudaFuncSetAttribute(k_gridD5512C, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k_gridD5512C<<<(unsigned)npi, 256, smem, s>>>(f, ngy, ngx, x, y, nxo, nyo, out);
+    B200_LAUNCH_CHECK();
+    return 0;
+}
+
+int launch_layout_tables(const double* src, int ntab, int ns, int pad, int ngrid, int poly, double* dst,
+                         cudaStream_t s) {
+    if (ntab <= 0 || ns <= 0) return 0;
+    B200_REQUIRE(ngrid == ns + 2 * pad && poly >= 0, "layout_tables: ngrid must be ns + 2 pad");
+    const long long ncell = poly > 0 ? (ngrid + poly - 1) / poly : 0;
+    const long long per = poly > 0 ? (long long)poly * poly * ncell * ncell : (long long)ngrid * ngrid;
+    const long long tot = per * ntab;
+    k_layout_tables<<<(unsigned)((tot + 255) / 256), 256, 0, s>>>(src, ntab, ns, pad, ngrid, poly, dst);
     B200_LAUNCH_CHECK();
     return 0;
 }
