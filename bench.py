@@ -219,6 +219,7 @@ def run_gpu(args):
 
     def step_resident():
         gb.reset_maps()
+        gb.reset_cache()  # every step is a new block: no InStamp-pair block survives from the previous one
         gb.run()
         return gather_cube(gb.out_map, world, rank)
 

@@ -39,7 +39,8 @@ int b200_release_scratch(void);
 enum b200_prof_kind {
     B200_PROF_CHOL_SUPER = 0, B200_PROF_POTRF_DIAG, B200_PROF_CHOL_PANEL, B200_PROF_CHOL_INNER,
     B200_PROF_BACK_SUPER, B200_PROF_BACK_DIAG, B200_PROF_BACK_INNER, B200_PROF_BUILD_A, B200_PROF_BUILD_B,
-    B200_PROF_FINALIZE, B200_PROF_GEMM, B200_PROF_ITER_CG, B200_PROF_LAKERNEL1, B200_PROF_EIGH, B200_PROF_NKINDS
+    B200_PROF_FINALIZE, B200_PROF_GEMM, B200_PROF_ITER_CG, B200_PROF_LAKERNEL1, B200_PROF_EIGH, B200_PROF_ASSEMBLE_A,
+    B200_PROF_NKINDS
 };
 int b200_profile(int on);
 int b200_profile_read(int kind, double* ms, double* work, long long* count);
@@ -113,6 +114,36 @@ int b200_dev_gather_stamp(const int* idx, int n, int npad, const double* src_x, 
 int b200_dev_build_A(const double* px, const double* py, const int* pcode, int n, int npad, const double* tables,
                      const b200_table_ref* lut, int nimg, int ncode, int ngrid, double dscale, double nc,
                      double flat_penalty, double* A, int lda, double diag_add, int poly, void* stream);
+/* InStamp-pair blocks of A (SysMatA.get_iisubmat / _compute_iisubmats, psfutil.py:1764-2092): the device form of
+ * the reference's block cache.  One descriptor per FULL block: all nA pixels of InStamp a (global pixel range
+ * offA..) against all nB pixels of InStamp b, a <= b in raster order, written row-major with leading dimension ld
+ * at pool + out (doubles).  same != 0 (a == b): the upper triangle is interpolated and mirrored (psfutil.py:1692-1714).
+ * lut selects the (nimg x nimg) table-reference block of the two PSF groups inside the lut array. */
+typedef struct b200_pair_desc {
+    int offA, nA, offB, nB;
+    long long out;
+    int ld, lut, same, pad_;
+} b200_pair_desc;
+/* gx, gy (npix): positions of every input pixel of the mosaic block in output pixels; gimg (npix): image index;
+ * descs, tile_prefix (npair, device): descriptors and the exclusive prefix sum of their 32x32 tile counts
+ * (ceil(nA/32)*ceil(nB/32)); ntiles: the total; points: number of entries evaluated (profiling only). */
+int b200_dev_pair_blocks(const double* gx, const double* gy, const int* gimg, const b200_pair_desc* descs,
+                         const int* tile_prefix, int npair, int ntiles, const double* tables,
+                         const b200_table_ref* lut, int nimg, int ngrid, double dscale, double nc, double flat_penalty,
+                         int poly, double* pool, double points, void* stream);
+/* One OutStamp's A cut out of cached pair blocks (the np.ix_ scatter of coadd.py:1028-1069): the stamp's n pixels are
+ * 9 consecutive segments (one per InStamp of the 3x3 neighbourhood, seg_start[0..9]); pixel k is global pixel gidx[k],
+ * i.e. pixel gidx[k] - inst_off[s] of its InStamp; blk[9*s+t], ld[9*s+t] (s <= t) locate block (s, t) inside pool.
+ * Identity in rows/columns n..npad-1, diag_add on the first n diagonal entries. */
+typedef struct b200_asm_desc {
+    long long blk[81];
+    int ld[81];
+    int seg_start[10];
+    int inst_off[9];
+    int pad_;
+} b200_asm_desc;
+int b200_dev_assemble_A(const b200_asm_desc* desc, const int* gidx, int n, int npad, const double* pool, double* A,
+                        int lda, double diag_add, void* stream);
 /* mBhalf (n_out, mpad, ldb) for one output stamp: replaces PSFOvl._call_io_cross (psfutil.py:1497-1595) and
  * coadd.py:1075-1082.  lut_io (ncode*n_out) table offsets (<0 absent); output pixel (iy,ix) sits at
  * (x0out + ix, y0out + iy) (coadd.py:879-882).  Padding rows/columns are zero-filled. */

@@ -48,6 +48,20 @@ class SolveSys(C.Structure):
                 ("ldx", i32)]
 
 
+class PairDesc(C.Structure):
+    """b200_pair_desc"""
+
+    _fields_ = [("offA", i32), ("nA", i32), ("offB", i32), ("nB", i32), ("out", C.c_longlong), ("ld", i32),
+                ("lut", i32), ("same", i32), ("pad_", i32)]
+
+
+class AsmDesc(C.Structure):
+    """b200_asm_desc"""
+
+    _fields_ = [("blk", C.c_longlong * 81), ("ld", i32 * 81), ("seg_start", i32 * 10), ("inst_off", i32 * 9),
+                ("pad_", i32)]
+
+
 class FinalizeArgs(C.Structure):
     """b200_finalize_args"""
 
@@ -76,6 +90,8 @@ PROTOTYPES = {
     "b200_dev_layout_tables": [vp, i32, i32, i32, i32, i32, vp, vp],
     "b200_dev_gather_stamp": [vp, i32, i32, vp, vp, vp, vp, i64, i32, vp, vp, vp, vp, i32, vp],
     "b200_dev_build_A": [vp, vp, vp, i32, i32, vp, vp, i32, i32, i32, f64, f64, f64, vp, i32, f64, i32, vp],
+    "b200_dev_pair_blocks": [vp, vp, vp, vp, vp, i32, i32, vp, vp, i32, i32, f64, f64, f64, i32, vp, f64, vp],
+    "b200_dev_assemble_A": [C.POINTER(AsmDesc), vp, i32, i32, vp, vp, i32, f64, vp],
     "b200_dev_build_B": [vp, vp, vp, i32, i32, vp, vp, i32, i32, f64, f64, i32, i32, f64, f64, vp, i32, szt, vp],
     "b200_dev_chol_solve": [C.POINTER(SolveSys), i32, i32, i32, vp],
     "b200_dev_pad_system": [vp, i32, i32, i32, vp, i32, C.POINTER(f64), i32, vp],
@@ -124,7 +140,8 @@ profile_read_raw = globals()["profile_read"]
 
 
 PROF_KINDS = ("chol_super_update", "potrf_diag", "chol_panel", "chol_inner_update", "back_super_update", "back_diag",
-              "back_inner_update", "build_A", "build_B", "finalize", "gemm_nt", "iter_cg", "lakernel1", "eigh")
+              "back_inner_update", "build_A", "build_B", "finalize", "gemm_nt", "iter_cg", "lakernel1", "eigh",
+              "assemble_A")
 
 
 def profile_read():

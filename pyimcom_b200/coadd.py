@@ -33,6 +33,9 @@ from .psfovl_host import anchor
 
 TABLEREF_DTYPE = np.dtype([("offset", "<i8"), ("flip", "<i4"), ("pad_", "<i4"), ("penalty_sub", "<f8")])
 assert TABLEREF_DTYPE.itemsize == C.sizeof(_lib.TableRef)
+PAIRDESC_DTYPE = np.dtype([("offA", "<i4"), ("nA", "<i4"), ("offB", "<i4"), ("nB", "<i4"), ("out", "<i8"), ("ld", "<i4"),
+                           ("lut", "<i4"), ("same", "<i4"), ("pad_", "<i4")])
+assert PAIRDESC_DTYPE.itemsize == C.sizeof(_lib.PairDesc)
 
 
 def h2d(a: np.ndarray) -> torch.Tensor:
@@ -94,13 +97,13 @@ class StampPlan:
     """Host-side description of one OutStamp (what OutStamp.__init__ / _process_input_stamps derive)."""
 
     __slots__ = ("j_st", "i_st", "n", "idx", "pcode", "groups", "seg_end", "seg_img", "inpix_cumsum", "x0out", "y0out",
-                 "lut", "lut_io")
+                 "lut", "lut_io", "insts")
 
 
 class GpuBlock:
     """One mosaic block on one GPU."""
 
-    def __init__(self, blk, tables, kernel: str | None = None):
+    def __init__(self, blk, tables, kernel: str | None = None, a_cache: bool = True):
         if not torch.cuda.is_available():
             raise RuntimeError("pyimcom_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
         self.blk, self.tab = blk, tables
@@ -113,6 +116,10 @@ class GpuBlock:
         self._uploaded = False
         # period of the polyphase in-in tables = native pixel pitch in table samples = oversamp (psfutil.py:610)
         self.poly = int(getattr(self.cfg, "oversamp", 0))
+        # A from cached InStamp-pair blocks (the device form of SysMatA's cache) or, if False, one fused kernel per
+        # OutStamp that interpolates all of its entries; both give bit-identical matrices
+        self.a_cache = bool(a_cache)
+        self.pool_bytes = None  # pair-block pool size; default: a quarter of the free HBM, at most 32 GB
 
     # ---------------------------------------------------------------------------------------------
     # host-side planning (coadd.py:846-977)
@@ -152,6 +159,7 @@ class GpuBlock:
         idx, pcode, seg_end, seg_img, counts = [], [], [], [], []
         groups = []
         pos = 0
+        p.insts = [(j_st + dj, i_st + di) for dj in (-1, 0, 1) for di in (-1, 0, 1)]
         for dj in (-1, 0, 1):
             for di in (-1, 0, 1):
                 jj, ii = j_st + dj, i_st + di
@@ -211,7 +219,29 @@ class GpuBlock:
         if rows:
             lut[np.ix_(present, present)] = np.array(rows, dtype=TABLEREF_DTYPE).reshape(len(present), len(present))
         p.lut, p.lut_io = lut, lut_io
+        if self.a_cache:  # table references of every (group_a, group_b) an InStamp pair of this stamp can need
+            for ga in range(len(groups)):
+                for gb in range(len(groups)):
+                    self._pair_lut(groups[ga], groups[gb])
         return p
+
+    def _pair_lut(self, Ga, Gb) -> int:
+        """Index of the (nimg x nimg) table-reference block for pixels of group Ga (rows) against group Gb (columns)."""
+        key = (Ga, Gb)
+        if key not in self._pair_lut_idx:
+            tab, cfg, nimg = self.tab, self.cfg, self.blk.n_inimage
+            arr = np.zeros((nimg, nimg), dtype=TABLEREF_DTYPE)
+            arr["offset"] = -1
+            tab.group(Ga)
+            tab.group(Gb)
+            n_in = len(tab.grp_imgs[Ga]) if Ga == Gb else (len(tab.grp_imgs[Ga]) * len(tab.grp_imgs[Gb])) ** 0.5
+            for ka in tab.grp_imgs[Ga]:
+                for kb in tab.grp_imgs[Gb]:
+                    t, tidx, flip = tab.table_ii_ref(Ga, ka, Gb, kb)
+                    arr[ka, kb] = (self.arena.offset(t, tidx, poly=True), int(flip), 0, cfg.flat_penalty / n_in)
+            self._pair_lut_idx[key] = len(self._pair_lut_list)
+            self._pair_lut_list.append(arr)
+        return self._pair_lut_idx[key]
 
     def prepare(self, stamps=None):
         """Plan the requested OutStamps (default: the whole block in the reference's 2x2-group order) and upload."""
@@ -221,6 +251,7 @@ class GpuBlock:
         self._global_pixels()
         self.arena = _Arena(self.cfg.nsamp_ovl, poly=self.poly)
         self._pair_cache, self._io_cache = {}, {}
+        self._pair_lut_idx, self._pair_lut_list = {}, []
         self.order = list(stamps) if stamps is not None else list(self.blk.stamp_order())
         self.plans = {ji: self.plan_stamp(*ji) for ji in self.order}
         t1 = time.perf_counter()
@@ -235,6 +266,13 @@ class GpuBlock:
         self.d_y = h2d(self.h_y)
         self.d_data = h2d(self.h_data)
         self.d_tables = self.arena.upload()
+        self.d_img = h2d(self.h_img)
+        plut = np.stack(self._pair_lut_list) if self._pair_lut_list else np.zeros((1, 1, 1), dtype=TABLEREF_DTYPE)
+        self.d_pair_lut = h2d(plut.view(np.uint8).reshape(-1))
+        self._pairs = {}  # (inst_a, inst_b) -> (pool offset in doubles, ld)
+        self._pool = None
+        self._pool_used = 0
+        self.pair_points = 0  # entries interpolated so far (vs sum of n^2/2 without the cache)
         plans = [self.plans[ji] for ji in self.order]
         # per-stamp metadata packed into a few arrays, one H2D copy each
         self.off_pix = np.concatenate([[0], np.cumsum([p.n for p in plans])]).astype(np.int64)
@@ -251,9 +289,15 @@ class GpuBlock:
         self.d_fade_w = h2d(trapezoid_weights(cfg.fade_kernel)) if cfg.fade_kernel > 0 else None
         self.h2d_bytes = self.arena.h2d_bytes + sum(
             t.numel() * t.element_size() for t in (self.d_x, self.d_y, self.d_data, self.d_idx, self.d_pcode_all,
-                                                   self.d_seg_end, self.d_seg_img, self.d_lut, self.d_lut_io))
+                                                   self.d_seg_end, self.d_seg_img, self.d_lut, self.d_lut_io, self.d_img, self.d_pair_lut))
         self.reset_maps()
         self._uploaded = True
+
+    def reset_cache(self):
+        """Forget every cached InStamp-pair block (a new mosaic block starts with an empty SysMatA cache)."""
+        self._pairs.clear()
+        self._pool_used = 0
+        self.pair_points = 0
 
     def reset_maps(self):
         """Zero-initialised block maps (coadd.py:2028-2047)."""
@@ -272,6 +316,79 @@ class GpuBlock:
     # ---------------------------------------------------------------------------------------------
     # device pipeline of one OutStamp
     # ---------------------------------------------------------------------------------------------
+    # ---------------------------------------------------------------------------------------------
+    # InStamp-pair block cache (SysMatA, psfutil.py:1764-2092)
+    # ---------------------------------------------------------------------------------------------
+    def _inst_count(self, ji):
+        return int(self.blk.instamps[ji[0]][ji[1]].pix_cumsum[-1])
+
+    def ensure_pairs(self, plans):
+        """Interpolate, in one launch, every InStamp-pair block the given OutStamps need that is not cached yet.
+
+        Blocks live in one pool (bump allocation).  When the pool is full the cache is dropped and the blocks of the
+        current OutStamps are recomputed: the traversal order makes older blocks dead anyway, as the reference's
+        reference counts do (psfutil.py:1997-2004)."""
+        def wanted():
+            seen, out = set(), []
+            for p in plans:
+                for a in range(9):
+                    for b in range(a, 9):
+                        key = (p.insts[a], p.insts[b])
+                        if key in self._pairs or key in seen:
+                            continue
+                        seen.add(key)
+                        nA, nB = self._inst_count(key[0]), self._inst_count(key[1])
+                        if nA and nB:
+                            out.append((key, nA, nB))
+            return out
+
+        need = wanted()
+        if not need:
+            return
+        size = lambda nA, nB: nA * ((nB + 3) // 4 * 4)  # noqa: E731
+        total = sum(size(nA, nB) for _, nA, nB in need)
+        cap = self._pool.numel() if self._pool is not None else 0
+        if self._pool_used + total > cap:
+            self._pairs.clear()  # evict everything (stream order keeps earlier readers safe)
+            self._pool_used = 0
+            need = wanted()
+            total = sum(size(nA, nB) for _, nA, nB in need)
+            if total > cap:
+                self._pool = None
+                budget = self.pool_bytes or min(32 << 30, torch.cuda.mem_get_info()[0] // 4)
+                self._pool = torch.empty(max(total, int(budget) // 8), dtype=torch.float64, device="cuda")
+        desc = np.zeros(len(need), dtype=PAIRDESC_DTYPE)
+        tiles = np.zeros(len(need) + 1, dtype=np.int64)
+        points = 0.0
+        for q, (key, nA, nB) in enumerate(need):
+            a, b = key
+            ld = (nB + 3) // 4 * 4
+            desc[q] = (int(self.inst_off[a]), nA, int(self.inst_off[b]), nB, self._pool_used, ld,
+                       self._pair_lut_idx[(anchor(a), anchor(b))], int(a == b), 0)
+            self._pairs[key] = (self._pool_used, ld)
+            self._pool_used += nA * ld
+            tiles[q + 1] = tiles[q] + ((nA + 31) // 32) * ((nB + 31) // 32)
+            points += nA * (nA + 1) / 2 if a == b else nA * nB
+        self.pair_points += points
+        cfg = self.cfg
+        d_desc = h2d(desc.view(np.uint8).reshape(-1))
+        d_tiles = h2d(tiles[:-1].astype(np.int32))
+        _lib.dev_pair_blocks(ptr(self.d_x), ptr(self.d_y), ptr(self.d_img), ptr(d_desc), ptr(d_tiles), len(need),
+                             int(tiles[-1]), ptr(self.d_tables), ptr(self.d_pair_lut), self.blk.n_inimage,
+                             self.arena.ngrid, float(cfg.dscale), float(cfg.nc_ovl), float(cfg.flat_penalty),
+                             self.arena.poly, ptr(self._pool), float(points), stream_handle())
+
+    def _asm_desc(self, p) -> _lib.AsmDesc:
+        d = _lib.AsmDesc()
+        for a in range(9):
+            d.inst_off[a] = int(self.inst_off[p.insts[a]])
+            for b in range(a, 9):
+                off, ld = self._pairs.get((p.insts[a], p.insts[b]), (0, 4))
+                d.blk[9 * a + b], d.ld[9 * a + b] = off, ld
+        for a in range(10):
+            d.seg_start[a] = int(p.inpix_cumsum[a])
+        return d
+
     def build_system(self, k: int):
         """Stage (a): gather + A + mBhalf for stamp number k of self.order.  Returns (DeviceSystem, indata)."""
         cfg = self.cfg
@@ -292,9 +409,14 @@ class GpuBlock:
                               indata.stride(0), st)
         A = torch.empty((npad, npad), dtype=torch.float64, device="cuda")
         ncode = 4 * nimg
-        _lib.dev_build_A(ptr(px), ptr(py), ptr(pcode), n, npad, ptr(self.d_tables), ptr(self.d_lut[k]), nimg, ncode,
-                         self.arena.ngrid, float(cfg.dscale), float(cfg.nc_ovl), float(cfg.flat_penalty), ptr(A),
-                         A.stride(0), 0.0, self.arena.poly, st)
+        if self.a_cache:
+            self.ensure_pairs([p])  # no-op when coadd_batch has already requested the whole batch's blocks
+            _lib.dev_assemble_A(C.byref(self._asm_desc(p)), ptr(idx), n, npad, ptr(self._pool), ptr(A), A.stride(0), 0.0,
+                                st)
+        else:
+            _lib.dev_build_A(ptr(px), ptr(py), ptr(pcode), n, npad, ptr(self.d_tables), ptr(self.d_lut[k]), nimg, ncode,
+                             self.arena.ngrid, float(cfg.dscale), float(cfg.nc_ovl), float(cfg.flat_penalty), ptr(A),
+                             A.stride(0), 0.0, self.arena.poly, st)
         mB = torch.empty((cfg.n_out, mpad, npad), dtype=torch.float64, device="cuda")
         _lib.dev_build_B(ptr(px), ptr(py), ptr(pcode), n, npad, ptr(self.d_tables), ptr(self.d_lut_io[k]), cfg.n_out,
                          self.arena.ngrid, float(cfg.dscale), float(cfg.nc_ovl), cfg.n2f, mpad, p.x0out, p.y0out, ptr(mB),
@@ -328,6 +450,8 @@ class GpuBlock:
         cfg = self.cfg
         kept = [dict() for _ in ks]
         live = []
+        if self.a_cache:
+            self.ensure_pairs([pl for pl in (self.plans[self.order[k]] for k in ks) if pl.n > 0])
         for q, k in enumerate(ks):
             p = self.plans[self.order[k]]
             if p.n == 0:  # lakernel.py:110-119 and coadd.py:1094-1100: nothing to add except UC = kappa = 1

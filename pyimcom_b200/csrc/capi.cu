@@ -293,6 +293,18 @@ int b200_dev_build_A(const double* px, const double* py, const int* pcode, int n
     return launch_build_A(px, py, pcode, n, npad, tables, lut, nimg, ncode, ngrid, dscale, nc, flat_penalty, A, lda,
                           diag_add, poly, ST(s));
 }
+int b200_dev_pair_blocks(const double* gx, const double* gy, const int* gimg, const b200_pair_desc* descs,
+                         const int* tile_prefix, int npair, int ntiles, const double* tables,
+                         const b200_table_ref* lut, int nimg, int ngrid, double dscale, double nc, double flat_penalty,
+                         int poly, double* pool, double points, void* s) {
+    return launch_pair_blocks(gx, gy, gimg, descs, tile_prefix, npair, ntiles, tables, lut, nimg, ngrid, dscale, nc,
+                              flat_penalty, poly, pool, points, ST(s));
+}
+int b200_dev_assemble_A(const b200_asm_desc* desc, const int* gidx, int n, int npad, const double* pool, double* A,
+                        int lda, double diag_add, void* s) {
+    B200_REQUIRE(desc != nullptr, "assemble_A: null descriptor");
+    return launch_assemble_A(*desc, gidx, n, npad, pool, A, lda, diag_add, ST(s));
+}
 int b200_dev_build_B(const double* px, const double* py, const int* pcode, int n, int npad, const double* tables,
                      const long long* lut_io, int n_out, int ngrid, double dscale, double nc, int n2f, int mpad,
                      double x0out, double y0out, double* B, int ldb, size_t strideB, void* s) {

@@ -307,6 +307,150 @@ __global__ void __launch_bounds__(256) k_build_A(const double* __restrict__ px, 
 }
 
 // ------------------------------------------------------------------------------------------------
+// InStamp-pair blocks of A and their cache (SysMatA, psfutil.py:1764-2092).
+//
+// Neighbouring output stamps share six of their nine InStamps, so most of the 9 + 36 InStamp-pair blocks of a
+// stamp's A recur in its neighbours: the reference keeps them in a reference-counted cache keyed
+// (ji_st1, ji_st2) and interpolates each only once (13 distinct blocks per InStamp instead of 45 per OutStamp).
+// k_pair_blocks evaluates a whole list of FULL pair blocks (all pixels of InStamp a x all pixels of InStamp b,
+// a <= b in raster order) in one launch; k_assemble_A then cuts one OutStamp's A out of the cached blocks
+// through its pixel selections.  Entry values, table choice, flips and the upper-triangle-then-mirror rule inside
+// a self block are those of k_build_A, so both routes give bit-identical matrices.
+// ------------------------------------------------------------------------------------------------
+template <int P>
+__global__ void __launch_bounds__(256) k_pair_blocks(const double* __restrict__ gx, const double* __restrict__ gy,
+                                                     const int* __restrict__ gimg, const PairDesc* __restrict__ descs,
+                                                     const int* __restrict__ tile_prefix, int npair,
+                                                     const double* __restrict__ tables,
+                                                     const TableRef* __restrict__ lut, int nimg, int ngrid,
+                                                     double dscale, double nc, double flat_penalty,
+                                                     double* __restrict__ pool) {
+    __shared__ double tile[32][33];
+    // which pair does this tile belong to: largest q with tile_prefix[q] <= blockIdx.x
+    int lo = 0, hi = npair - 1;
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (tile_prefix[mid] <= (int)blockIdx.x)
+            lo = mid;
+        else
+            hi = mid - 1;
+    }
+    const PairDesc d = descs[lo];
+    const int t = blockIdx.x - tile_prefix[lo];
+    const int ntj = (d.nB + 31) >> 5;
+    const int bi = t / ntj, bj = t - bi * ntj;
+    if (d.same && bj < bi) return;  // self block: upper tiles only, mirrored below
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int j = bj * 32 + tx;
+    double xj = 0, yj = 0;
+    int cj = 0;
+    if (j < d.nB) {
+        xj = gx[d.offB + j];
+        yj = gy[d.offB + j];
+        cj = gimg[d.offB + j];
+    }
+    double* blk = pool + d.out;
+    const TableRef* plut = lut + (size_t)d.lut * nimg * nimg;
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+        const int li = ty + 8 * r;
+        const int i = bi * 32 + li;
+        double v = 0.0;
+        if (i < d.nA && j < d.nB && (!d.same || i <= j)) {
+            const int ci = gimg[d.offA + i];
+            const double x = __dadd_rn(__dadd_rn(__ddiv_rn(__dadd_rn(gx[d.offA + i], -xj), dscale), nc), 6.0);
+            const double y = __dadd_rn(__dadd_rn(__ddiv_rn(__dadd_rn(gy[d.offA + i], -yj), dscale), nc), 6.0);
+            const TableRef tr = plut[ci * nimg + cj];
+            const int xi = (int)x, yi = (int)y;
+            if (tr.offset >= 0 && d5512_on_grid(xi, ngrid) && d5512_on_grid(yi, ngrid)) {
+                double wx[10], wy[10];
+                d5512_getw(wx, x - xi - 0.5);
+                d5512_getw(wy, y - yi - 0.5);
+                if (P > 0) {
+                    const PolyOff<(P > 0 ? P : 1)> po(yi, xi, ngrid, (ngrid + P - 1) / (P > 0 ? P : 1), tr.flip);
+                    v = d5512_taps_poly(tables + tr.offset, po, wx, wy);
+                } else {
+                    v = d5512_taps(tables + tr.offset, ngrid, ngrid, yi, xi, wx, wy, tr.flip);
+                }
+            }
+            if (flat_penalty != 0.0) {  // psfutil.py:1483-1486, 1705-1708
+                v = __dadd_rn(v, -tr.penalty_sub);
+                if (ci == cj) v = __dadd_rn(v, flat_penalty);
+            }
+            blk[(size_t)i * d.ld + j] = v;
+        }
+        tile[li][tx] = v;
+    }
+    if (!d.same) return;
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+        const int lj = ty + 8 * r;
+        const int jj = bj * 32 + lj, ii = bi * 32 + tx;
+        if (jj < d.nB && ii < d.nA && ii < jj) blk[(size_t)jj * d.ld + ii] = tile[tx][lj];
+    }
+}
+
+// One OutStamp's A (npad x lda) from cached pair blocks.  Stamp pixel k (0 <= k < n) is pixel gidx[k] of the block's
+// global pixel list and belongs to segment s (one of the 9 InStamps, seg_start[s] <= k < seg_start[s+1]); its index
+// inside that InStamp is gidx[k] - inst_off[s].  Upper-triangle tiles are read row-contiguously from block
+// (s_i, s_j), s_i <= s_j, and the mirrored tile is written through shared memory; rows/columns n..npad-1 carry the
+// identity; diag_add goes onto the first n diagonal entries.
+__global__ void __launch_bounds__(256) k_assemble_A(AsmDesc d, const int* __restrict__ gidx, int n, int npad,
+                                                    const double* __restrict__ pool, double* __restrict__ A, int lda,
+                                                    double diag_add) {
+    __shared__ double tile[32][33];
+    const int nt = npad / 32;
+    int bi, rem = blockIdx.x;
+    {
+        const double b = 2.0 * nt + 1.0;
+        int guess = (int)((b - sqrt(b * b - 8.0 * rem)) * 0.5);
+        if (guess < 0) guess = 0;
+        if (guess > nt - 1) guess = nt - 1;
+        while (guess > 0 && (long)guess * (2 * nt - guess + 1) / 2 > rem) guess--;
+        while ((long)(guess + 1) * (2 * nt - guess) / 2 <= rem) guess++;
+        bi = guess;
+        rem -= (int)((long)bi * (2 * nt - bi + 1) / 2);
+    }
+    const int bj = bi + rem;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int j = bj * 32 + tx;
+    int sj = 0, lj = 0;
+    if (j < n) {
+        while (sj < 8 && j >= d.seg_start[sj + 1]) sj++;
+        lj = gidx[j] - d.inst_off[sj];
+    }
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+        const int li = ty + 8 * r;
+        const int i = bi * 32 + li;
+        double v = 0.0;
+        if (i < n && j < n) {
+            if (i <= j) {
+                int si = 0;
+                while (si < 8 && i >= d.seg_start[si + 1]) si++;
+                const int ii = gidx[i] - d.inst_off[si];
+                const int q = si * 9 + sj;  // si <= sj because segments are consecutive runs of the stamp order
+                v = pool[d.blk[q] + (size_t)ii * d.ld[q] + lj];
+                if (i == j) v += diag_add;
+                A[(size_t)i * lda + j] = v;
+            }
+        } else if (i < npad && j < npad) {
+            v = (i == j) ? 1.0 : 0.0;
+            if (i <= j) A[(size_t)i * lda + j] = v;
+        }
+        tile[li][tx] = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+        const int lj2 = ty + 8 * r;
+        const int jj = bj * 32 + lj2, ii = bi * 32 + tx;
+        if (jj < npad && ii < npad && ii < jj) A[(size_t)jj * lda + ii] = tile[tx][lj2];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // Fused mBhalf assembly for one output stamp (stage a; replaces psfutil.py:1497-1595 and
 // coadd.py:1075-1082).  mBhalf[o][a=(iy,ix)][i] = gridD5512C of io-table(group_i,image_i,o) at
 // ((x_i - xout[ix])/dscale + nc + 6, (y_i - yout[iy])/dscale + nc + 6).
@@ -628,6 +772,48 @@ int launch_build_A(const double* px, const double* py, const int* pcode, int n, 
     }
 #undef B200_BUILD_A
     prof_end(8.0 * npad * (double)npad + 20.0 * n, s);  // bytes: the matrix written once + positions/codes read
+    B200_LAUNCH_CHECK();
+    return 0;
+}
+
+int launch_pair_blocks(const double* gx, const double* gy, const int* gimg, const PairDesc* descs,
+                       const int* tile_prefix, int npair, int ntiles, const double* tables, const TableRef* lut,
+                       int nimg, int ngrid, double dscale, double nc, double flat_penalty, int poly, double* pool,
+                       double points, cudaStream_t s) {
+    if (npair <= 0 || ntiles <= 0) return 0;
+    prof_begin(PROF_BUILD_A, s);
+#define B200_PAIR(PP)                                                                                                \
+    k_pair_blocks<PP><<<(unsigned)ntiles, 256, 0, s>>>(gx, gy, gimg, descs, tile_prefix, npair, tables, lut, nimg, ngrid, \
+                                                       dscale, nc, flat_penalty, pool)
+    switch (poly) {
+        case 0: B200_PAIR(0); break;
+        case 2: B200_PAIR(2); break;
+        case 3: B200_PAIR(3); break;
+        case 4: B200_PAIR(4); break;
+        case 5: B200_PAIR(5); break;
+        case 6: B200_PAIR(6); break;
+        case 8: B200_PAIR(8); break;
+        case 10: B200_PAIR(10); break;
+        case 12: B200_PAIR(12); break;
+        case 16: B200_PAIR(16); break;
+        default:
+            set_error("pair_blocks: no polyphase instantiation for period %d (0, 2-6, 8, 10, 12, 16)", poly);
+            return -1;
+    }
+#undef B200_PAIR
+    prof_end(8.0 * points, s);  // bytes: every block entry written once
+    B200_LAUNCH_CHECK();
+    return 0;
+}
+
+int launch_assemble_A(const AsmDesc& d, const int* gidx, int n, int npad, const double* pool, double* A, int lda,
+                      double diag_add, cudaStream_t s) {
+    if (npad <= 0) return 0;
+    B200_REQUIRE(npad % 32 == 0 && npad >= n && lda >= npad, "assemble_A: npad must be a multiple of 32, >= n, <= lda");
+    const long nt = npad / 32;
+    prof_begin(PROF_ASSEMBLE_A, s);
+    k_assemble_A<<<(unsigned)(nt * (nt + 1) / 2), 256, 0, s>>>(d, gidx, n, npad, pool, A, lda, diag_add);
+    prof_end(8.0 * npad * (double)npad + 8.0 * 0.5 * n * (double)n, s);  // A written once + the upper half read from blocks
     B200_LAUNCH_CHECK();
     return 0;
 }

@@ -12,6 +12,8 @@ namespace b200 {
 using TableRef = ::b200_table_ref;
 using SolveSys = ::b200_solve_sys;
 using FinalizeArgs = ::b200_finalize_args;
+using PairDesc = ::b200_pair_desc;
+using AsmDesc = ::b200_asm_desc;
 
 constexpr int NB = B200_NB;      // Cholesky/TRSM block size == DMMA GEMM tile edge
 constexpr int MAXB = B200_MAXB;  // systems per batched launch (descriptors travel as kernel parameters)
@@ -40,6 +42,12 @@ int launch_gather_stamp(const int* idx, int n, int npad, const double* src_x, co
 int launch_build_A(const double* px, const double* py, const int* pcode, int n, int npad, const double* tables,
                    const TableRef* lut, int nimg, int ncode, int ngrid, double dscale, double nc, double flat_penalty,
                    double* A, int lda, double diag_add, int poly, cudaStream_t s);
+int launch_pair_blocks(const double* gx, const double* gy, const int* gimg, const PairDesc* descs,
+                       const int* tile_prefix, int npair, int ntiles, const double* tables, const TableRef* lut,
+                       int nimg, int ngrid, double dscale, double nc, double flat_penalty, int poly, double* pool,
+                       double points, cudaStream_t s);
+int launch_assemble_A(const AsmDesc& d, const int* gidx, int n, int npad, const double* pool, double* A, int lda,
+                      double diag_add, cudaStream_t s);
 int launch_build_B(const double* px, const double* py, const int* pcode, int n, int npad, const double* tables,
                    const long long* lut_io, int n_out, int ngrid, double dscale, double nc, int n2f, int mpad,
                    double x0out, double y0out, double* B, int ldb, size_t strideB, cudaStream_t s);

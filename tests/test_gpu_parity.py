@@ -348,6 +348,32 @@ def test_block_vs_oracle_and_reference(name, golden_dir):
         assert np.abs(s.UC - g[tag + "UC"]).max() < tol * max(1.0, np.abs(g[tag + "UC"]).max())
 
 
+@pytest.mark.parametrize("name", ["pad4", "nout2split", "chol1"])
+def test_pair_block_cache_is_bit_identical(name):
+    """A cut from cached InStamp-pair blocks (device SysMatA) == A from the fused per-stamp kernel, bit for bit; the
+    cache interpolates fewer entries than the stamps hold, and survives a pool too small for more than one stamp."""
+    spec = cases.BLOCK_CASES[name]
+    blk = cases.make_block(spec)
+    tab = PSFTables(blk, G.iD5512C, G.gridD5512C)
+    stamps = list(blk.stamp_order())
+    fused = GpuBlock(blk, tab, a_cache=False).prepare(stamps=stamps)
+    cached = GpuBlock(blk, tab, a_cache=True).prepare(stamps=stamps)
+    tiny = GpuBlock(blk, tab, a_cache=True)
+    tiny.pool_bytes = 8  # forces an eviction + regrow on every request
+    tiny.prepare(stamps=stamps)
+    tot = 0
+    for k in range(len(stamps)):
+        if fused.plans[stamps[k]].n == 0:
+            continue
+        a0 = fused.build_system(k)[0].A
+        a1 = cached.build_system(k)[0].A
+        a2 = tiny.build_system(k)[0].A
+        assert torch.equal(a0, a1) and torch.equal(a0, a2)
+        tot += fused.plans[stamps[k]].n ** 2 / 2
+    if len(stamps) > 1:
+        assert cached.pair_points < tot
+
+
 def test_block_run_maps():
     """Whole-block loop: the accumulated maps equal the overlap-add of the per-stamp oracle results."""
     spec = cases.BLOCK_CASES["pad4"]
