@@ -36,6 +36,11 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 from pyimcom_b200.synth import StampConfig, SynthBlock  # noqa: E402
 
+# DRAM traffic of the dominant kernel from the committed ncu capture (profiles/ncu_r01_a.txt: k_chol_super_update,
+# grid (4,25,16), 7.72 ms under ncu): dram__bytes_read.sum + dram__bytes_write.sum of that launch
+NCU_TRAFFIC_BYTES = 2.282096e9 + 182.914048e6
+NCU_TRAFFIC_NOTE = ("ncu --set full, one launch of k_chol_super_update (super-panel c0=24 of 49 block columns, 16 systems): "
+                    "2.28 GB read + 0.18 GB written vs 2.34e11 flop => 95 flop/B, far above the FP64 ridge (~5.5 flop/B)")
 METRIC = "coadd_output_pixels_per_sec"
 UNIT = "output px/s"
 SEED0 = 1000
@@ -223,12 +228,22 @@ def run_gpu(args):
         gb.run()
         return gather_cube(gb.out_map, world, rank)
 
+    e2e_host = []
+
     def step_e2e():
+        t0 = time.perf_counter()
         g2 = GpuBlock(blk, tab)
         g2.prepare()
+        t1 = time.perf_counter()
         g2.run()
+        t2 = time.perf_counter()
         maps = g2.download()
         gather_cube(g2.out_map, world, rank)
+        t3 = time.perf_counter()
+        ms = torch.cuda.memory_stats()
+        e2e_host.append((round(1e3 * (t1 - t0), 1), round(1e3 * (t2 - t1), 1), round(1e3 * (t3 - t2), 1),
+                         ms.get("segment.all.allocated", 0), ms.get("segment.all.freed", 0),
+                         round(ms.get("reserved_bytes.all.current", 0) / 2**30, 2), ms.get("num_alloc_retries", 0)))
         return g2, maps
 
     for _ in range(max(args.warmup, 3)):
@@ -248,8 +263,25 @@ def run_gpu(args):
     t_res = e0.elapsed_time(e1) * 1e-3
     prof = _lib.profile_read()
     _lib.profile(0)
+    # ---- one extra step with the solve groups serialised on one stream: per-launch event intervals of the timed
+    # region above include time-sharing between the concurrent solve streams; this pass shows each kernel alone ----
+    from pyimcom_b200 import lakernel as GL
+
+    n_streams = GL.SOLVE_STREAMS
+    prof_serial = {}
+    if n_streams > 1:
+        GL.SOLVE_STREAMS = 1
+        step_resident()
+        barrier()
+        _lib.profile(1)
+        step_resident()
+        barrier()
+        prof_serial = _lib.profile_read()
+        _lib.profile(0)
+        GL.SOLVE_STREAMS = n_streams
     # ---- timed: end to end from host buffers ----
-    step_e2e()
+    for _ in range(3):  # warm-up: the caching allocators (device and pinned host) settle on this path's block sizes
+        step_e2e()
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -272,29 +304,55 @@ def run_gpu(args):
             pass
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
         hbm_src = "MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
-        stages = {}
-        for name, (ms, work, cnt) in prof.items():
-            tensor = name in ("chol_super_update", "chol_panel", "chol_inner_update", "back_super_update", "back_diag",
-                              "back_inner_update", "gemm_nt", "potrf_diag")
-            rate = work / (ms * 1e-3) / (1e12 if tensor else 1e9) if ms > 0 else 0.0
-            stages[name] = {"launches": cnt, "ms_total": round(ms, 3), "share_of_step": round(ms * 1e-3 / t_res, 4),
-                            "achieved": round(rate, 3), "unit": "TFLOP/s" if tensor else "GB/s",
-                            "frac": round(rate / (fp64_peak if tensor else hbm_peak), 4)}
+        TENSOR = ("chol_super_update", "chol_panel", "chol_inner_update", "back_super_update", "back_diag",
+                  "back_inner_update", "gemm_nt", "potrf_diag")
+
+        def stage_table(pr, t_total):
+            out = {}
+            for name, (ms, work, cnt) in pr.items():
+                tensor = name in TENSOR
+                rate = work / (ms * 1e-3) / (1e12 if tensor else 1e9) if ms > 0 else 0.0
+                out[name] = {"launches": cnt, "ms_total": round(ms, 3), "share_of_step": round(ms * 1e-3 / t_total, 4),
+                             "achieved": round(rate, 3), "unit": "TFLOP/s" if tensor else "GB/s",
+                             "frac": round(rate / (fp64_peak if tensor else hbm_peak), 4)}
+            return out
+
+        def dmma_total(pr):
+            ms = sum(pr[k][0] for k in pr if k.startswith(("chol_", "back_")))
+            fl = sum(pr[k][1] for k in pr if k.startswith(("chol_", "back_")))
+            return ms, fl
+
+        stages = stage_table(prof, t_res)
         dom = "chol_super_update"
         ms, work, cnt = prof.get(dom, (0.0, 0.0, 0))
         ach = work / (ms * 1e-3) / 1e12 if ms > 0 else 0.0
-        tensor_ms = sum(prof[k][0] for k in prof if k.startswith(("chol_", "back_")))
-        tensor_fl = sum(prof[k][1] for k in prof if k.startswith(("chol_", "back_")))
+        tensor_ms, tensor_fl = dmma_total(prof)
         roofline = {"bound": "tensor", "kernel": "k_chol_super_update (FP64 DMMA m8n8k4 tile GEMM, long-K)",
                     "achieved": round(ach, 3), "peak": round(fp64_peak, 3), "unit": "TFLOP/s",
-                    "frac": round(ach / fp64_peak, 4), "traffic": None,
+                    "frac": round(ach / fp64_peak, 4),
+                    "traffic": NCU_TRAFFIC_BYTES,
+                    "traffic_note": NCU_TRAFFIC_NOTE,
                     "peak_source": f"cuBLAS DGEMM {N}^3 through torch.matmul, best of 5, measured in this run "
                                    "(MEASURED_PEAKS.json has no FP64 entry)",
                     "launches": cnt, "avg_launch_ms": round(ms / max(cnt, 1), 4),
                     "flops_per_launch": work / max(cnt, 1),
+                    "note": (f"timed region runs {n_streams} concurrent solve streams: a launch's event interval includes the "
+                             "time it shares the SMs with the other streams' kernels; 'serialized' repeats the step on "
+                             "one stream") if n_streams > 1 else "one stream",
                     "all_dmma_kernels": {"achieved": round(tensor_fl / (tensor_ms * 1e-3) / 1e12, 3) if tensor_ms else 0,
-                                         "share_of_step": round(tensor_ms * 1e-3 / t_res, 4)},
+                                         "share_of_step": round(tensor_ms * 1e-3 / t_res, 4),
+                                         "flops_per_step": tensor_fl / max(args.steps, 1),
+                                         "achieved_wall": round(tensor_fl / t_res / 1e12, 3)},
                     "hbm_peak_gbs": hbm_peak, "hbm_peak_source": hbm_src, "stages": stages}
+        if prof_serial:
+            t_ser = sum(v[0] for v in prof_serial.values()) * 1e-3
+            ms_s, work_s, cnt_s = prof_serial.get(dom, (0.0, 0.0, 0))
+            ach_s = work_s / (ms_s * 1e-3) / 1e12 if ms_s > 0 else 0.0
+            sm, sf = dmma_total(prof_serial)
+            roofline["serialized"] = {"achieved": round(ach_s, 3), "frac": round(ach_s / fp64_peak, 4), "launches": cnt_s,
+                                      "avg_launch_ms": round(ms_s / max(cnt_s, 1), 4),
+                                      "all_dmma_kernels": {"achieved": round(sf / (sm * 1e-3) / 1e12, 3) if sm else 0},
+                                      "stages": stage_table(prof_serial, max(t_ser, 1e-9))}
         cores = os.cpu_count() or 1
         cpu = None
         if world == 1 and not args.no_cpu:
@@ -308,7 +366,8 @@ def run_gpu(args):
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": config_dict(cfg, n_stamps, {"n_input_px_per_stamp": n_in, "parallelism": f"blocks x{world}"}),
                 "e2e": {"value": world * px_per_step * args.steps / t_e2e, "unit": UNIT, "h2d_bytes_per_step": h2d,
-                        "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * t_e2e / args.steps},
+                        "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * t_e2e / args.steps,
+                        "host_ms_prepare_run_download": e2e_host[-args.steps:]},
                 "gpu_launches": int(launches), "stamps_per_sec": world * n_stamps * args.steps / t_res,
                 "clocks": clk.summary(), "roofline": roofline, "cpu_baseline": cpu}
         print(json.dumps(line), flush=True)

@@ -355,8 +355,7 @@ class GpuBlock:
             total = sum(size(nA, nB) for _, nA, nB in need)
             if total > cap:
                 self._pool = None
-                budget = self.pool_bytes or min(32 << 30, torch.cuda.mem_get_info()[0] // 4)
-                self._pool = torch.empty(max(total, int(budget) // 8), dtype=torch.float64, device="cuda")
+                self._pool = torch.empty(max(total, self._pool_target() // 8), dtype=torch.float64, device="cuda")
         desc = np.zeros(len(need), dtype=PAIRDESC_DTYPE)
         tiles = np.zeros(len(need) + 1, dtype=np.int64)
         points = 0.0
@@ -377,6 +376,25 @@ class GpuBlock:
                              int(tiles[-1]), ptr(self.d_tables), ptr(self.d_pair_lut), self.blk.n_inimage,
                              self.arena.ngrid, float(cfg.dscale), float(cfg.nc_ovl), float(cfg.flat_penalty),
                              self.arena.poly, ptr(self._pool), float(points), stream_handle())
+
+    def _pool_target(self) -> int:
+        """Bytes of the pair-block pool: everything the planned OutStamps can ever need if that fits the budget
+        (pool_bytes, default 16 GB or a quarter of the free HBM), else the budget (older blocks are then evicted)."""
+        if self.pool_bytes:
+            return int(self.pool_bytes)
+        seen, tot = set(), 0
+        for ji in self.order:
+            p = self.plans[ji]
+            if p.n == 0:
+                continue
+            for a in range(9):
+                for b in range(a, 9):
+                    key = (p.insts[a], p.insts[b])
+                    if key not in seen:
+                        seen.add(key)
+                        tot += self._inst_count(key[0]) * ((self._inst_count(key[1]) + 3) // 4 * 4)
+        budget = min(16 << 30, (torch.cuda.mem_get_info()[0] // 4) >> 28 << 28)
+        return int(min(8 * tot, budget))
 
     def _asm_desc(self, p) -> _lib.AsmDesc:
         d = _lib.AsmDesc()

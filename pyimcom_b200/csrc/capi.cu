@@ -67,12 +67,26 @@ struct ProfRec {
 static int g_prof_on = 0;
 static std::vector<ProfRec> g_prof;
 
+// events are pooled: creating them inside the timed region would put driver calls between the launches
+static std::vector<cudaEvent_t> g_event_pool;
+static size_t g_event_next = 0;
+
+static bool prof_event(cudaEvent_t* e) {
+    if (g_event_next == g_event_pool.size()) {
+        cudaEvent_t ne;
+        if (cudaEventCreate(&ne) != cudaSuccess) return false;
+        g_event_pool.push_back(ne);
+    }
+    *e = g_event_pool[g_event_next++];
+    return true;
+}
+
 void prof_begin(int kind, cudaStream_t st) {
     if (!g_prof_on) return;
     ProfRec r;
     r.kind = kind;
     r.work = 0.0;
-    if (cudaEventCreate(&r.a) != cudaSuccess || cudaEventCreate(&r.b) != cudaSuccess) return;
+    if (!prof_event(&r.a) || !prof_event(&r.b)) return;
     cudaEventRecord(r.a, st);
     g_prof.push_back(r);
 }
@@ -85,11 +99,8 @@ void prof_end(double work, cudaStream_t st) {
 }
 
 static void prof_reset() {
-    for (auto& r : g_prof) {
-        cudaEventDestroy(r.a);
-        cudaEventDestroy(r.b);
-    }
     g_prof.clear();
+    g_event_next = 0;  // the pooled events are reused by the next recording
 }
 
 }  // namespace b200
@@ -134,6 +145,13 @@ int b200_release_scratch(void) {
 }
 int b200_profile(int on) {
     prof_reset();
+    if (on) {  // pre-create events for ~8k launches so that the first recorded step does not pay for them
+        while (g_event_pool.size() < 16384) {
+            cudaEvent_t e;
+            B200_CUDA(cudaEventCreate(&e));
+            g_event_pool.push_back(e);
+        }
+    }
     g_prof_on = on;
     return 0;
 }

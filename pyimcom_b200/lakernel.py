@@ -17,6 +17,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import os
 import warnings
 from dataclasses import dataclass, field
 
@@ -161,18 +162,54 @@ def _padded_system(ds: DeviceSystem, incs):
     return W
 
 
+SOLVE_STREAMS = int(os.environ.get("B200_SOLVE_STREAMS", "3"))  # concurrent groups of systems in the batched factorisation (1 = everything on the caller's stream)
+_SIDE = {}
+
+
+def _side_streams(n):
+    dev = torch.cuda.current_device()
+    have = _SIDE.setdefault(dev, [])
+    while len(have) < n:
+        have.append(torch.cuda.Stream())
+    return have[:n]
+
+
 def _chol_solve_items(items):
     """Factor + solve A_k + sum(incs_k) for every item (ds, incs, j_out); the systems of all items go through
     the batched factorisation together (up to MAXB per launch sequence) and the LAPACK-style info codes are read
     back once.  Failing items take the repair branch of CholKernel._cholesky_wrapper (lakernel.py:262-279).
     Returns the list of solutions X_k (mpad, npad), rows = Ti."""
-    Ws = [_padded_system(ds, incs) for ds, incs, _ in items]
-    Xs = [ds.mB[j].clone() for ds, _, j in items]
+    n_items = len(items)
+    Xs = [None] * n_items
     infos = []
-    for c0 in range(0, len(items), _lib.MAXB):
-        info, _keep = chol_solve_batch(Ws[c0:c0 + _lib.MAXB], Xs[c0:c0 + _lib.MAXB])
-        infos.append(info)
-    del Ws
+    cur = torch.cuda.current_stream()
+    nstream = min(SOLVE_STREAMS, n_items) if n_items > 1 else 1
+    if nstream <= 1:
+        chunks = [(c0, min(c0 + _lib.MAXB, n_items), cur) for c0 in range(0, n_items, _lib.MAXB)]
+    else:
+        # independent groups of systems on separate streams: the serial diagonal-block factorisations and the partial
+        # last waves of one group's tile kernels are filled by the other group's work
+        per = min(_lib.MAXB, -(-n_items // nstream))
+        pool = _side_streams(nstream)
+        chunks = [(c0, min(c0 + per, n_items), pool[q % nstream]) for q, c0 in enumerate(range(0, n_items, per))]
+        for st in pool:
+            st.wait_stream(cur)
+    for c0, c1, st in chunks:
+        with torch.cuda.stream(st):
+            Ws = [_padded_system(ds, incs) for ds, incs, _ in items[c0:c1]]
+            for k in range(c0, c1):
+                ds, _, j = items[k]
+                Xs[k] = ds.mB[j].clone()
+                if st is not cur:
+                    Xs[k].record_stream(cur)  # consumed by the T-apply stage on the caller's stream
+            info, _keep = chol_solve_batch(Ws, Xs[c0:c1])
+            if st is not cur:
+                info.record_stream(cur)
+            infos.append(info)
+            del Ws
+    if nstream > 1:
+        for st in pool:
+            cur.wait_stream(st)
     bad = torch.cat(infos).cpu().numpy()
     if bad.any():
         shifts = {}

@@ -52,6 +52,8 @@ def test_struct_layouts(lib):
     assert ctypes.sizeof(lib.TableRef) == 24
     assert ctypes.sizeof(lib.SolveSys) == 48
     assert ctypes.sizeof(lib.FinalizeArgs) == 184
+    assert ctypes.sizeof(lib.PairDesc) == 40
+    assert ctypes.sizeof(lib.AsmDesc) == 1056  # 648 + 324 + 40 + 36 + 4, rounded up to the 8-byte alignment
 
 
 def test_seams_expose_reference_names():
