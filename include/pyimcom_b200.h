@@ -170,7 +170,7 @@ int b200_dev_chol_solve(const b200_solve_sys* sys, int nsys, int do_factor, int 
 /* W <- A (n x n) + sum(incs) on the diagonal, identity in rows/cols n..npad-1 (lakernel.py:295-299, 356). */
 int b200_dev_pad_system(double* W, int ldw, int n, int npad, const double* A, int lda, const double* incs, int ninc,
                         void* stream);
-/* C (M x N) = [C +/-] A (M x K) * B (N x K)^T; M,N multiples of 128, K multiple of 16; accumulate 0/+1/-1. */
+/* C (M x N) = [C +/-] A (M x K) * B (N x K)^T; M,N multiples of 128, K even; accumulate 0/+1/-1. */
 int b200_dev_gemm_nt(const double* A, int lda, const double* B, int ldb, double* C, int ldc, int M, int N, int K,
                      int accumulate, void* stream);
 int b200_dev_transpose(const double* A, int lda, double* At, int ldat, int rows, int cols, void* stream);

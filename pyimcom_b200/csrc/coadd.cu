@@ -75,27 +75,45 @@ __global__ void __launch_bounds__(FT) k_finalize(FinalizeArgs A) {
     for (int c0 = 0; c0 < A.n; c0 += CH) {
         const int cw = min(CH, A.n - c0);
         // ---- stream: combine nodes, D/N partials, fade + float32 cast, T32 store, tile fill ----
-        for (int j = lane; j < CH; j += 32) {
-            const int col = c0 + j;
-            double tv = 0.0;
-            if (live && j < cw) {
-                double ti;
-                if (A.w) {
-                    ti = 0.0;
+        // U independent 8-byte loads per operand and lane are issued before any of them is consumed: the stage is a
+        // pure HBM/L2 stream and needs bytes in flight, not arithmetic
+        constexpr int U = 8;
+        for (int jb = 0; jb < CH; jb += 32 * U) {
+            double tiv[U], bv[U];
 #pragma unroll
-                    for (int p = 0; p < 16; p++)
-                        if (p < A.nv) ti += A.Tpi[p * A.strideT + (size_t)a * A.ldt + col] * wnode[p];
-                } else {
-                    ti = A.Tpi[(size_t)a * A.ldt + col];
+            for (int u = 0; u < U; u++) {
+                const int j = jb + u * 32 + lane;
+                const int col = c0 + j;
+                const bool ok = live && j < cw;
+                double ti = 0.0;
+                if (ok) {
+                    if (A.w) {
+#pragma unroll
+                        for (int p = 0; p < 16; p++)
+                            if (p < A.nv) ti += __ldg(A.Tpi + p * A.strideT + (size_t)a * A.ldt + col) * wnode[p];
+                    } else {
+                        ti = __ldg(A.Tpi + (size_t)a * A.ldt + col);
+                    }
                 }
-                if (A.Ti64) A.Ti64[(size_t)a * A.ldt64 + col] = ti;
-                if (A.mB) dsum += A.mB[(size_t)a * A.ldb + col] * ti;
-                nsum += ti * ti;
-                const float t32 = fade32((float)ti, iy, ix, A.n2f, A.n2f, fk2, sfade);
-                if (A.T32) A.T32[(size_t)a * A.ldt32 + col] = t32;
-                tv = (double)t32;
+                tiv[u] = ti;
+                bv[u] = (ok && A.mB) ? __ldg(A.mB + (size_t)a * A.ldb + col) : 0.0;
             }
-            tile[warp * LDT + j] = tv;
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                const int j = jb + u * 32 + lane;
+                const int col = c0 + j;
+                double tv = 0.0;
+                if (live && j < cw) {
+                    const double ti = tiv[u];
+                    if (A.Ti64) A.Ti64[(size_t)a * A.ldt64 + col] = ti;
+                    dsum += bv[u] * ti;
+                    nsum += ti * ti;
+                    const float t32 = fade32((float)ti, iy, ix, A.n2f, A.n2f, fk2, sfade);
+                    if (A.T32) A.T32[(size_t)a * A.ldt32 + col] = t32;
+                    tv = (double)t32;
+                }
+                tile[warp * LDT + j] = tv;
+            }
         }
         __syncwarp();
         // per-(instamp,image) segment sums of the faded float32 T (coadd.py:1327-1337), from the tile row

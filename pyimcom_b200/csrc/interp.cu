@@ -97,18 +97,26 @@ __device__ __forceinline__ double d5512_taps(const double* __restrict__ g, int n
 // ncell = ceil(ngrid / P)): lanes whose positions differ by P samples now read neighbouring doubles of one plane.
 // The re-layout is done once per table when the arena is built; values and the order of the arithmetic are
 // untouched, so the result is bit-identical to the row-major path.
+// base + off (bytes, < 4 GiB) as ONE instruction (IMAD.WIDE.U32) instead of the four-instruction 64-bit index
+// arithmetic the compiler emits for  tables[offset64 + oy + ox]
+__device__ __forceinline__ const double* addr_u32(const void* base, unsigned off) {
+    unsigned long long r;
+    asm("mad.wide.u32 %0, %1, 1, %2;" : "=l"(r) : "r"(off), "l"(base));
+    return reinterpret_cast<const double*>(r);
+}
+
 template <int P>
 struct PolyOff {
-    int ox[10], oy[10];
+    unsigned ox[10], oy[10];  // byte offsets inside one table (a polyphase table is < 4 GiB)
     // integer corner (yi-4, xi-4); flip mirrors both axes (np.flip of the table, psfutil.py:1659-1665)
     __device__ __forceinline__ PolyOff(int yi, int xi, int ngrid, int ncell, int flip) {
-        const int plane = ncell * ncell;
+        const unsigned plane = (unsigned)(ncell * ncell);
 #pragma unroll
         for (int j = 0; j < 10; j++) {
-            const int x = flip ? ngrid - 1 - (xi - 4 + j) : xi - 4 + j;
-            const int y = flip ? ngrid - 1 - (yi - 4 + j) : yi - 4 + j;
-            ox[j] = (x % P) * plane + x / P;
-            oy[j] = (y % P) * (P * plane) + (y / P) * ncell;
+            const unsigned x = (unsigned)(flip ? ngrid - 1 - (xi - 4 + j) : xi - 4 + j);
+            const unsigned y = (unsigned)(flip ? ngrid - 1 - (yi - 4 + j) : yi - 4 + j);
+            ox[j] = ((x % P) * plane + x / P) * 8u;
+            oy[j] = ((y % P) * (P * plane) + (y / P) * (unsigned)ncell) * 8u;
         }
     }
 };
@@ -119,10 +127,10 @@ __device__ __forceinline__ double d5512_taps_poly(const double* __restrict__ g, 
     double acc = 0.0;
 #pragma unroll
     for (int i = 0; i < 10; i++) {
-        const double* p = g + o.oy[i];
+        const double* p = addr_u32(g, o.oy[i]);
         double strip = 0.0;
 #pragma unroll
-        for (int j = 0; j < 10; j++) strip = fma(wx[j], __ldg(p + o.ox[j]), strip);
+        for (int j = 0; j < 10; j++) strip = fma(wx[j], __ldg(addr_u32(p, o.ox[j])), strip);
         acc = fma(strip, wy[i], acc);
     }
     return acc;
@@ -318,7 +326,7 @@ __global__ void __launch_bounds__(256) k_build_A(const double* __restrict__ px, 
 // a self block are those of k_build_A, so both routes give bit-identical matrices.
 // ------------------------------------------------------------------------------------------------
 template <int P>
-__global__ void __launch_bounds__(256) k_pair_blocks(const double* __restrict__ gx, const double* __restrict__ gy,
+__global__ void __launch_bounds__(256, 3) k_pair_blocks(const double* __restrict__ gx, const double* __restrict__ gy,
                                                      const int* __restrict__ gimg, const PairDesc* __restrict__ descs,
                                                      const int* __restrict__ tile_prefix, int npair,
                                                      const double* __restrict__ tables,

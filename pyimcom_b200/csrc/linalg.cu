@@ -23,10 +23,15 @@ namespace b200 {
 
 namespace {
 
-constexpr int KT = 16;           // K extent of one pipeline stage
+constexpr int KT = 32;           // K extent of one pipeline stage
 constexpr int LDSM = KT + 4;     // smem row stride in doubles: 20 = 4 mod 16 -> conflict-free fragment loads
-constexpr int STAGES = 4;
-constexpr int GT = 256;          // threads per GEMM CTA
+constexpr int STAGES = 3;
+#ifndef B200_GEMM_WARPS_M
+#define B200_GEMM_WARPS_M 2
+#endif
+constexpr int WARPS_M = B200_GEMM_WARPS_M, WARPS_N = 4;  // warp grid over the 128x128 tile
+constexpr int GT = 32 * WARPS_M * WARPS_N;               // threads per GEMM CTA
+constexpr int MI = NB / WARPS_M / 8, NI = NB / WARPS_N / 8;  // m8n8 fragments per warp tile
 constexpr int SP = 4;            // block columns per super-panel (512 matrix columns)
 constexpr int STAGE_DOUBLES = 2 * NB * LDSM;
 constexpr size_t GEMM_SMEM = (size_t)STAGES * STAGE_DOUBLES * sizeof(double);  // 163840 B
@@ -59,29 +64,35 @@ __device__ __forceinline__ void gemm_tile_nt(const double* A, int lda, const dou
                                              int ldb, double* C, int ldc, int K, double* Ct, int ldct,
                                              double* smem) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int wm = warp >> 2, wn = warp & 3;  // 2 x 4 warps, warp tile 64 x 32
+    const int wm = warp / WARPS_N, wn = warp % WARPS_N;  // warp tile (8 MI) x (8 NI)
     const int g = lane >> 2, q = lane & 3;
+    constexpr int WTM = 8 * MI, WTN = 8 * NI;
 
-    double acc[8][4][2];
+    double acc[MI][NI][2];
     if (MODE == TILE_ASSIGN) {
 #pragma unroll
-        for (int mi = 0; mi < 8; mi++)
+        for (int mi = 0; mi < MI; mi++)
 #pragma unroll
-            for (int ni = 0; ni < 4; ni++) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
+            for (int ni = 0; ni < NI; ni++) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
     }
 
-    const int nk = K / KT;
-    // loader mapping: 1024 16-byte chunks per operand per stage; thread handles chunks tid + 256*r
+    const int nk = (K + KT - 1) / KT;
+    // loader mapping: 1024 16-byte chunks per operand per stage; thread handles chunks tid + GT*r
     auto load_stage = [&](int slot, int kt) {
         double* As = smem + (size_t)slot * STAGE_DOUBLES;
         double* Bs = As + NB * LDSM;
         const int k0 = kt * KT;
 #pragma unroll
-        for (int r = 0; r < 4; r++) {
+        for (int r = 0; r < NB * (KT / 2) / GT; r++) {
             const int c = tid + GT * r;
-            const int row = c >> 3, kc = (c & 7) * 2;
-            cp_async16(As + row * LDSM + kc, A + (size_t)row * lda + k0 + kc);
-            cp_async16(Bs + row * LDSM + kc, B + (size_t)row * ldb + k0 + kc);
+            const int row = c / (KT / 2), kc = (c % (KT / 2)) * 2;
+            if (k0 + kc < K) {
+                cp_async16(As + row * LDSM + kc, A + (size_t)row * lda + k0 + kc);
+                cp_async16(Bs + row * LDSM + kc, B + (size_t)row * ldb + k0 + kc);
+            } else {  // K tail of the last stage (K is even): zero operands contribute nothing
+                *reinterpret_cast<double2*>(As + row * LDSM + kc) = make_double2(0.0, 0.0);
+                *reinterpret_cast<double2*>(Bs + row * LDSM + kc) = make_double2(0.0, 0.0);
+            }
         }
     };
 #pragma unroll
@@ -91,11 +102,11 @@ __device__ __forceinline__ void gemm_tile_nt(const double* A, int lda, const dou
     }
     if (MODE != TILE_ASSIGN) {  // overlaps with the pipeline fill
 #pragma unroll
-        for (int mi = 0; mi < 8; mi++)
+        for (int mi = 0; mi < MI; mi++)
 #pragma unroll
-            for (int ni = 0; ni < 4; ni++) {
+            for (int ni = 0; ni < NI; ni++) {
                 const double2 v = *reinterpret_cast<const double2*>(
-                    C + (size_t)(wm * 64 + mi * 8 + g) * ldc + wn * 32 + ni * 8 + q * 2);
+                    C + (size_t)(wm * WTM + mi * 8 + g) * ldc + wn * WTN + ni * 8 + q * 2);
                 acc[mi][ni][0] = (MODE == TILE_SUB) ? -v.x : v.x;
                 acc[mi][ni][1] = (MODE == TILE_SUB) ? -v.y : v.y;
             }
@@ -105,27 +116,27 @@ __device__ __forceinline__ void gemm_tile_nt(const double* A, int lda, const dou
         __syncthreads();
         if (kt + STAGES - 1 < nk) load_stage((kt + STAGES - 1) % STAGES, kt + STAGES - 1);
         cp_async_commit();
-        const double* As = smem + (size_t)(kt % STAGES) * STAGE_DOUBLES + (wm * 64 + g) * LDSM + q;
-        const double* Bs = smem + (size_t)(kt % STAGES) * STAGE_DOUBLES + NB * LDSM + (wn * 32 + g) * LDSM + q;
+        const double* As = smem + (size_t)(kt % STAGES) * STAGE_DOUBLES + (wm * WTM + g) * LDSM + q;
+        const double* Bs = smem + (size_t)(kt % STAGES) * STAGE_DOUBLES + NB * LDSM + (wn * WTN + g) * LDSM + q;
 #pragma unroll
         for (int kk = 0; kk < KT / 4; kk++) {
-            double a[8], b[4];
+            double a[MI], b[NI];
 #pragma unroll
-            for (int mi = 0; mi < 8; mi++) a[mi] = As[mi * 8 * LDSM + kk * 4];
+            for (int mi = 0; mi < MI; mi++) a[mi] = As[mi * 8 * LDSM + kk * 4];
 #pragma unroll
-            for (int ni = 0; ni < 4; ni++) b[ni] = Bs[ni * 8 * LDSM + kk * 4];
+            for (int ni = 0; ni < NI; ni++) b[ni] = Bs[ni * 8 * LDSM + kk * 4];
 #pragma unroll
-            for (int mi = 0; mi < 8; mi++)
+            for (int mi = 0; mi < MI; mi++)
 #pragma unroll
-                for (int ni = 0; ni < 4; ni++) dmma884(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
+                for (int ni = 0; ni < NI; ni++) dmma884(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
         }
     }
     cp_async_wait<0>();
 #pragma unroll
-    for (int mi = 0; mi < 8; mi++)
+    for (int mi = 0; mi < MI; mi++)
 #pragma unroll
-        for (int ni = 0; ni < 4; ni++) {
-            const int r = wm * 64 + mi * 8 + g, c = wn * 32 + ni * 8 + q * 2;
+        for (int ni = 0; ni < NI; ni++) {
+            const int r = wm * WTM + mi * 8 + g, c = wn * WTN + ni * 8 + q * 2;
             double2 v;
             v.x = (MODE == TILE_SUB) ? -acc[mi][ni][0] : acc[mi][ni][0];
             v.y = (MODE == TILE_SUB) ? -acc[mi][ni][1] : acc[mi][ni][1];
@@ -561,13 +572,13 @@ int launch_chol_solve(const SolveSys* h_sys, int nsys, int do_factor, int do_sol
     return 0;
 }
 
-// C (M x N) = [C +/-] A (M x K) * B (N x K)^T ; M, N multiples of 128, K multiple of 16.
+// C (M x N) = [C +/-] A (M x K) * B (N x K)^T ; M, N multiples of 128, K even.
 // accumulate: 0 assign, 1 add, -1 subtract.
 int launch_gemm_nt(const double* A, int lda, const double* B, int ldb, double* C, int ldc, int M, int N, int K,
                    int accumulate, cudaStream_t st) {
     if (M <= 0 || N <= 0) return 0;
-    B200_REQUIRE(M % NB == 0 && N % NB == 0 && K % KT == 0 && K > 0 && lda % 2 == 0 && ldb % 2 == 0 && ldc % 2 == 0,
-                 "gemm_nt wants M,N multiples of 128, K multiple of 16, even leading dimensions");
+    B200_REQUIRE(M % NB == 0 && N % NB == 0 && K % 2 == 0 && K > 0 && lda % 2 == 0 && ldb % 2 == 0 && ldc % 2 == 0,
+                 "gemm_nt wants M,N multiples of 128, even K and leading dimensions");
     if (int rc = gemm_attrs()) return rc;
     dim3 grid(N / NB, M / NB);
     if (accumulate == 0)
