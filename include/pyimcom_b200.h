@@ -174,11 +174,23 @@ int b200_dev_pad_system(double* W, int ldw, int n, int npad, const double* A, in
 int b200_dev_gemm_nt(const double* A, int lda, const double* B, int ldb, double* C, int ldc, int M, int N, int K,
                      int accumulate, void* stream);
 int b200_dev_transpose(const double* A, int lda, double* At, int ldat, int rows, int cols, void* stream);
-/* np.linalg.eigh (lakernel.py:162, 201, 266): parallel one-sided Jacobi.  A (n x n, lda) is destroyed; Vt (n, ldv)
- * receives the eigenvectors as ROWS, lam (n) the eigenvalues (unsorted).  Returns the sweep count in *sweeps
- * (host int, may be NULL).  This call synchronises the stream once per sweep (convergence test). */
+/* np.linalg.eigh (lakernel.py:162, 201, 266): block Jacobi (pairs of 16-row blocks, 32x32 sub-problems in shared
+ * memory).  A (n x n, lda) is destroyed and must be padded with the identity up to ntot = 16 * (ceil(n/16) rounded up
+ * to even) rows and columns (lda, ldv >= ntot, even); Vt (ntot, ldv) receives the eigenvectors as ROWS, lam (n) the
+ * eigenvalues (unsorted).  Returns the sweep count in *sweeps (host int, may be NULL).  This call synchronises the
+ * stream once per sweep (convergence test). */
 int b200_dev_eigh(double* A, int lda, int n, double* Vt, int ldv, double* lam, int max_sweeps, int* sweeps,
                   void* stream);
+
+/* The same for up to B200_MAXB independent matrices at once (the OutStamps of a batch): every round is one launch
+ * over all systems, so the 16-row block pairs of all of them fill the GPU; a system that has converged drops out. */
+typedef struct b200_eigh_problem {
+    double* A;   /* (ntot, lda) in, destroyed; identity padding as for b200_dev_eigh */
+    double* Vt;  /* (ntot, ldv) out: eigenvectors as rows */
+    double* lam; /* (n) out */
+    int lda, ldv, n, pad_;
+} b200_eigh_problem;
+int b200_dev_eigh_batch(const b200_eigh_problem* problems, int nsys, int max_sweeps, int* sweeps, void* stream);
 
 /* ---- 4. device: per-output-pixel Lagrange multiplier (stage b) --------------------------------- */
 int b200_dev_lakernel1(const double* lam, const double* mPhalf, int ldp, int m, int n, double C, double targetleak,

@@ -62,6 +62,12 @@ class AsmDesc(C.Structure):
                 ("pad_", i32)]
 
 
+class EighProblem(C.Structure):
+    """b200_eigh_problem"""
+
+    _fields_ = [("A", vp), ("Vt", vp), ("lam", vp), ("lda", i32), ("ldv", i32), ("n", i32), ("pad_", i32)]
+
+
 class FinalizeArgs(C.Structure):
     """b200_finalize_args"""
 
@@ -97,6 +103,7 @@ PROTOTYPES = {
     "b200_dev_pad_system": [vp, i32, i32, i32, vp, i32, C.POINTER(f64), i32, vp],
     "b200_dev_gemm_nt": [vp, i32, vp, i32, vp, i32, i32, i32, i32, i32, vp],
     "b200_dev_transpose": [vp, i32, vp, i32, i32, i32, vp],
+    "b200_dev_eigh_batch": [C.POINTER(EighProblem), i32, i32, C.POINTER(i32), vp],
     "b200_dev_eigh": [vp, i32, i32, vp, i32, vp, i32, C.POINTER(i32), vp],
     "b200_dev_lakernel1": [vp, vp, i32, i32, i32, f64, f64, f64, f64, i32, vp, vp, vp, vp, i32, f64, vp],
     "b200_dev_eigen_single": [vp, vp, i32, i32, i32, f64, f64, vp, vp, vp, i32, vp],

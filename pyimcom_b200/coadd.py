@@ -26,7 +26,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from .lakernel import SOLVERS, ApplySpec, DeviceSystem, apply_T, eigen_decompose, ptr, rup, solve_chol_batch, solve_eigen
+from .lakernel import SOLVERS, ApplySpec, DeviceSystem, apply_T, eigen_decompose_batch, ptr, rup, solve_chol_batch, solve_eigen
 from .lakernel import stream_handle
 from .lakernel import trapezoid_weights
 from .psfovl_host import anchor
@@ -208,6 +208,8 @@ class GpuBlock:
                 io = tab.get_io(Ga)
                 io_c[(Ga, ka)] = [self.arena.offset(io, (tab.grp_index(Ga, ka), o)) for o in range(cfg.n_out)]
             lut_io[ca, :] = io_c[(Ga, ka)]
+            if self.a_cache:  # the per-stamp in-in look-up table is only read by the fused kernel
+                continue
             for (Gb, kb) in gk:
                 key = (Ga, ka, Gb, kb)
                 if key not in pair:
@@ -477,6 +479,9 @@ class GpuBlock:
                 continue
             ds, indata = self.build_system(k)
             live.append((q, k, p, ds, indata))
+        if self.kernel == "Eigen" and live:  # one decomposition per stamp serves every output PSF; all stamps together
+            for (q, k, p, ds, indata), eig in zip(live, eigen_decompose_batch([t[3] for t in live])):
+                kept[q]["_eig"] = eig
         for j_out in range(cfg.n_out):
             if self.kernel == "Cholesky":
                 kos = solve_chol_batch([t[3] for t in live], cfg, j_out) if live else []
@@ -484,8 +489,6 @@ class GpuBlock:
                 if self.kernel == "Cholesky":
                     ko = kos[u]
                 elif self.kernel == "Eigen":
-                    if j_out == 0:
-                        kept[q]["_eig"] = eigen_decompose(ds)
                     ko = solve_eigen(ds, cfg, j_out, eig=kept[q]["_eig"])
                 else:
                     ko = SOLVERS[self.kernel](ds, cfg, j_out)
@@ -538,6 +541,8 @@ class GpuBlock:
     def batch_size(self) -> int:
         """OutStamps solved together: as many as MAXB systems allow, within an HBM budget (A, W, mBhalf and X of
         every stamp of the batch are live at once: ~(2 npad^2 + 2 n_out mpad npad) * 8 bytes per kappa node)."""
+        if self.kernel == "Eigen" and self.order:
+            return min(self.max_batch, _lib.MAXB)
         if self.kernel != "Cholesky" or not self.order:
             return 1
         cfg = self.cfg

@@ -345,6 +345,10 @@ int b200_dev_gemm_nt(const double* A, int lda, const double* B, int ldb, double*
 int b200_dev_transpose(const double* A, int lda, double* At, int ldat, int rows, int cols, void* s) {
     return launch_transpose(A, lda, At, ldat, rows, cols, ST(s));
 }
+int b200_dev_eigh_batch(const b200_eigh_problem* problems, int nsys, int max_sweeps, int* sweeps, void* s) {
+    B200_REQUIRE(problems != nullptr || nsys <= 0, "eigh_batch: null problem list");
+    return launch_jacobi_eigh_batch(problems, nsys, max_sweeps, sweeps, ST(s));
+}
 int b200_dev_eigh(double* A, int lda, int n, double* Vt, int ldv, double* lam, int max_sweeps, int* sweeps, void* s) {
     return launch_jacobi_eigh(A, lda, n, Vt, ldv, lam, max_sweeps, sweeps, ST(s));
 }

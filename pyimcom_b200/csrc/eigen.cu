@@ -1,19 +1,16 @@
 // Symmetric eigendecomposition for EigenKernel and the Cholesky repair branch:
 // replaces np.linalg.eigh at lakernel.py:162, 201, 266.
 //
-// Parallel two-sided (classical) Jacobi in implicit form: the kernel keeps G = V^T A and V^T (V = I
-// initially) and never stores H = V^T A V; the three entries a rotation of the pair (p, q) needs are dot
-// products of rows, h_pp = g_p . v_p, h_qq = g_q . v_q, h_pq = g_p . v_q, and the rotation that zeroes h_pq
-// is applied to rows p, q of both G and V^T (which is H <- J^T H J).  Working on H rather than on the Gram
-// matrix G G^T = V^T A^2 V (one-sided Hestenes) keeps the absolute accuracy at eps |A|_F for the small
+// Two-sided (classical) Jacobi in implicit, blocked form: the kernels keep G = V^T A and V^T (V = I initially) and
+// never store H = V^T A V; the entries a rotation needs are dot products of rows, h_pq = g_p . v_q, and a rotation
+// of the pair (p, q) is applied to rows p, q of both G and V^T (which is H <- J^T H J).  Working on H rather than on
+// the Gram matrix G G^T = V^T A^2 V (one-sided Hestenes) keeps the absolute accuracy at eps |A|_F for the small
 // eigenvalues too, which is what LAPACK's eigh delivers and what 1/(lam + kappa) in EigenKernel needs.
-// Pairs are scheduled by the round-robin ("circle") tournament: npl/2 disjoint pairs per round, npl - 1
-// rounds per sweep, one kernel launch per round, one CTA per pair.
-// The pair (p,q) is skipped when |h_pq| <= tol sqrt|h_pp h_qq| (tol = max(1e-15, sqrt(n) eps)) or when
-// |h_pq| <= 2 sqrt(n) eps |A|_F (the rounding floor of the implicit dot products): any orthonormal basis of a
-// numerically degenerate subspace serves the callers (T, Sigma and U/C are invariant to it).
+// Rotations are skipped when |h_pq| <= 2 sqrt(n) eps |A|_F (the rounding floor of the implicit dot products): any
+// orthonormal basis of a numerically degenerate subspace serves the callers (T, Sigma and U/C are invariant to it).
 // Every reduction uses a fixed thread -> element mapping and a fixed tree: the result is deterministic.
 #include <math.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "kernels.h"
@@ -49,18 +46,21 @@ __device__ __forceinline__ void block_sum3(double& a, double& b, double& c, doub
     c = tc;
 }
 
-__global__ void k_jacobi_init(double* __restrict__ Vt, int ldv, int n, const double* __restrict__ G, int lda,
+// V^T = I on the whole padded range (ntot rows/columns); per-row squared norms of the real n x n part of A
+__global__ void k_jacobi_init(double* __restrict__ Vt, int ldv, int n, int ntot, const double* __restrict__ G, int lda,
                               double* __restrict__ fro2) {
     __shared__ double red[40];
     const int r = blockIdx.x;
     double s = 0.0;
-    for (int c = threadIdx.x; c < n; c += blockDim.x) {
+    for (int c = threadIdx.x; c < ntot; c += blockDim.x) {
         Vt[(size_t)r * ldv + c] = (r == c) ? 1.0 : 0.0;
-        const double v = G[(size_t)r * lda + c];
-        s += v * v;
+        if (r < n && c < n) {
+            const double v = G[(size_t)r * lda + c];
+            s += v * v;
+        }
     }
     s = block_sum(s, red);
-    if (threadIdx.x == 0) fro2[r] = s;
+    if (threadIdx.x == 0 && r < n) fro2[r] = s;
 }
 
 // sum of the per-row squared norms -> state[0] = |A|_F^2 (single CTA, deterministic)
@@ -72,13 +72,34 @@ __global__ void k_jacobi_fro(const double* __restrict__ fro2, int n, double* __r
     if (threadIdx.x == 0) state[0] = s;
 }
 
-__global__ void __launch_bounds__(JT) k_jacobi_round(double* __restrict__ G, int lda, double* __restrict__ Vt, int ldv,
-                                                     int n, int npl, int round, double tol,
-                                                     const double* __restrict__ state, int* __restrict__ nrot) {
-    __shared__ double red[32];
-    // circle method: player npl-1 is fixed, the others rotate
-    const int k = blockIdx.x, mod = npl - 1;
-    int p, q;
+// ---- block Jacobi round ---------------------------------------------------------------------------------------
+// The row-pair kernel above moves 8 rows of length n through L2 for ONE rotation.  Here a CTA takes a PAIR OF
+// 16-ROW BLOCKS (P, Q): it forms the 32x32 matrix H_sub = G_PQ V_PQ^T (= V_PQ^T A V_PQ) with one pass over the 64
+// rows, runs one cyclic sweep of two-sided Jacobi on it in shared memory (496 rotations, accumulated in J), and
+// applies J^T to the 32 rows of G and of V^T with a second pass: 496 row pairs per visit for the traffic of 16.
+// Block pairs follow the same round-robin tournament (nblk/2 disjoint pairs per round = one launch, nblk - 1 rounds
+// per sweep).  All reductions have a fixed order: the result is deterministic.
+constexpr int BJ = 16;           // rows per block
+constexpr int B2 = 2 * BJ;       // rows per block pair
+constexpr int BCK = 128;         // columns per chunk
+constexpr int LDK = B2 + 2;      // phase 1: k-major chunk [BCK][LDK] (32 rows contiguous per k)
+constexpr int LDX = BCK + 4;     // phase 4: row-major chunk [B2][LDX]
+constexpr int LDS_ = B2 + 1;     // S and J: [B2][LDS_]
+constexpr size_t BJ_SMEM = sizeof(double) * ((size_t)2 * BCK * LDK + 2 * B2 * B2 + 2 * B2 * LDS_ + 64);
+
+struct EighSys {
+    double* G;
+    double* Vt;
+    int ldg, ldv, nblk;  // nblk even (>= 2): number of 16-row blocks, padding blocks carry the identity
+    double floor1;       // 2 sqrt(n) eps |A|_F
+    int* nrot;
+};
+struct EighBatch {
+    EighSys s[MAXB];
+};
+
+__device__ __forceinline__ void circle_pair(int npl, int round, int k, int& p, int& q) {
+    const int mod = npl - 1;
     if (k == 0) {
         p = npl - 1;
         q = round % mod;
@@ -91,35 +112,177 @@ __global__ void __launch_bounds__(JT) k_jacobi_round(double* __restrict__ G, int
         p = q;
         q = t;
     }
-    if (q >= n) return;  // dummy player of an odd-sized problem
-    double* gp = G + (size_t)p * lda;
-    double* gq = G + (size_t)q * lda;
-    double* vp = Vt + (size_t)p * ldv;
-    double* vq = Vt + (size_t)q * ldv;
-    double a = 0.0, b = 0.0, g = 0.0;
-    for (int c = threadIdx.x; c < n; c += JT) {
-        const double x = gp[c], y = gq[c], u = vp[c], w = vq[c];
-        a += x * u;
-        b += y * w;
-        g += x * w;
+}
+
+__global__ void __launch_bounds__(256, 2) k_jacobi_block_round(EighBatch bt, int round) {
+    extern __shared__ __align__(16) double sm[];
+    const EighSys& sy = bt.s[blockIdx.y];
+    const int npl = sy.nblk;
+    if (npl < 2 || (int)blockIdx.x >= npl / 2 || round >= npl - 1) return;
+    int P, Q;
+    circle_pair(npl, round, blockIdx.x, P, Q);
+    const int ncol = npl * BJ;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    double* Gk = sm;                      // [BCK][LDK]  G chunk, k-major
+    double* Vk = Gk + BCK * LDK;          // [BCK][LDK]  V chunk, k-major
+    double* Hp = Vk + BCK * LDK;          // [2 K-halves][32][32] partial H
+    double* S = Hp + 2 * B2 * B2;         // [32][33]
+    double* J = S + B2 * LDS_;            // [32][33]
+    double* cs = J + B2 * LDS_;           // [16][2] rotation of each pair of the inner round (c, s); s = 0: skip
+    __shared__ int s_any;
+    auto grow = [&](int r) { return (r < BJ ? P * BJ + r : Q * BJ + (r - BJ)); };
+
+    // ---- phase 1: H = G_PQ V_PQ^T.  Warp w: K half (w & 1) of every chunk, rows 8 (w >> 1) .. +8; lane tile 2 rows x
+    // 4 columns; the two partial H are added in a fixed order afterwards.
+    const int kh = warp & 1;
+    const int a0 = 8 * (warp >> 1) + 2 * (lane >> 3), b0 = 4 * (lane & 7);
+    double acc[2][4];
+#pragma unroll
+    for (int i = 0; i < 2; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) acc[i][j] = 0.0;
+    for (int c0 = 0; c0 < ncol; c0 += BCK) {
+        __syncthreads();
+        for (int e = tid; e < B2 * BCK; e += 256) {
+            const int r = e / BCK, k = e - r * BCK;
+            const int c = c0 + k;
+            const size_t gr = (size_t)grow(r);
+            Gk[k * LDK + r] = c < ncol ? sy.G[gr * sy.ldg + c] : 0.0;
+            Vk[k * LDK + r] = c < ncol ? sy.Vt[gr * sy.ldv + c] : 0.0;
+        }
+        __syncthreads();
+#pragma unroll 8
+        for (int kk = 0; kk < BCK / 2; kk++) {
+            const int k = kh * (BCK / 2) + kk;
+            const double2 g = *reinterpret_cast<const double2*>(Gk + k * LDK + a0);
+            const double2 v0 = *reinterpret_cast<const double2*>(Vk + k * LDK + b0);
+            const double2 v1 = *reinterpret_cast<const double2*>(Vk + k * LDK + b0 + 2);
+            acc[0][0] = fma(g.x, v0.x, acc[0][0]);
+            acc[0][1] = fma(g.x, v0.y, acc[0][1]);
+            acc[0][2] = fma(g.x, v1.x, acc[0][2]);
+            acc[0][3] = fma(g.x, v1.y, acc[0][3]);
+            acc[1][0] = fma(g.y, v0.x, acc[1][0]);
+            acc[1][1] = fma(g.y, v0.y, acc[1][1]);
+            acc[1][2] = fma(g.y, v1.x, acc[1][2]);
+            acc[1][3] = fma(g.y, v1.y, acc[1][3]);
+        }
     }
-    block_sum3(a, b, g, red);
-    const double ab = sqrt(fabs(a)) * sqrt(fabs(b));
-    const double floor1 = 2.0 * 2.220446049250313e-16 * sqrt((double)n * state[0]);  // 2 sqrt(n) eps |A|_F
-    if (!(fabs(g) > tol * ab) || fabs(g) <= floor1) return;
-    const double zeta = (b - a) / (2.0 * g);
-    const double t = (zeta >= 0.0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
-    const double cs = 1.0 / sqrt(1.0 + t * t), sn = cs * t;
-    double *op = gp, *oq = gq, *wp = vp, *wq = vq;
-    for (int c = threadIdx.x; c < n; c += JT) {
-        const double x = gp[c], y = gq[c];
-        op[c] = cs * x - sn * y;
-        oq[c] = sn * x + cs * y;
-        const double u = vp[c], w = vq[c];
-        wp[c] = cs * u - sn * w;
-        wq[c] = sn * u + cs * w;
+#pragma unroll
+    for (int i = 0; i < 2; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) Hp[(kh * B2 + a0 + i) * B2 + b0 + j] = acc[i][j];
+    __syncthreads();
+    // ---- phase 2: S = (H + H^T) / 2, J = I; anything to do?
+    if (tid == 0) s_any = 0;
+    for (int e = tid; e < B2 * B2; e += 256) {
+        const int a = e >> 5, b = e & 31;
+        const double h = Hp[a * B2 + b] + Hp[(B2 + a) * B2 + b];
+        const double ht = Hp[b * B2 + a] + Hp[(B2 + b) * B2 + a];
+        S[a * LDS_ + b] = 0.5 * (h + ht);
+        J[a * LDS_ + b] = (a == b) ? 1.0 : 0.0;
     }
-    if (threadIdx.x == 0) atomicAdd(nrot, 1);
+    __syncthreads();
+    {
+        int act = 0;
+        for (int e = tid; e < B2 * B2; e += 256) {
+            const int a = e >> 5, b = e & 31;
+            if (a != b && fabs(S[a * LDS_ + b]) > sy.floor1) act = 1;
+        }
+        if (act) s_any = 1;  // benign race: every writer stores 1
+    }
+    __syncthreads();
+    if (!s_any) return;
+    // ---- phase 3: one cyclic sweep of two-sided Jacobi on S (32 x 32), rotations accumulated in J.
+    // 16 disjoint pairs per inner round, 16 threads per pair.
+    const int pr = tid >> 4, sub = tid & 15;
+    int napplied = 0;
+    for (int rnd = 0; rnd < B2 - 1; rnd++) {
+        int p, q;
+        circle_pair(B2, rnd, pr, p, q);
+        if (sub == 0) {
+            const double a = S[p * LDS_ + p], b = S[q * LDS_ + q], g = S[p * LDS_ + q];
+            double c = 1.0, s = 0.0;
+            if (fabs(g) > sy.floor1) {
+                const double zeta = (b - a) / (2.0 * g);
+                const double t = (zeta >= 0.0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+                c = 1.0 / sqrt(1.0 + t * t);
+                s = c * t;
+            }
+            cs[2 * pr] = c;
+            cs[2 * pr + 1] = s;
+        }
+        __syncthreads();
+        const double c = cs[2 * pr], s = cs[2 * pr + 1];
+        if (s != 0.0) {  // rows p, q:  S <- R^T S
+            napplied = 1;
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                const int col = sub + 16 * h;
+                const double x = S[p * LDS_ + col], y = S[q * LDS_ + col];
+                S[p * LDS_ + col] = c * x - s * y;
+                S[q * LDS_ + col] = s * x + c * y;
+            }
+        }
+        __syncthreads();
+        if (s != 0.0) {  // columns p, q:  S <- S R,  J <- J R
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                const int row = sub + 16 * h;
+                const double x = S[row * LDS_ + p], y = S[row * LDS_ + q];
+                S[row * LDS_ + p] = c * x - s * y;
+                S[row * LDS_ + q] = s * x + c * y;
+                const double u = J[row * LDS_ + p], w = J[row * LDS_ + q];
+                J[row * LDS_ + p] = c * u - s * w;
+                J[row * LDS_ + q] = s * u + c * w;
+            }
+        }
+        __syncthreads();
+    }
+    if (!__syncthreads_or(napplied)) return;
+    if (tid == 0) atomicAdd(sy.nrot, 1);
+    // ---- phase 4: rows <- J^T rows, for G and V^T.  Thread tile: 4 rows (4*warp ..) x 4 columns (4*lane ..).
+    double* X = sm;  // [B2][LDX] row-major chunk (reuses the phase-1 buffers)
+    for (int arr = 0; arr < 2; arr++) {
+        double* base = arr ? sy.Vt : sy.G;
+        const int ld = arr ? sy.ldv : sy.ldg;
+        for (int c0 = 0; c0 < ncol; c0 += BCK) {
+            __syncthreads();
+            for (int e = tid; e < B2 * (BCK / 2); e += 256) {
+                const int r = e / (BCK / 2), k2 = (e - r * (BCK / 2)) * 2;
+                const int c = c0 + k2;
+                double2 t = make_double2(0.0, 0.0);
+                if (c < ncol) t = *reinterpret_cast<const double2*>(base + (size_t)grow(r) * ld + c);
+                *reinterpret_cast<double2*>(X + r * LDX + k2) = t;
+            }
+            __syncthreads();
+            double o[4][4];
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+#pragma unroll
+                for (int j = 0; j < 4; j++) o[i][j] = 0.0;
+#pragma unroll 4
+            for (int b = 0; b < B2; b++) {
+                const double2 x0 = *reinterpret_cast<const double2*>(X + b * LDX + 4 * lane);
+                const double2 x1 = *reinterpret_cast<const double2*>(X + b * LDX + 4 * lane + 2);
+                const double xv[4] = {x0.x, x0.y, x1.x, x1.y};
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    const double jt = J[b * LDS_ + 4 * warp + i];  // J^T[a][b] = J[b][a]
+#pragma unroll
+                    for (int j = 0; j < 4; j++) o[i][j] = fma(jt, xv[j], o[i][j]);
+                }
+            }
+            const int c = c0 + 4 * lane;
+            if (c < ncol) {
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    double* dst = base + (size_t)grow(4 * warp + i) * ld + c;
+                    *reinterpret_cast<double2*>(dst) = make_double2(o[i][0], o[i][1]);
+                    *reinterpret_cast<double2*>(dst + 2) = make_double2(o[i][2], o[i][3]);
+                }
+            }
+        }
+    }
 }
 
 __global__ void __launch_bounds__(JT) k_jacobi_finish(const double* __restrict__ G, int lda,
@@ -135,45 +298,98 @@ __global__ void __launch_bounds__(JT) k_jacobi_finish(const double* __restrict__
 
 }  // namespace
 
+int launch_jacobi_eigh_batch(const EighProblem* pr, int nsys, int max_sweeps, int* sweeps_done, cudaStream_t st) {
+    if (sweeps_done) *sweeps_done = 0;
+    if (nsys <= 0) return 0;
+    B200_REQUIRE(nsys <= MAXB, "at most MAXB eigenproblems per batched call");
+    static bool attr = false;
+    if (!attr) {
+        B200_CUDA(cudaFuncSetAttribute(k_jacobi_block_round, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BJ_SMEM));
+        attr = true;
+    }
+    // device state per system: |A|_F^2, nmax per-row norms; then the nsys rotation counters
+    int nmax = 0;
+    for (int q = 0; q < nsys; q++) nmax = pr[q].n > nmax ? pr[q].n : nmax;
+    if (nmax <= 0) return 0;
+    const size_t per = (size_t)nmax + 2;
+    void* wsv = nullptr;
+    if (int rc = scratch(7, sizeof(double) * per * nsys + sizeof(int) * MAXB + 64, &wsv)) return rc;
+    double* state = (double*)wsv;
+    int* nrot = (int*)(state + per * nsys);
+    EighBatch bt;
+    int nblk_max = 0;
+    for (int q = 0; q < nsys; q++) {
+        const EighProblem& p = pr[q];
+        int nblk = (p.n + BJ - 1) / BJ;
+        nblk += nblk & 1;
+        if (nblk < 2) nblk = 2;
+        const int ntot = nblk * BJ;
+        B200_REQUIRE(p.n > 0 && p.lda >= ntot && p.ldv >= ntot && p.lda % 2 == 0 && p.ldv % 2 == 0,
+                     "eigh: A and Vt must be padded (identity) to a multiple of 32 rows/columns, even leading dimensions");
+        double* st_q = state + per * q;
+        k_jacobi_init<<<ntot, 256, 0, st>>>(p.Vt, p.ldv, p.n, ntot, p.A, p.lda, st_q + 1);
+        k_jacobi_fro<<<1, 256, 0, st>>>(st_q + 1, p.n, st_q);
+        B200_LAUNCHED(2);
+        bt.s[q].G = p.A;
+        bt.s[q].Vt = p.Vt;
+        bt.s[q].ldg = p.lda;
+        bt.s[q].ldv = p.ldv;
+        bt.s[q].nblk = p.n > 1 ? nblk : 0;
+        bt.s[q].nrot = nrot + q;
+        nblk_max = nblk > nblk_max ? nblk : nblk_max;
+    }
+    for (int q = nsys; q < MAXB; q++) {
+        bt.s[q] = bt.s[0];
+        bt.s[q].nblk = 0;
+    }
+    B200_CUDA(cudaGetLastError());
+    double fro2_h[MAXB];
+    for (int q = 0; q < nsys; q++)
+        B200_CUDA(cudaMemcpyAsync(&fro2_h[q], state + per * q, sizeof(double), cudaMemcpyDeviceToHost, st));
+    B200_CUDA(cudaStreamSynchronize(st));
+    double floor_mult = 1.0;
+    if (const char* e = getenv("B200_EIGH_FLOOR_MULT")) floor_mult = atof(e);  // experiment knob
+    for (int q = 0; q < nsys; q++)
+        bt.s[q].floor1 = floor_mult * 2.0 * 2.220446049250313e-16 * sqrt((double)pr[q].n * fro2_h[q]);
+    int sweep = 0;
+    prof_begin(PROF_EIGH, st);
+    for (; sweep < max_sweeps; sweep++) {
+        bool live = false;
+        for (int q = 0; q < nsys; q++) live = live || bt.s[q].nblk > 0;
+        if (!live) break;
+        B200_CUDA(cudaMemsetAsync(nrot, 0, sizeof(int) * MAXB, st));
+        for (int r = 0; r < nblk_max - 1; r++)
+            k_jacobi_block_round<<<dim3(nblk_max / 2, nsys), 256, BJ_SMEM, st>>>(bt, r);
+        B200_LAUNCHED(nblk_max - 1);
+        B200_CUDA(cudaGetLastError());
+        int h[MAXB];
+        B200_CUDA(cudaMemcpyAsync(h, nrot, sizeof(int) * nsys, cudaMemcpyDeviceToHost, st));
+        B200_CUDA(cudaStreamSynchronize(st));
+        for (int q = 0; q < nsys; q++)
+            if (h[q] == 0) bt.s[q].nblk = 0;  // converged: its CTAs exit at once from now on
+    }
+    prof_end(0.0, st);
+    if (sweeps_done) *sweeps_done = sweep;
+    for (int q = 0; q < nsys; q++) {
+        k_jacobi_finish<<<pr[q].n, JT, 0, st>>>(pr[q].A, pr[q].lda, pr[q].Vt, pr[q].ldv, pr[q].n, pr[q].lam);
+        B200_LAUNCHED(1);
+    }
+    B200_CUDA(cudaGetLastError());
+    return 0;
+}
+
 int launch_jacobi_eigh(double* A, int lda, int n, double* Vt, int ldv, double* lam, int max_sweeps, int* sweeps_done,
                        cudaStream_t st) {
     if (sweeps_done) *sweeps_done = 0;
     if (n <= 0) return 0;
-    B200_REQUIRE(lda >= n && ldv >= n, "eigh: leading dimensions too small");
-    // device state: [0] |A|_F^2 ; then n per-row norms ; then the rotation counter
-    void* wsv = nullptr;
-    if (int rc = scratch(7, sizeof(double) * (size_t)(n + 2) + 64, &wsv)) return rc;
-    double* state = (double*)wsv;
-    double* fro2 = state + 1;
-    int* nrot = (int*)(state + n + 2);
-    k_jacobi_init<<<n, 256, 0, st>>>(Vt, ldv, n, A, lda, fro2);
-    B200_LAUNCH_CHECK();
-    k_jacobi_fro<<<1, 256, 0, st>>>(fro2, n, state);
-    B200_LAUNCH_CHECK();
-    if (n > 1) {
-        const int npl = n + (n & 1);
-        double tol = sqrt((double)n) * 2.220446049250313e-16;
-        if (tol < 1e-15) tol = 1e-15;
-        int sweep = 0;
-        for (; sweep < max_sweeps; sweep++) {
-            B200_CUDA(cudaMemsetAsync(nrot, 0, sizeof(int), st));
-            for (int r = 0; r < npl - 1; r++)
-                k_jacobi_round<<<npl / 2, JT, 0, st>>>(A, lda, Vt, ldv, n, npl, r, tol, state, nrot);
-            B200_LAUNCHED(npl - 1);
-            B200_CUDA(cudaGetLastError());
-            int h = 0;
-            B200_CUDA(cudaMemcpyAsync(&h, nrot, sizeof(int), cudaMemcpyDeviceToHost, st));
-            B200_CUDA(cudaStreamSynchronize(st));
-            if (h == 0) {
-                sweep++;
-                break;
-            }
-        }
-        if (sweeps_done) *sweeps_done = sweep;
-    }
-    k_jacobi_finish<<<n, JT, 0, st>>>(A, lda, Vt, ldv, n, lam);
-    B200_LAUNCH_CHECK();
-    return 0;
+    EighProblem p;
+    p.A = A;
+    p.Vt = Vt;
+    p.lam = lam;
+    p.lda = lda;
+    p.ldv = ldv;
+    p.n = n;
+    return launch_jacobi_eigh_batch(&p, 1, max_sweeps, sweeps_done, st);
 }
 
 }  // namespace b200

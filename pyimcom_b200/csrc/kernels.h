@@ -14,6 +14,7 @@ using SolveSys = ::b200_solve_sys;
 using FinalizeArgs = ::b200_finalize_args;
 using PairDesc = ::b200_pair_desc;
 using AsmDesc = ::b200_asm_desc;
+using EighProblem = ::b200_eigh_problem;
 
 constexpr int NB = B200_NB;      // Cholesky/TRSM block size == DMMA GEMM tile edge
 constexpr int MAXB = B200_MAXB;  // systems per batched launch (descriptors travel as kernel parameters)
@@ -86,6 +87,7 @@ int launch_iter_cg(const double* AA, int lda, double diag_add, const double* mB,
                    double rtol, int maxiter, double* Ti, int ldt, int* niter, int* nsel, cudaStream_t s);
 
 // eigen.cu
+int launch_jacobi_eigh_batch(const EighProblem* pr, int nsys, int max_sweeps, int* sweeps_done, cudaStream_t s);
 int launch_jacobi_eigh(double* A, int lda, int n, double* Vt, int ldv, double* lam, int max_sweeps, int* sweeps_done,
                        cudaStream_t s);
 

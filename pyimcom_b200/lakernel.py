@@ -145,14 +145,32 @@ def chol_solve_batch(Ws, Xs, factor=True, solve=True):
     return info, keep
 
 
+def eigh_device_batch(items):
+    """np.linalg.eigh replacement for several matrices at once: items = [(A_pad, n), ...] (A_pad destroyed, identity
+    padded).  Returns [(lam (npad,), Vt (npad, npad) with eigenvectors as rows)], and the sweep count."""
+    out, sweeps_max = [], 0
+    for c0 in range(0, len(items), _lib.MAXB):
+        chunk = items[c0:c0 + _lib.MAXB]
+        pr = (_lib.EighProblem * len(chunk))()
+        res = []
+        for k, (A_pad, n) in enumerate(chunk):
+            npad = A_pad.shape[0]
+            Vt = _zeros64(npad, npad)
+            lam = _zeros64(npad)
+            pr[k].A, pr[k].Vt, pr[k].lam = A_pad.data_ptr(), Vt.data_ptr(), lam.data_ptr()
+            pr[k].lda, pr[k].ldv, pr[k].n = A_pad.stride(0), Vt.stride(0), int(n)
+            res.append((lam, Vt))
+        sweeps = C.c_int(0)
+        _lib.dev_eigh_batch(pr, len(chunk), 80, C.byref(sweeps), stream_handle())
+        sweeps_max = max(sweeps_max, sweeps.value)
+        out += res
+    return out, sweeps_max
+
+
 def eigh_device(A_pad, n):
     """np.linalg.eigh replacement: returns (lam (n,), Vt (npad, npad) with eigenvectors as rows). A_pad is destroyed."""
-    npad = A_pad.shape[0]
-    Vt = _zeros64(npad, npad)
-    lam = _zeros64(npad)
-    sweeps = C.c_int(0)
-    _lib.dev_eigh(ptr(A_pad), A_pad.stride(0), n, ptr(Vt), Vt.stride(0), ptr(lam), 60, C.byref(sweeps), stream_handle())
-    return lam, Vt, sweeps.value
+    ((lam, Vt),), sweeps = eigh_device_batch([(A_pad, n)])
+    return lam, Vt, sweeps
 
 
 def _padded_system(ds: DeviceSystem, incs):
@@ -288,12 +306,21 @@ def solve_chol(ds: DeviceSystem, cfg, j_out: int) -> KernelOutput:
     return solve_chol_batch([ds], cfg, j_out)[0]
 
 
+def eigen_decompose_batch(dss):
+    """eigh(A) once per stamp (lakernel.py:162, 201), all stamps of a batch together: returns per stamp
+    (lam (npad,), Q^T (rows = eigenvectors), Q, sweeps)."""
+    res, sweeps = eigh_device_batch([(ds.A.clone(), ds.n) for ds in dss])
+    out = []
+    for ds, (lam, Vt) in zip(dss, res):
+        Q = _f64(ds.npad, ds.npad)
+        _lib.dev_transpose(ptr(Vt), Vt.stride(0), ptr(Q), Q.stride(0), ds.npad, ds.npad, stream_handle())
+        out.append((lam, Vt, Q, sweeps))
+    return out
+
+
 def eigen_decompose(ds: DeviceSystem):
-    """eigh(A) once per stamp (lakernel.py:162, 201): returns lam (npad,), Q^T (rows = eigenvectors) and Q."""
-    lam, Vt, sweeps = eigh_device(ds.A.clone(), ds.n)
-    Q = _f64(ds.npad, ds.npad)
-    _lib.dev_transpose(ptr(Vt), Vt.stride(0), ptr(Q), Q.stride(0), ds.npad, ds.npad, stream_handle())
-    return lam, Vt, Q, sweeps
+    """Single-stamp form of eigen_decompose_batch."""
+    return eigen_decompose_batch([ds])[0]
 
 
 def solve_eigen(ds: DeviceSystem, cfg, j_out: int, eig=None, nbis: int = 13) -> KernelOutput:

@@ -53,6 +53,7 @@ def test_struct_layouts(lib):
     assert ctypes.sizeof(lib.SolveSys) == 48
     assert ctypes.sizeof(lib.FinalizeArgs) == 184
     assert ctypes.sizeof(lib.PairDesc) == 40
+    assert ctypes.sizeof(lib.EighProblem) == 40
     assert ctypes.sizeof(lib.AsmDesc) == 1056  # 648 + 324 + 40 + 36 + 4, rounded up to the 8-byte alignment
 
 
