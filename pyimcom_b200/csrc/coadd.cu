@@ -21,12 +21,6 @@ constexpr int ROWS = 8;     // output pixels per CTA
 constexpr int CH = 512;     // columns per chunk held in shared memory
 constexpr int LDT = CH + 4; // smem row stride (doubles): 516 = 4 mod 16 -> conflict-free DMMA fragment loads
 
-__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
-    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
-                 : "+d"(c0), "+d"(c1)
-                 : "d"(a), "d"(b));
-}
-
 // trapezoid weight sequence applied to one float32 value exactly as numpy does it (coadd.py:1269-1282):
 // each "*=" promotes to float64, multiplies, and rounds back to float32.
 __device__ __forceinline__ float fade32(float v, int iy, int ix, int ny, int nx, int fk2, const double* __restrict__ s) {

@@ -46,6 +46,24 @@ void prof_end(double work, cudaStream_t st);  // work: flops (tensor kinds) or b
 int scratch(int slot, size_t bytes, void** out);
 void scratch_release();
 
+// ---- FP64 tensor-core step and asynchronous global -> shared copies (shared by the tile kernels) -------------
+// D (8x8) += A (8x4, row) * B (4x8, col): lane (g = lane/4, q = lane%4) supplies A[g][q] and B[q][g] and owns
+// D[g][2q], D[g][2q+1].  SASS: DMMA.8x8x4.
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+__device__ __forceinline__ void cp_async16(double* smem, const double* gmem) {
+    unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
 // ---- small reductions --------------------------------------------------------------------------
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll

@@ -21,31 +21,6 @@ namespace {
 
 constexpr int JT = 256;
 
-// three simultaneous deterministic block sums
-__device__ __forceinline__ void block_sum3(double& a, double& b, double& c, double* red /* >= 3*9 doubles */) {
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    a = warp_sum(a);
-    b = warp_sum(b);
-    c = warp_sum(c);
-    __syncthreads();
-    if (lane == 0) {
-        red[wid] = a;
-        red[8 + wid] = b;
-        red[16 + wid] = c;
-    }
-    __syncthreads();
-    double ta = 0.0, tb = 0.0, tc = 0.0;
-#pragma unroll
-    for (int w = 0; w < JT / 32; w++) {
-        ta += red[w];
-        tb += red[8 + w];
-        tc += red[16 + w];
-    }
-    a = ta;
-    b = tb;
-    c = tc;
-}
-
 // V^T = I on the whole padded range (ntot rows/columns); per-row squared norms of the real n x n part of A
 __global__ void k_jacobi_init(double* __restrict__ Vt, int ldv, int n, int ntot, const double* __restrict__ G, int lda,
                               double* __restrict__ fro2) {
@@ -81,11 +56,14 @@ __global__ void k_jacobi_fro(const double* __restrict__ fro2, int n, double* __r
 // per sweep).  All reductions have a fixed order: the result is deterministic.
 constexpr int BJ = 16;           // rows per block
 constexpr int B2 = 2 * BJ;       // rows per block pair
-constexpr int BCK = 128;         // columns per chunk
-constexpr int LDK = B2 + 2;      // phase 1: k-major chunk [BCK][LDK] (32 rows contiguous per k)
-constexpr int LDX = BCK + 4;     // phase 4: row-major chunk [B2][LDX]
+constexpr int CK1 = 64;          // phase 1: columns per chunk (G and V chunks, double buffered)
+constexpr int LDH = CK1 + 4;     // 68 = 4 mod 16: conflict-free DMMA fragment loads
+constexpr int CK4 = 128;         // phase 4: columns per chunk (one array, double buffered)
+constexpr int LDX = CK4 + 4;     // 132 = 4 mod 16
 constexpr int LDS_ = B2 + 1;     // S and J: [B2][LDS_]
-constexpr size_t BJ_SMEM = sizeof(double) * ((size_t)2 * BCK * LDK + 2 * B2 * B2 + 2 * B2 * LDS_ + 64);
+constexpr int LDJ = B2 + 4;      // J^T: [B2][LDJ], 36 = 4 mod 16
+constexpr int BUF_DOUBLES = 4 * B2 * LDH;  // 8704 >= 2 * B2 * LDX (8448) and >= 8 * B2 * B2 (8192, partial H)
+constexpr size_t BJ_SMEM = sizeof(double) * ((size_t)BUF_DOUBLES + 2 * B2 * LDS_ + B2 * LDJ + 64);
 
 struct EighSys {
     double* G;
@@ -123,61 +101,85 @@ __global__ void __launch_bounds__(256, 2) k_jacobi_block_round(EighBatch bt, int
     circle_pair(npl, round, blockIdx.x, P, Q);
     const int ncol = npl * BJ;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    double* Gk = sm;                      // [BCK][LDK]  G chunk, k-major
-    double* Vk = Gk + BCK * LDK;          // [BCK][LDK]  V chunk, k-major
-    double* Hp = Vk + BCK * LDK;          // [2 K-halves][32][32] partial H
-    double* S = Hp + 2 * B2 * B2;         // [32][33]
-    double* J = S + B2 * LDS_;            // [32][33]
-    double* cs = J + B2 * LDS_;           // [16][2] rotation of each pair of the inner round (c, s); s = 0: skip
+    const int g = lane >> 2, q = lane & 3;
+    double* buf = sm;                      // chunk stages, later the 8 partial H
+    double* S = buf + BUF_DOUBLES;         // [32][33]
+    double* J = S + B2 * LDS_;             // [32][33]
+    double* JT = J + B2 * LDS_;            // [32][36]  J^T, the A operand of phase 4
+    double* cs = JT + B2 * LDJ;            // [16][2] rotation of each pair of the inner round (c, s); s = 0: skip
     __shared__ int s_any;
     auto grow = [&](int r) { return (r < BJ ? P * BJ + r : Q * BJ + (r - BJ)); };
 
-    // ---- phase 1: H = G_PQ V_PQ^T.  Warp w: K half (w & 1) of every chunk, rows 8 (w >> 1) .. +8; lane tile 2 rows x
-    // 4 columns; the two partial H are added in a fixed order afterwards.
-    const int kh = warp & 1;
-    const int a0 = 8 * (warp >> 1) + 2 * (lane >> 3), b0 = 4 * (lane & 7);
-    double acc[2][4];
+    // ---- phase 1: H = G_PQ V_PQ^T on the FP64 tensor pipe.  64-column chunks of the 32 G rows and the 32 V rows are
+    // double buffered with cp.async; warp w takes columns 8w .. 8w+7 of every chunk and accumulates the full 32x32
+    // (4 x 4 m8n8 tiles); the eight partial H are added in warp order afterwards.
+    {
+        auto load1 = [&](int stage, int c0) {
+            double* Gs = buf + (2 * stage) * B2 * LDH;
+            double* Vs = Gs + B2 * LDH;
+            for (int e = tid; e < B2 * (CK1 / 2); e += 256) {
+                const int r = e / (CK1 / 2), k2 = (e - r * (CK1 / 2)) * 2;
+                const int c = c0 + k2;
+                const size_t gr = (size_t)grow(r);
+                if (c < ncol) {
+                    cp_async16(Gs + r * LDH + k2, sy.G + gr * sy.ldg + c);
+                    cp_async16(Vs + r * LDH + k2, sy.Vt + gr * sy.ldv + c);
+                } else {
+                    *reinterpret_cast<double2*>(Gs + r * LDH + k2) = make_double2(0.0, 0.0);
+                    *reinterpret_cast<double2*>(Vs + r * LDH + k2) = make_double2(0.0, 0.0);
+                }
+            }
+        };
+        double acc[4][4][2];
 #pragma unroll
-    for (int i = 0; i < 2; i++)
+        for (int mi = 0; mi < 4; mi++)
 #pragma unroll
-        for (int j = 0; j < 4; j++) acc[i][j] = 0.0;
-    for (int c0 = 0; c0 < ncol; c0 += BCK) {
-        __syncthreads();
-        for (int e = tid; e < B2 * BCK; e += 256) {
-            const int r = e / BCK, k = e - r * BCK;
-            const int c = c0 + k;
-            const size_t gr = (size_t)grow(r);
-            Gk[k * LDK + r] = c < ncol ? sy.G[gr * sy.ldg + c] : 0.0;
-            Vk[k * LDK + r] = c < ncol ? sy.Vt[gr * sy.ldv + c] : 0.0;
+            for (int ni = 0; ni < 4; ni++) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
+        const int nch = (ncol + CK1 - 1) / CK1;
+        load1(0, 0);
+        cp_async_commit();
+        for (int ch = 0; ch < nch; ch++) {
+            if (ch + 1 < nch) load1((ch + 1) & 1, (ch + 1) * CK1);
+            cp_async_commit();
+            cp_async_wait<1>();
+            __syncthreads();
+            const double* Gs = buf + (2 * (ch & 1)) * B2 * LDH + g * LDH + 8 * warp + q;
+            const double* Vs = Gs + B2 * LDH;
+#pragma unroll
+            for (int kk = 0; kk < 2; kk++) {
+                double a[4], b[4];
+#pragma unroll
+                for (int mi = 0; mi < 4; mi++) a[mi] = Gs[mi * 8 * LDH + kk * 4];
+#pragma unroll
+                for (int ni = 0; ni < 4; ni++) b[ni] = Vs[ni * 8 * LDH + kk * 4];
+#pragma unroll
+                for (int mi = 0; mi < 4; mi++)
+#pragma unroll
+                    for (int ni = 0; ni < 4; ni++) dmma884(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
+            }
+            __syncthreads();
         }
-        __syncthreads();
-#pragma unroll 8
-        for (int kk = 0; kk < BCK / 2; kk++) {
-            const int k = kh * (BCK / 2) + kk;
-            const double2 g = *reinterpret_cast<const double2*>(Gk + k * LDK + a0);
-            const double2 v0 = *reinterpret_cast<const double2*>(Vk + k * LDK + b0);
-            const double2 v1 = *reinterpret_cast<const double2*>(Vk + k * LDK + b0 + 2);
-            acc[0][0] = fma(g.x, v0.x, acc[0][0]);
-            acc[0][1] = fma(g.x, v0.y, acc[0][1]);
-            acc[0][2] = fma(g.x, v1.x, acc[0][2]);
-            acc[0][3] = fma(g.x, v1.y, acc[0][3]);
-            acc[1][0] = fma(g.y, v0.x, acc[1][0]);
-            acc[1][1] = fma(g.y, v0.y, acc[1][1]);
-            acc[1][2] = fma(g.y, v1.x, acc[1][2]);
-            acc[1][3] = fma(g.y, v1.y, acc[1][3]);
-        }
+        cp_async_wait<0>();
+        double* Hw = buf + warp * B2 * B2;
+#pragma unroll
+        for (int mi = 0; mi < 4; mi++)
+#pragma unroll
+            for (int ni = 0; ni < 4; ni++) {
+                Hw[(8 * mi + g) * B2 + 8 * ni + 2 * q] = acc[mi][ni][0];
+                Hw[(8 * mi + g) * B2 + 8 * ni + 2 * q + 1] = acc[mi][ni][1];
+            }
     }
-#pragma unroll
-    for (int i = 0; i < 2; i++)
-#pragma unroll
-        for (int j = 0; j < 4; j++) Hp[(kh * B2 + a0 + i) * B2 + b0 + j] = acc[i][j];
     __syncthreads();
     // ---- phase 2: S = (H + H^T) / 2, J = I; anything to do?
     if (tid == 0) s_any = 0;
     for (int e = tid; e < B2 * B2; e += 256) {
         const int a = e >> 5, b = e & 31;
-        const double h = Hp[a * B2 + b] + Hp[(B2 + a) * B2 + b];
-        const double ht = Hp[b * B2 + a] + Hp[(B2 + b) * B2 + a];
+        double h = 0.0, ht = 0.0;
+#pragma unroll
+        for (int w = 0; w < 8; w++) {
+            h += buf[(w * B2 + a) * B2 + b];
+            ht += buf[(w * B2 + b) * B2 + a];
+        }
         S[a * LDS_ + b] = 0.5 * (h + ht);
         J[a * LDS_ + b] = (a == b) ? 1.0 : 0.0;
     }
@@ -240,49 +242,72 @@ __global__ void __launch_bounds__(256, 2) k_jacobi_block_round(EighBatch bt, int
     }
     if (!__syncthreads_or(napplied)) return;
     if (tid == 0) atomicAdd(sy.nrot, 1);
-    // ---- phase 4: rows <- J^T rows, for G and V^T.  Thread tile: 4 rows (4*warp ..) x 4 columns (4*lane ..).
-    double* X = sm;  // [B2][LDX] row-major chunk (reuses the phase-1 buffers)
-    for (int arr = 0; arr < 2; arr++) {
-        double* base = arr ? sy.Vt : sy.G;
+    for (int e = tid; e < B2 * B2; e += 256) {
+        const int a = e >> 5, b = e & 31;
+        JT[a * LDJ + b] = J[b * LDS_ + a];
+    }
+    __syncthreads();
+    // ---- phase 4: rows <- J^T rows for G and for V^T, on the tensor pipe.  128-column chunks of the 32 rows are
+    // double buffered with cp.async; warp w owns columns 16w .. 16w+15 of a chunk (4 x 2 m8n8 tiles, K = 32);
+    // the A fragments (J^T) stay in registers for the whole pass.
+    double areg[4][8];
+#pragma unroll
+    for (int mi = 0; mi < 4; mi++)
+#pragma unroll
+        for (int kk = 0; kk < 8; kk++) areg[mi][kk] = JT[(8 * mi + g) * LDJ + 4 * kk + q];
+    const int nch4 = (ncol + CK4 - 1) / CK4;
+    auto load4 = [&](int stage, int t) {  // t enumerates (array, chunk)
+        const int arr = t / nch4, c0 = (t - arr * nch4) * CK4;
+        const double* base = arr ? sy.Vt : sy.G;
         const int ld = arr ? sy.ldv : sy.ldg;
-        for (int c0 = 0; c0 < ncol; c0 += BCK) {
-            __syncthreads();
-            for (int e = tid; e < B2 * (BCK / 2); e += 256) {
-                const int r = e / (BCK / 2), k2 = (e - r * (BCK / 2)) * 2;
-                const int c = c0 + k2;
-                double2 t = make_double2(0.0, 0.0);
-                if (c < ncol) t = *reinterpret_cast<const double2*>(base + (size_t)grow(r) * ld + c);
-                *reinterpret_cast<double2*>(X + r * LDX + k2) = t;
-            }
-            __syncthreads();
-            double o[4][4];
+        double* X = buf + stage * B2 * LDX;
+        for (int e = tid; e < B2 * (CK4 / 2); e += 256) {
+            const int r = e / (CK4 / 2), k2 = (e - r * (CK4 / 2)) * 2;
+            const int c = c0 + k2;
+            if (c < ncol)
+                cp_async16(X + r * LDX + k2, base + (size_t)grow(r) * ld + c);
+            else
+                *reinterpret_cast<double2*>(X + r * LDX + k2) = make_double2(0.0, 0.0);
+        }
+    };
+    const int nt = 2 * nch4;
+    load4(0, 0);
+    cp_async_commit();
+    for (int t = 0; t < nt; t++) {
+        if (t + 1 < nt) load4((t + 1) & 1, t + 1);
+        cp_async_commit();
+        cp_async_wait<1>();
+        __syncthreads();
+        const double* X = buf + (t & 1) * B2 * LDX + q * LDX + 16 * warp + g;
+        double o[4][2][2];
 #pragma unroll
-            for (int i = 0; i < 4; i++)
+        for (int mi = 0; mi < 4; mi++)
 #pragma unroll
-                for (int j = 0; j < 4; j++) o[i][j] = 0.0;
-#pragma unroll 4
-            for (int b = 0; b < B2; b++) {
-                const double2 x0 = *reinterpret_cast<const double2*>(X + b * LDX + 4 * lane);
-                const double2 x1 = *reinterpret_cast<const double2*>(X + b * LDX + 4 * lane + 2);
-                const double xv[4] = {x0.x, x0.y, x1.x, x1.y};
+            for (int ni = 0; ni < 2; ni++) o[mi][ni][0] = o[mi][ni][1] = 0.0;
 #pragma unroll
-                for (int i = 0; i < 4; i++) {
-                    const double jt = J[b * LDS_ + 4 * warp + i];  // J^T[a][b] = J[b][a]
+        for (int kk = 0; kk < 8; kk++) {
+            const double b0 = X[kk * 4 * LDX], b1 = X[kk * 4 * LDX + 8];
 #pragma unroll
-                    for (int j = 0; j < 4; j++) o[i][j] = fma(jt, xv[j], o[i][j]);
-                }
-            }
-            const int c = c0 + 4 * lane;
-            if (c < ncol) {
-#pragma unroll
-                for (int i = 0; i < 4; i++) {
-                    double* dst = base + (size_t)grow(4 * warp + i) * ld + c;
-                    *reinterpret_cast<double2*>(dst) = make_double2(o[i][0], o[i][1]);
-                    *reinterpret_cast<double2*>(dst + 2) = make_double2(o[i][2], o[i][3]);
-                }
+            for (int mi = 0; mi < 4; mi++) {
+                dmma884(o[mi][0][0], o[mi][0][1], areg[mi][kk], b0);
+                dmma884(o[mi][1][0], o[mi][1][1], areg[mi][kk], b1);
             }
         }
+        const int arr = t / nch4, c0 = (t - arr * nch4) * CK4;
+        double* base = arr ? sy.Vt : sy.G;
+        const int ld = arr ? sy.ldv : sy.ldg;
+#pragma unroll
+        for (int mi = 0; mi < 4; mi++)
+#pragma unroll
+            for (int ni = 0; ni < 2; ni++) {
+                const int c = c0 + 16 * warp + 8 * ni + 2 * q;
+                if (c < ncol)
+                    *reinterpret_cast<double2*>(base + (size_t)grow(8 * mi + g) * ld + c) =
+                        make_double2(o[mi][ni][0], o[mi][ni][1]);
+            }
+        __syncthreads();
     }
+    cp_async_wait<0>();
 }
 
 __global__ void __launch_bounds__(JT) k_jacobi_finish(const double* __restrict__ G, int lda,

@@ -36,22 +36,6 @@ constexpr int SP = 4;            // block columns per super-panel (512 matrix co
 constexpr int STAGE_DOUBLES = 2 * NB * LDSM;
 constexpr size_t GEMM_SMEM = (size_t)STAGES * STAGE_DOUBLES * sizeof(double);  // 163840 B
 
-__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
-    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
-                 : "+d"(c0), "+d"(c1)
-                 : "d"(a), "d"(b));
-}
-
-__device__ __forceinline__ void cp_async16(double* smem, const double* gmem) {
-    unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gmem) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() {
-    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
-}
-
 enum TileMode { TILE_ASSIGN = 0, TILE_SUB = 1, TILE_ADD = 2 };
 
 // One 128x128 output tile:  C = op(C, A[128,K] * B[128,K]^T).
