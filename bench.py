@@ -77,8 +77,18 @@ class ClockSampler:
 
     def __init__(self, index=0):
         self.index, self.lines, self.proc = index, [], None
+        self.i0 = self.i1 = None
+
+    def mark(self):
+        self.i0 = len(self.lines)
+
+    def mark_end(self):
+        time.sleep(0.12)  # let the 100 ms sampler print the last line of the timed region
+        self.i1 = len(self.lines)
 
     def __enter__(self):
+        if os.environ.get("B200_BENCH_NO_SAMPLER"):
+            return self
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
                                           "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
@@ -104,7 +114,8 @@ class ClockSampler:
     def summary(self):
         sm, mx, reasons = [], 0, set()
         names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
-        for ln in self.lines:
+        lines = self.lines[self.i0:self.i1] if self.i0 is not None and self.lines[self.i0:self.i1] else self.lines
+        for ln in lines:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 6:
                 continue
@@ -246,19 +257,23 @@ def run_gpu(args):
                          round(ms.get("reserved_bytes.all.current", 0) / 2**30, 2), ms.get("num_alloc_retries", 0)))
         return g2, maps
 
-    for _ in range(max(args.warmup, 3)):
-        step_resident()
-    # ---- timed: resident inputs ----
-    barrier()
-    _lib.profile(1)
-    n0 = _lib.launch_count()
+    # the clock sampler starts before the warm-up (nvidia-smi takes a moment to produce its first line on an 8-GPU
+    # box); only the lines printed during the timed region are kept if there are any
     with ClockSampler(local) as clk:
+        for _ in range(max(args.warmup, 3)):
+            step_resident()
+        # ---- timed: resident inputs ----
+        barrier()
+        _lib.profile(1)
+        n0 = _lib.launch_count()
+        clk.mark()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(args.steps):
             step_resident()
         e1.record()
         barrier()
+        clk.mark_end()
     launches = _lib.launch_count() - n0
     t_res = e0.elapsed_time(e1) * 1e-3
     prof = _lib.profile_read()

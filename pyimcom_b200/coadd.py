@@ -93,6 +93,18 @@ class _Arena:
         return dst
 
 
+_TOTAL_HBM = {}
+
+
+def hbm_free_estimate() -> int:
+    """Bytes this process can still place on the current device, from torch's own counters.  cudaMemGetInfo is not
+    used on the hot path: it takes a driver-wide lock and was measured to stall for tens of ms while work is queued."""
+    dev = torch.cuda.current_device()
+    if dev not in _TOTAL_HBM:
+        _TOTAL_HBM[dev] = torch.cuda.get_device_properties(dev).total_memory
+    return max(0, int(0.92 * _TOTAL_HBM[dev]) - torch.cuda.memory_allocated(dev))
+
+
 class StampPlan:
     """Host-side description of one OutStamp (what OutStamp.__init__ / _process_input_stamps derive)."""
 
@@ -395,7 +407,7 @@ class GpuBlock:
                     if key not in seen:
                         seen.add(key)
                         tot += self._inst_count(key[0]) * ((self._inst_count(key[1]) + 3) // 4 * 4)
-        budget = min(16 << 30, (torch.cuda.mem_get_info()[0] // 4) >> 28 << 28)
+        budget = min(16 << 30, (hbm_free_estimate() // 4) >> 28 << 28)
         return int(min(8 * tot, budget))
 
     def _asm_desc(self, p) -> _lib.AsmDesc:
@@ -550,7 +562,7 @@ class GpuBlock:
         nmax = max(self.plans[ji].n for ji in self.order)
         npad, mpad = rup(nmax), rup(cfg.n2f**2)
         per = 8.0 * ((1 + nv) * npad * npad + (cfg.n_out + nv) * mpad * npad)
-        free = torch.cuda.mem_get_info()[0] + torch.cuda.memory_reserved() - torch.cuda.memory_allocated()
+        free = hbm_free_estimate()
         return int(max(1, min(0.5 * free // per, self.max_batch)))
 
     max_batch = 16

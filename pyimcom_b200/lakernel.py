@@ -181,6 +181,7 @@ def _padded_system(ds: DeviceSystem, incs):
 
 
 SOLVE_STREAMS = int(os.environ.get("B200_SOLVE_STREAMS", "3"))  # concurrent groups of systems in the batched factorisation (1 = everything on the caller's stream)
+STREAM_PRIORITIES = os.environ.get("B200_STREAM_PRIORITIES", "1") != "0"
 _SIDE = {}
 
 
@@ -188,7 +189,10 @@ def _side_streams(n):
     dev = torch.cuda.current_device()
     have = _SIDE.setdefault(dev, [])
     while len(have) < n:
-        have.append(torch.cuda.Stream())
+        # staggered priorities (lower number = higher priority): the first group runs as if alone, the others fill
+        # the SMs it leaves idle, instead of all groups contending for every freed SM
+        prio = -len(have) if STREAM_PRIORITIES else 0
+        have.append(torch.cuda.Stream(priority=prio))
     return have[:n]
 
 
