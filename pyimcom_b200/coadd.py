@@ -421,8 +421,11 @@ class GpuBlock:
             d.seg_start[a] = int(p.inpix_cumsum[a])
         return d
 
-    def build_system(self, k: int):
-        """Stage (a): gather + A + mBhalf for stamp number k of self.order.  Returns (DeviceSystem, indata)."""
+    def build_system(self, k: int, need_A: bool = True):
+        """Stage (a): gather + A + mBhalf for stamp number k of self.order.  Returns (DeviceSystem, indata).
+
+        need_A=False (pair-block cache on): A is not materialised; the solver cuts A + kappa I straight out of the
+        cached blocks through DeviceSystem.assemble."""
         cfg = self.cfg
         p = self.plans[self.order[k]]
         st = stream_handle()
@@ -439,13 +442,22 @@ class GpuBlock:
         _lib.dev_gather_stamp(ptr(idx), n, npad, ptr(self.d_x), ptr(self.d_y), None, ptr(self.d_data),
                               self.d_data.stride(0), cfg.n_inframe, ptr(px), ptr(py), None, ptr(indata),
                               indata.stride(0), st)
-        A = torch.empty((npad, npad), dtype=torch.float64, device="cuda")
         ncode = 4 * nimg
+        A, assemble = None, None
         if self.a_cache:
             self.ensure_pairs([p])  # no-op when coadd_batch has already requested the whole batch's blocks
-            _lib.dev_assemble_A(C.byref(self._asm_desc(p)), ptr(idx), n, npad, ptr(self._pool), ptr(A), A.stride(0), 0.0,
-                                st)
+            desc, pool = self._asm_desc(p), self._pool
+
+            def assemble(diag_add, desc=desc, pool=pool, idx=idx, n=n, npad=npad):
+                W = torch.empty((npad, npad), dtype=torch.float64, device="cuda")
+                _lib.dev_assemble_A(C.byref(desc), ptr(idx), n, npad, ptr(pool), ptr(W), W.stride(0), float(diag_add),
+                                    stream_handle())
+                return W
+
+            if need_A:
+                A = assemble(0.0)
         else:
+            A = torch.empty((npad, npad), dtype=torch.float64, device="cuda")
             _lib.dev_build_A(ptr(px), ptr(py), ptr(pcode), n, npad, ptr(self.d_tables), ptr(self.d_lut[k]), nimg, ncode,
                              self.arena.ngrid, float(cfg.dscale), float(cfg.nc_ovl), float(cfg.flat_penalty), ptr(A),
                              A.stride(0), 0.0, self.arena.poly, st)
@@ -454,7 +466,7 @@ class GpuBlock:
                          self.arena.ngrid, float(cfg.dscale), float(cfg.nc_ovl), cfg.n2f, mpad, p.x0out, p.y0out, ptr(mB),
                          mB.stride(1), mB.stride(0), st)
         ds = DeviceSystem(n=n, m=m, n2f=cfg.n2f, A=A, mB=mB, C=np.asarray(self.tab.outovlc, dtype=np.float64),
-                          px=px, py=py)
+                          px=px, py=py, assemble=assemble)
         if self.kernel == "Iterative":
             g = torch.arange(cfg.n2f, dtype=torch.float64, device="cuda")
             ds.outy = (p.y0out + g).repeat_interleave(cfg.n2f).contiguous()
@@ -482,6 +494,8 @@ class GpuBlock:
         cfg = self.cfg
         kept = [dict() for _ in ks]
         live = []
+        # single-kappa Cholesky needs A only as A + kappa I: skip materialising it unless the caller keeps the stamp
+        need_A = keep or self.kernel != "Cholesky" or len(np.atleast_1d(cfg.kappaC_arr)) > 1
         if self.a_cache:
             self.ensure_pairs([pl for pl in (self.plans[self.order[k]] for k in ks) if pl.n > 0])
         for q, k in enumerate(ks):
@@ -489,7 +503,7 @@ class GpuBlock:
             if p.n == 0:  # lakernel.py:110-119 and coadd.py:1094-1100: nothing to add except UC = kappa = 1
                 self._empty_stamp(p, keep)
                 continue
-            ds, indata = self.build_system(k)
+            ds, indata = self.build_system(k, need_A=need_A)
             live.append((q, k, p, ds, indata))
         if self.kernel == "Eigen" and live:  # one decomposition per stamp serves every output PSF; all stamps together
             for (q, k, p, ds, indata), eig in zip(live, eigen_decompose_batch([t[3] for t in live])):

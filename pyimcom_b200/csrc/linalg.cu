@@ -565,12 +565,14 @@ int launch_gemm_nt(const double* A, int lda, const double* B, int ldb, double* C
                  "gemm_nt wants M,N multiples of 128, even K and leading dimensions");
     if (int rc = gemm_attrs()) return rc;
     dim3 grid(N / NB, M / NB);
+    prof_begin(PROF_GEMM, st);
     if (accumulate == 0)
         k_gemm_nt<TILE_ASSIGN><<<grid, GT, GEMM_SMEM, st>>>(A, lda, B, ldb, C, ldc, K);
     else if (accumulate > 0)
         k_gemm_nt<TILE_ADD><<<grid, GT, GEMM_SMEM, st>>>(A, lda, B, ldb, C, ldc, K);
     else
         k_gemm_nt<TILE_SUB><<<grid, GT, GEMM_SMEM, st>>>(A, lda, B, ldb, C, ldc, K);
+    prof_end(2.0 * M * (double)N * K, st);
     B200_LAUNCH_CHECK();
     return 0;
 }

@@ -72,10 +72,19 @@ class DeviceSystem:
     py: torch.Tensor | None = None
     outx: torch.Tensor | None = None  # (m,) f64 output pixel positions (IterKernel only)
     outy: torch.Tensor | None = None
+    # Block driver only: A may be left unmaterialised (None); assemble(diag_add) then cuts A + diag_add*I straight
+    # out of the cached InStamp-pair blocks, which saves the copy A -> W of the single-kappa Cholesky path.
+    assemble: object = None
 
     @property
     def npad(self):
-        return self.A.shape[0]
+        return self.A.shape[0] if self.A is not None else self.mB.shape[2]
+
+    def matrix(self) -> torch.Tensor:
+        """A, materialised on first use."""
+        if self.A is None:
+            self.A = self.assemble(0.0)
+        return self.A
 
     @property
     def mpad(self):
@@ -174,6 +183,9 @@ def eigh_device(A_pad, n):
 
 
 def _padded_system(ds: DeviceSystem, incs):
+    if ds.A is None and ds.assemble is not None and len(incs) <= 1:
+        return ds.assemble(float(incs[0]) if incs else 0.0)  # same single rounding A_ii + inc as k_pad_system
+    ds.matrix()
     W = _f64(ds.npad, ds.npad)
     arr, k = _incs(incs)
     _lib.dev_pad_system(ptr(W), W.stride(0), ds.n, ds.npad, ptr(ds.A), ds.A.stride(0), arr, k, stream_handle())
@@ -238,7 +250,7 @@ def _chol_solve_items(items):
         for k in np.nonzero(bad)[0]:
             ds, incs, j = items[k]
             if id(ds) not in shifts:  # one eigh per stamp serves all of its failing nodes
-                lam, _, _ = eigh_device(ds.A.clone(), ds.n)
+                lam, _, _ = eigh_device(ds.matrix().clone(), ds.n)
                 shifts[id(ds)] = float(lam[: ds.n].min().item())
             w0 = shifts[id(ds)]
             warnings.warn(f"CholKernel: repaired negative eigenvalue {w0:19.12e}", stacklevel=3)
@@ -313,7 +325,7 @@ def solve_chol(ds: DeviceSystem, cfg, j_out: int) -> KernelOutput:
 def eigen_decompose_batch(dss):
     """eigh(A) once per stamp (lakernel.py:162, 201), all stamps of a batch together: returns per stamp
     (lam (npad,), Q^T (rows = eigenvectors), Q, sweeps)."""
-    res, sweeps = eigh_device_batch([(ds.A.clone(), ds.n) for ds in dss])
+    res, sweeps = eigh_device_batch([(ds.matrix().clone(), ds.n) for ds in dss])
     out = []
     for ds, (lam, Vt) in zip(dss, res):
         Q = _f64(ds.npad, ds.npad)
@@ -389,7 +401,7 @@ def solve_iter(ds: DeviceSystem, cfg, j_out: int, exact_UC=None) -> KernelOutput
 
     def exact_E(p, q, out, ostride):
         ATp = _f64(mpad, npad)  # (Tpi[p] @ A): A is symmetric, so the NT product with A's rows is the same
-        _lib.dev_gemm_nt(ptr(Tpi[p]), Tpi.stride(1), ptr(ds.A), ds.A.stride(0), ptr(ATp), ATp.stride(0), mpad, npad, npad,
+        _lib.dev_gemm_nt(ptr(Tpi[p]), Tpi.stride(1), ptr(ds.matrix()), ds.matrix().stride(0), ptr(ATp), ATp.stride(0), mpad, npad, npad,
                          0, st)
         return ATp
 

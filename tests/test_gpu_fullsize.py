@@ -107,3 +107,36 @@ def test_paper4_block_properties(block):
     assert np.abs(star - model)[win].max() < 0.02 * model.max()
     assert abs((star * xx)[win].sum() / star[win].sum() - sx) < 0.05
     assert abs((star * yy)[win].sum() / star[win].sum() - sy) < 0.05
+
+
+def test_tests_shaped_block_multikappa_batched():
+    """BASELINE configs[0] geometry (n ~ 1.5 k, m = 729) with three kappa nodes: all 16 stamps x 3 nodes go through the
+    batched factorisation together (48 systems, 3 launch sequences on 3 streams); two stamps are compared with the
+    oracle, including the discrete bracket / branch decisions of build_reduced_T_wrap."""
+    from pyimcom_b200.synth import StampConfig, SynthBlock
+
+    cfg = StampConfig(n1=4, n2=25, dtheta_arcsec=0.04, fade_kernel=1, postage_pad=0, npixpsf=42, oversamp=6,
+                      instamp_pad_arcsec=0.8, n_inframe=4, linear_algebra="Cholesky",
+                      kappaC_arr=np.array([1e-5, 1e-4, 1e-3]), uctarget=1e-6, sigmamax=0.5)
+    blk = SynthBlock(cfg, n_image=3, seed=12345, psf_sigmas=(0.85, 0.95, 1.05), star=True)
+    tab = PSFTables(blk, G.iD5512C, G.gridD5512C, dedup=True)
+    gb = GpuBlock(blk, tab).prepare()
+    kept = gb.coadd_batch(list(range(len(gb.order))), keep=True)
+    torch.cuda.synchronize()
+    otab = PSFTables(blk, R.iD5512C, R.gridD5512C, dedup=True)
+    for q in (3, 10):
+        j, i = gb.order[q]
+        o = OracleOutStamp(blk, otab, j, i)
+        o.build_system_matrices()
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            k = OL.CholKernel(o)
+            k()
+        ko, res, ds = kept[q][0]["ko"], kept[q][0]["res"], kept[q]["ds"]
+        assert np.array_equal(ko.extras["iv"].cpu().numpy(), k.f64[0]["iv"])  # P-discrete
+        assert np.array_equal(ko.extras["branch"].cpu().numpy(), k.f64[0]["branch"])
+        assert rel(res["Ti64"][:ds.m, :ds.n].cpu().numpy(), k.f64[0]["Ti"]) < 1e-9  # P-f64
+        o.post_kernel()
+        o.perform_coaddition()  # fades o.T in place, as coadd.py:1321-1324 does
+        assert rel(res["T32"][:ds.m, :ds.n].cpu().numpy(), o.T[0]) < 2e-6
+        assert rel(res["outimage"].cpu().numpy().reshape(o.outimage[0].shape), o.outimage[0]) < 1e-5

@@ -39,7 +39,9 @@ CONFIGS = {
     "3_iter_large_stamp": dict(cfg=dict(n1=2, n2=32, dtheta_arcsec=0.0390625, fade_kernel=0, postage_pad=1, npixpsf=48,
                                         oversamp=8, instamp_pad_arcsec=0.6, n_inframe=6, linear_algebra="Iterative",
                                         kappaC_arr=[0.0], iter_rtol=1.5e-3, iter_max=30), n_image=6, seed=2024,
-                               sig=(0.85, 0.9, 0.95, 1.0, 1.05, 1.1), tol=2e-3),
+                               # kappa = 0 makes A singular: the reference's own CG result moves by 8e-3 under a 1e-15 relative
+                               # perturbation of A (oracle run), so T is only defined to ~1e-2 here
+                               sig=(0.85, 0.9, 0.95, 1.0, 1.05, 1.1), tol=3e-2),
     "5_nout3_psfsplit": dict(cfg=dict(T_SHAPE, linear_algebra="Cholesky", kappaC_arr=[5e-4], n_out=3, psfsplit=True,
                                       sigmatarget=0.85, sigmatarget_extra=(0.93, 1.02),
                                       outpsf_extra=("GAUSSIAN", "GAUSSIAN")), n_image=3, seed=777,
@@ -80,6 +82,14 @@ def main():
             torch.cuda.synchronize()
             t_gpu = e0.elapsed_time(e1) * 1e-3 / reps
             launches = (_lib.launch_count() - n0) // reps
+            # one more pass with per-launch events: device time and algorithmic work per kernel kind
+            _lib.profile(1)
+            gb.reset_maps(); gb.reset_cache(); gb.run()
+            torch.cuda.synchronize()
+            prof = {k: {"ms": round(v[0], 3), "launches": v[2],
+                        "rate": (round(v[1] / (v[0] * 1e-3) / 1e9, 1) if v[0] > 0 and v[1] > 0 else None)}
+                    for k, v in _lib.profile_read().items()}
+            _lib.profile(0)
             # CPU oracle on a bounded sample + parity of the first stamp
             otab = PSFTables(blk, R.iD5512C, R.gridD5512C, dedup=True)
             sample = gb.order[:2]
@@ -103,7 +113,7 @@ def main():
                 "parity": {"A_rel": rel(s.sysmata, o.sysmata), "mBhalf_rel": rel(s.mhalfb, o.mhalfb),
                            "T_rel": rel(s.T, o.T), "outimage_rel": rel(s.outimage, o.outimage),
                            "Sigma_rel": rel(s.Sigma, o.Sigma), "UC_abs": float(np.abs(s.UC - o.UC).max())},
-                "tol_T": spec["tol"]}
+                "tol_T": spec["tol"], "per_kind_ms_one_block (rate: GFLOP/s for tensor kinds, GB/s otherwise)": prof}
         line["parity_ok"] = bool(line["parity"]["A_rel"] < 1e-9 and line["parity"]["mBhalf_rel"] < 1e-9
                                  and line["parity"]["T_rel"] < spec["tol"])
         print(json.dumps(line), flush=True)
