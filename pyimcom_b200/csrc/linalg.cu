@@ -24,30 +24,23 @@ namespace b200 {
 namespace {
 
 constexpr int KT = 32;           // K extent of one pipeline stage
-constexpr int LDSM = KT + 4;     // smem row stride in doubles: 36 = 4 mod 16 -> conflict-free fragment loads
+constexpr int LDSM = KT + 4;     // smem row stride in doubles: 20 = 4 mod 16 -> conflict-free fragment loads
 constexpr int STAGES = 3;
-// Experiment kept as a compile-time option (-DB200_FMA_COLS=16 or 32; default 0 = off).  The FP64 tensor pipe (DMMA)
-// and the FP64 FMA pipe issue concurrently on sm_100a (tools/probe/pipe_probe.cu: 8 DMMA warps per SM sustain
-// 37 TFLOP/s and DFMA warps added next to them cost nothing; DFMA alone peaks at 24.6 TFLOP/s), so the tile can be
-// split by columns: tensor warps take [0, ND) and two extra warps compute the last FMA_COLS columns with plain fused
-// multiply-adds from the same staged operands (thread = 2 rows x FMA_COLS columns, warp-uniform B loads).  Measured
-// on B200 (DGEMM 8192^3): 32.2 TFLOP/s tensor-only, 24.6 with FMA_COLS = 16, 19.4 with 32 -- two FMA warps cannot
-// retire their share (one DFMA per 3 clk per scheduler) inside the tensor warps' k-tile time and become the critical
-// path at every barrier, so the option stays off.
-#ifndef B200_FMA_COLS
-#define B200_FMA_COLS 0
+// Tried and dropped (round 1): splitting the tile between the tensor pipe and the FP64 FMA pipe.  The two pipes do
+// issue concurrently on sm_100a (tools/probe/pipe_probe.cu: 8 DMMA warps per SM sustain 37 TFLOP/s and DFMA warps
+// added next to them cost nothing; DFMA alone peaks at 24.6 TFLOP/s), but two extra FMA warps computing the last 16
+// (32) columns of the tile from the same staged operands brought DGEMM 8192^3 from 32.2 down to 24.6 (19.4) TFLOP/s:
+// at one DFMA per 3 clk per scheduler they cannot retire their share inside the tensor warps' k-tile time and become
+// the critical path at every barrier.
+#ifndef B200_GEMM_WARPS_M
+#define B200_GEMM_WARPS_M 2
 #endif
-constexpr int FMA_COLS = B200_FMA_COLS;          // 0: tensor pipe only
-constexpr int ND = NB - FMA_COLS;                // columns on the tensor pipe
-constexpr int WARPS_M = FMA_COLS ? 4 : 2, WARPS_N = FMA_COLS ? 2 : 4;  // tensor-warp grid over the 128 x ND part
-constexpr int DW = WARPS_M * WARPS_N;            // tensor warps
-constexpr int FMA_WARPS = FMA_COLS ? 2 : 0;      // 64 threads x 2 rows = 128 rows
-constexpr int GT = 32 * (DW + FMA_WARPS);        // threads per GEMM CTA
-constexpr int MI = NB / WARPS_M / 8, NI = ND / WARPS_N / 8;  // m8n8 fragments per tensor-warp tile
-static_assert(ND % (8 * WARPS_N) == 0, "tensor part must split into m8n8 tiles");
+constexpr int WARPS_M = B200_GEMM_WARPS_M, WARPS_N = 4;  // warp grid over the 128x128 tile
+constexpr int GT = 32 * WARPS_M * WARPS_N;               // threads per GEMM CTA
+constexpr int MI = NB / WARPS_M / 8, NI = NB / WARPS_N / 8;  // m8n8 fragments per warp tile
 constexpr int SP = 4;            // block columns per super-panel (512 matrix columns)
 constexpr int STAGE_DOUBLES = 2 * NB * LDSM;
-constexpr size_t GEMM_SMEM = (size_t)STAGES * STAGE_DOUBLES * sizeof(double);  // 221184 B
+constexpr size_t GEMM_SMEM = (size_t)STAGES * STAGE_DOUBLES * sizeof(double);  // 163840 B
 
 enum TileMode { TILE_ASSIGN = 0, TILE_SUB = 1, TILE_ADD = 2 };
 
@@ -61,32 +54,27 @@ __device__ __forceinline__ void gemm_tile_nt(const double* A, int lda, const dou
                                              int ldb, double* C, int ldc, int K, double* Ct, int ldct,
                                              double* smem) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const bool fma_warp = warp >= DW;
-    const int wm = warp / WARPS_N, wn = warp % WARPS_N;  // tensor-warp tile (8 MI) x (8 NI)
+    const int wm = warp / WARPS_N, wn = warp % WARPS_N;  // warp tile (8 MI) x (8 NI)
     const int g = lane >> 2, q = lane & 3;
     constexpr int WTM = 8 * MI, WTN = 8 * NI;
-    const int fr = tid - 32 * DW;  // FMA warps: thread owns rows fr and fr + 64, columns ND .. NB-1
-    constexpr int FC = FMA_COLS ? FMA_COLS : 1;
 
-    // one accumulator file for both kinds of warp, so that the two views share registers:
-    //   tensor warps  ACC(mi, ni, e) = R[(mi * NI + ni) * 2 + e]      (MI * NI * 2 doubles)
-    //   FMA warps     FACC(i, j)     = R[i * FC + j]                  (2 * FC doubles)
-    constexpr int NR = (MI * NI * 2 > 2 * FC) ? MI * NI * 2 : 2 * FC;
-    double R[NR];
-#define ACC(mi, ni, e) R[((mi) * NI + (ni)) * 2 + (e)]
-#define FACC(i, j) R[(i) * FC + (j)]
+    double acc[MI][NI][2];
     if (MODE == TILE_ASSIGN) {
 #pragma unroll
-        for (int t = 0; t < NR; t++) R[t] = 0.0;
+        for (int mi = 0; mi < MI; mi++)
+#pragma unroll
+            for (int ni = 0; ni < NI; ni++) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
     }
 
     const int nk = (K + KT - 1) / KT;
-    // loader mapping: NB * KT/2 16-byte chunks per operand per stage, chunk c -> (row c / (KT/2), columns 2 (c % (KT/2)))
+    // loader mapping: 1024 16-byte chunks per operand per stage; thread handles chunks tid + GT*r
     auto load_stage = [&](int slot, int kt) {
         double* As = smem + (size_t)slot * STAGE_DOUBLES;
         double* Bs = As + NB * LDSM;
         const int k0 = kt * KT;
-        for (int c = tid; c < NB * (KT / 2); c += GT) {
+#pragma unroll
+        for (int r = 0; r < NB * (KT / 2) / GT; r++) {
+            const int c = tid + GT * r;
             const int row = c / (KT / 2), kc = (c % (KT / 2)) * 2;
             if (k0 + kc < K) {
                 cp_async16(As + row * LDSM + kc, A + (size_t)row * lda + k0 + kc);
@@ -103,107 +91,52 @@ __device__ __forceinline__ void gemm_tile_nt(const double* A, int lda, const dou
         cp_async_commit();
     }
     if (MODE != TILE_ASSIGN) {  // overlaps with the pipeline fill
-        if (!fma_warp) {
 #pragma unroll
-            for (int mi = 0; mi < MI; mi++)
+        for (int mi = 0; mi < MI; mi++)
 #pragma unroll
-                for (int ni = 0; ni < NI; ni++) {
-                    const double2 v = *reinterpret_cast<const double2*>(
-                        C + (size_t)(wm * WTM + mi * 8 + g) * ldc + wn * WTN + ni * 8 + q * 2);
-                    ACC(mi, ni, 0) = (MODE == TILE_SUB) ? -v.x : v.x;
-                    ACC(mi, ni, 1) = (MODE == TILE_SUB) ? -v.y : v.y;
-                }
-        } else if (FMA_COLS) {
-#pragma unroll
-            for (int i = 0; i < 2; i++)
-#pragma unroll
-                for (int j = 0; j < FC; j += 2) {
-                    const double2 v = *reinterpret_cast<const double2*>(C + (size_t)(fr + 64 * i) * ldc + ND + j);
-                    FACC(i, j) = (MODE == TILE_SUB) ? -v.x : v.x;
-                    FACC(i, j + 1) = (MODE == TILE_SUB) ? -v.y : v.y;
-                }
-        }
+            for (int ni = 0; ni < NI; ni++) {
+                const double2 v = *reinterpret_cast<const double2*>(
+                    C + (size_t)(wm * WTM + mi * 8 + g) * ldc + wn * WTN + ni * 8 + q * 2);
+                acc[mi][ni][0] = (MODE == TILE_SUB) ? -v.x : v.x;
+                acc[mi][ni][1] = (MODE == TILE_SUB) ? -v.y : v.y;
+            }
     }
     for (int kt = 0; kt < nk; kt++) {
         cp_async_wait<STAGES - 2>();
         __syncthreads();
         if (kt + STAGES - 1 < nk) load_stage((kt + STAGES - 1) % STAGES, kt + STAGES - 1);
         cp_async_commit();
-        const double* stage = smem + (size_t)(kt % STAGES) * STAGE_DOUBLES;
-        if (!fma_warp) {
-            const double* As = stage + (wm * WTM + g) * LDSM + q;
-            const double* Bs = stage + NB * LDSM + (wn * WTN + g) * LDSM + q;
+        const double* As = smem + (size_t)(kt % STAGES) * STAGE_DOUBLES + (wm * WTM + g) * LDSM + q;
+        const double* Bs = smem + (size_t)(kt % STAGES) * STAGE_DOUBLES + NB * LDSM + (wn * WTN + g) * LDSM + q;
 #pragma unroll
-            for (int kk = 0; kk < KT / 4; kk++) {
-                double a[MI], b[NI];
+        for (int kk = 0; kk < KT / 4; kk++) {
+            double a[MI], b[NI];
 #pragma unroll
-                for (int mi = 0; mi < MI; mi++) a[mi] = As[mi * 8 * LDSM + kk * 4];
+            for (int mi = 0; mi < MI; mi++) a[mi] = As[mi * 8 * LDSM + kk * 4];
 #pragma unroll
-                for (int ni = 0; ni < NI; ni++) b[ni] = Bs[ni * 8 * LDSM + kk * 4];
+            for (int ni = 0; ni < NI; ni++) b[ni] = Bs[ni * 8 * LDSM + kk * 4];
 #pragma unroll
-                for (int mi = 0; mi < MI; mi++)
+            for (int mi = 0; mi < MI; mi++)
 #pragma unroll
-                    for (int ni = 0; ni < NI; ni++) dmma884(ACC(mi, ni, 0), ACC(mi, ni, 1), a[mi], b[ni]);
-            }
-        } else if (FMA_COLS) {
-            const double* As = stage + fr * LDSM;
-            const double* Bs = stage + NB * LDSM + ND * LDSM;
-#pragma unroll 2
-            for (int k2 = 0; k2 < KT; k2 += 2) {
-                const double2 a0 = *reinterpret_cast<const double2*>(As + k2);
-                const double2 a1 = *reinterpret_cast<const double2*>(As + 64 * LDSM + k2);
-                double2 b[FC];
-#pragma unroll
-                for (int j = 0; j < FC; j++)
-                    b[j] = *reinterpret_cast<const double2*>(Bs + j * LDSM + k2);  // warp-uniform address
-#pragma unroll
-                for (int j = 0; j < FC; j++) {  // 2 FC independent chains before any accumulator is touched again
-                    FACC(0, j) = fma(a0.x, b[j].x, FACC(0, j));
-                    FACC(1, j) = fma(a1.x, b[j].x, FACC(1, j));
-                }
-#pragma unroll
-                for (int j = 0; j < FC; j++) {
-                    FACC(0, j) = fma(a0.y, b[j].y, FACC(0, j));
-                    FACC(1, j) = fma(a1.y, b[j].y, FACC(1, j));
-                }
-            }
+                for (int ni = 0; ni < NI; ni++) dmma884(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
         }
     }
     cp_async_wait<0>();
-    if (!fma_warp) {
 #pragma unroll
-        for (int mi = 0; mi < MI; mi++)
+    for (int mi = 0; mi < MI; mi++)
 #pragma unroll
-            for (int ni = 0; ni < NI; ni++) {
-                const int r = wm * WTM + mi * 8 + g, c = wn * WTN + ni * 8 + q * 2;
-                double2 v;
-                v.x = (MODE == TILE_SUB) ? -ACC(mi, ni, 0) : ACC(mi, ni, 0);
-                v.y = (MODE == TILE_SUB) ? -ACC(mi, ni, 1) : ACC(mi, ni, 1);
-                *reinterpret_cast<double2*>(C + (size_t)r * ldc + c) = v;
-                if (Ct) {
-                    Ct[(size_t)c * ldct + r] = v.x;
-                    Ct[(size_t)(c + 1) * ldct + r] = v.y;
-                }
+        for (int ni = 0; ni < NI; ni++) {
+            const int r = wm * WTM + mi * 8 + g, c = wn * WTN + ni * 8 + q * 2;
+            double2 v;
+            v.x = (MODE == TILE_SUB) ? -acc[mi][ni][0] : acc[mi][ni][0];
+            v.y = (MODE == TILE_SUB) ? -acc[mi][ni][1] : acc[mi][ni][1];
+            *reinterpret_cast<double2*>(C + (size_t)r * ldc + c) = v;
+            if (Ct) {
+                Ct[(size_t)c * ldct + r] = v.x;
+                Ct[(size_t)(c + 1) * ldct + r] = v.y;
             }
-    } else if (FMA_COLS) {
-#pragma unroll
-        for (int i = 0; i < 2; i++)
-#pragma unroll
-            for (int j = 0; j < FC; j += 2) {
-                const int r = fr + 64 * i, c = ND + j;
-                double2 v;
-                v.x = (MODE == TILE_SUB) ? -FACC(i, j) : FACC(i, j);
-                v.y = (MODE == TILE_SUB) ? -FACC(i, j + 1) : FACC(i, j + 1);
-                *reinterpret_cast<double2*>(C + (size_t)r * ldc + c) = v;
-                if (Ct) {
-                    Ct[(size_t)c * ldct + r] = v.x;
-                    Ct[(size_t)(c + 1) * ldct + r] = v.y;
-                }
-            }
-    }
+        }
 }
-#undef ACC
-#undef FACC
 
 // ---- generic C (+)= A B^T over a grid of tiles (also the public DGEMM of the library) ----------
 template <int MODE>
