@@ -297,8 +297,8 @@ def run_gpu(args):
         _lib.profile(0)
         GL.SOLVE_STREAMS = n_streams
     # ---- timed: end to end from host buffers ----
-    for _ in range(3):  # warm-up: the caching allocators (device and pinned host) settle on this path's block sizes
-        step_e2e()
+    for _ in range(6):  # warm-up: the caching allocators (device, per stream; pinned host) need a few steps to settle
+        step_e2e()      # on this path's block sizes -- a late cudaMalloc of a GB-sized segment costs 10-200 ms
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()

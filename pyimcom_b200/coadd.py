@@ -27,6 +27,7 @@ import torch
 
 from . import _lib
 from .lakernel import SOLVERS, ApplySpec, DeviceSystem, apply_T, eigen_decompose_batch, ptr, rup, solve_chol_batch, solve_eigen
+from .lakernel import solve_chol_finish, solve_chol_launch, side_streams_in_use
 from .lakernel import stream_handle
 from .lakernel import trapezoid_weights
 from .psfovl_host import anchor
@@ -94,6 +95,9 @@ class _Arena:
 
 
 _TOTAL_HBM = {}
+# Pair-block pools outlive the GpuBlock that used them: a fresh block takes a parked pool instead of asking the
+# allocator for another multi-GB segment (a cudaMalloc of that size was measured to stall a step by > 100 ms).
+_PARKED_POOLS = {}
 
 
 def hbm_free_estimate() -> int:
@@ -363,13 +367,23 @@ class GpuBlock:
         total = sum(size(nA, nB) for _, nA, nB in need)
         cap = self._pool.numel() if self._pool is not None else 0
         if self._pool_used + total > cap:
+            cur = torch.cuda.current_stream()
+            for st in side_streams_in_use():  # a pipelined batch may still be cutting its A out of the pool there
+                cur.wait_stream(st)
             self._pairs.clear()  # evict everything (stream order keeps earlier readers safe)
             self._pool_used = 0
             need = wanted()
             total = sum(size(nA, nB) for _, nA, nB in need)
             if total > cap:
-                self._pool = None
-                self._pool = torch.empty(max(total, self._pool_target() // 8), dtype=torch.float64, device="cuda")
+                self._release_pool()
+                want = max(total, self._pool_target() // 8)
+                parked = _PARKED_POOLS.setdefault(torch.cuda.current_device(), [])
+                fit = [t for t in parked if t.numel() >= want]
+                if fit:
+                    self._pool = min(fit, key=lambda t: t.numel())
+                    parked[:] = [t for t in parked if t is not self._pool]  # (list.remove would compare tensors)
+                else:
+                    self._pool = torch.empty(want, dtype=torch.float64, device="cuda")
         desc = np.zeros(len(need), dtype=PAIRDESC_DTYPE)
         tiles = np.zeros(len(need) + 1, dtype=np.int64)
         points = 0.0
@@ -390,6 +404,20 @@ class GpuBlock:
                              int(tiles[-1]), ptr(self.d_tables), ptr(self.d_pair_lut), self.blk.n_inimage,
                              self.arena.ngrid, float(cfg.dscale), float(cfg.nc_ovl), float(cfg.flat_penalty),
                              self.arena.poly, ptr(self._pool), float(points), stream_handle())
+
+    def _release_pool(self):
+        """Park the pair-block pool for the next GpuBlock on this device (at most two are kept)."""
+        pool, self._pool = getattr(self, "_pool", None), None
+        if pool is not None and _PARKED_POOLS is not None:
+            parked = _PARKED_POOLS.setdefault(pool.device.index, [])
+            if len(parked) < 2:
+                parked.append(pool)
+
+    def __del__(self):
+        try:
+            self._release_pool()
+        except Exception:  # interpreter shutdown
+            pass
 
     def _pool_target(self) -> int:
         """Bytes of the pair-block pool: everything the planned OutStamps can ever need if that fits the budget
@@ -586,8 +614,45 @@ class GpuBlock:
         independent stamps (order inside the block is the reference's)."""
         assert self._uploaded, "call prepare() first"
         nb = batch or self.batch_size()
-        for k0 in range(0, len(self.order), nb):
-            self.coadd_batch(list(range(k0, min(k0 + nb, len(self.order)))))
+        batches = [list(range(k0, min(k0 + nb, len(self.order)))) for k0 in range(0, len(self.order), nb)]
+        if self.kernel == "Cholesky" and self.cfg.n_out == 1 and len(batches) > 1 and self.a_cache:
+            return self._run_pipelined(batches)
+        for ks in batches:
+            self.coadd_batch(ks)
+        return self
+
+    def _run_pipelined(self, batches):
+        """Software pipeline over batches (CholKernel, one output PSF): the stage-(a) kernels of batch k+1 are enqueued
+        on the caller's stream before anybody waits for batch k, whose factorisation runs on the solve streams; the
+        T-apply of batch k then overlaps the factorisation of batch k+1.  The solve streams never run dry and their
+        partial waves are filled by the interpolation / apply kernels."""
+        cfg = self.cfg
+        need_A = len(np.atleast_1d(cfg.kappaC_arr)) > 1
+        pending = None
+
+        def finish(pend):
+            live, handle = pend
+            kos = solve_chol_finish(handle)
+            for u, (k, p, ds, indata) in enumerate(live):
+                spec = self.apply_spec(k, indata, want_T32=False, want_Ti64=False)
+                self._overlap_add(p, 0, apply_T(ds, kos[u], 0, spec))
+
+        for ks in batches:
+            plans = [self.plans[self.order[k]] for k in ks]
+            self.ensure_pairs([pl for pl in plans if pl.n > 0])
+            live = []
+            for k, p in zip(ks, plans):
+                if p.n == 0:
+                    self._empty_stamp(p, False)
+                    continue
+                ds, indata = self.build_system(k, need_A=need_A)
+                live.append((k, p, ds, indata))
+            handle = solve_chol_launch([t[2] for t in live], cfg, 0)
+            if pending is not None:
+                finish(pending)
+            pending = (live, handle)
+        if pending is not None:
+            finish(pending)
         return self
 
     def download(self):

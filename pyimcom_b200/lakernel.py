@@ -208,18 +208,23 @@ def _side_streams(n):
     return have[:n]
 
 
-def _chol_solve_items(items):
-    """Factor + solve A_k + sum(incs_k) for every item (ds, incs, j_out); the systems of all items go through
-    the batched factorisation together (up to MAXB per launch sequence) and the LAPACK-style info codes are read
-    back once.  Failing items take the repair branch of CholKernel._cholesky_wrapper (lakernel.py:262-279).
-    Returns the list of solutions X_k (mpad, npad), rows = Ti."""
+def side_streams_in_use():
+    """The solve streams created so far on the current device."""
+    return list(_SIDE.get(torch.cuda.current_device(), []))
+
+
+def _chol_launch(items):
+    """Enqueue factor + solve of A_k + sum(incs_k) for every item (ds, incs, j_out): the systems go through the
+    batched factorisation together (up to MAXB per launch sequence, independent groups on separate streams).
+    Nothing is synchronised; returns the handle _chol_finish completes."""
     n_items = len(items)
     Xs = [None] * n_items
-    infos = []
+    infos, events = [], []
     cur = torch.cuda.current_stream()
     nstream = min(SOLVE_STREAMS, n_items) if n_items > 1 else 1
     if nstream <= 1:
         chunks = [(c0, min(c0 + _lib.MAXB, n_items), cur) for c0 in range(0, n_items, _lib.MAXB)]
+        pool = []
     else:
         # independent groups of systems on separate streams: the serial diagonal-block factorisations and the partial
         # last waves of one group's tile kernels are filled by the other group's work
@@ -241,10 +246,21 @@ def _chol_solve_items(items):
                 info.record_stream(cur)
             infos.append(info)
             del Ws
-    if nstream > 1:
-        for st in pool:
-            cur.wait_stream(st)
-    bad = torch.cat(infos).cpu().numpy()
+    for st in pool:  # the caller's stream will wait for exactly this work, not for whatever is enqueued later
+        ev = torch.cuda.Event()
+        ev.record(st)
+        events.append(ev)
+    return dict(items=items, Xs=Xs, infos=infos, events=events)
+
+
+def _chol_finish(h):
+    """Join the solve streams, read the LAPACK-style info codes back once, and send failing items through the
+    repair branch of CholKernel._cholesky_wrapper (lakernel.py:262-279).  Returns the solutions X_k (mpad, npad)."""
+    items, Xs = h["items"], h["Xs"]
+    cur = torch.cuda.current_stream()
+    for ev in h["events"]:
+        cur.wait_event(ev)
+    bad = torch.cat(h["infos"]).cpu().numpy()
     if bad.any():
         shifts = {}
         for k in np.nonzero(bad)[0]:
@@ -260,6 +276,11 @@ def _chol_solve_items(items):
             if int(info2.item()) != 0:
                 raise np.linalg.LinAlgError("Cholesky failed after the eigenvalue repair")
     return Xs
+
+
+def _chol_solve_items(items):
+    """Factor + solve for every item (ds, incs, j_out), with the repair branch; returns the list of solutions."""
+    return _chol_finish(_chol_launch(items))
 
 
 def _chol_with_repair(ds: DeviceSystem, inc_lists, j_out):
@@ -290,9 +311,9 @@ def _node_reduce(ds, j_out, Tpi, kappa_arr, kappaC_arr, ucmin, smax, Epq_in=None
                         extras=dict(Dp=Dp, Npq=Npq, Epq=Epq, out_w=ow, iv=iv, branch=br))
 
 
-def solve_chol_batch(dss, cfg, j_out: int):
-    """CholKernel for one output PSF of several output stamps at once (lakernel.py:281-394): the nv systems of
-    every stamp share one batched factorisation.  Returns one KernelOutput per stamp."""
+def solve_chol_launch(dss, cfg, j_out: int):
+    """CholKernel for one output PSF of several output stamps at once (lakernel.py:281-394): enqueue the nv systems of
+    every stamp into one batched factorisation.  Returns the handle solve_chol_finish turns into KernelOutputs."""
     kappaC = np.asarray(cfg.kappaC_arr, dtype=np.float64)
     nv = kappaC.size
     items = []
@@ -305,7 +326,16 @@ def solve_chol_batch(dss, cfg, j_out: int):
         for p in range(nv):  # cumulative diagonal increments (lakernel.py:356)
             run.append(float(kappa_arr[p] - (kappa_arr[p - 1] if p > 0 else 0)))
             items.append((ds, list(run), j_out))
-    Xs = _chol_solve_items(items)
+    return dict(h=_chol_launch(items), dss=list(dss), cfg=cfg, j_out=j_out) if items else None
+
+
+def solve_chol_finish(handle):
+    if handle is None:
+        return []
+    dss, cfg, j_out = handle["dss"], handle["cfg"], handle["j_out"]
+    kappaC = np.asarray(cfg.kappaC_arr, dtype=np.float64)
+    nv = kappaC.size
+    Xs = _chol_finish(handle["h"])
     outs = []
     for q, ds in enumerate(dss):
         kappa_arr = kappaC * float(ds.C[j_out])
@@ -315,6 +345,11 @@ def solve_chol_batch(dss, cfg, j_out: int):
             Tpi = torch.stack(Xs[q * nv:(q + 1) * nv])
             outs.append(_node_reduce(ds, j_out, Tpi, kappa_arr, kappaC, cfg.uctarget, cfg.sigmamax))
     return outs
+
+
+def solve_chol_batch(dss, cfg, j_out: int):
+    """solve_chol_launch + solve_chol_finish.  Returns one KernelOutput per stamp."""
+    return solve_chol_finish(solve_chol_launch(dss, cfg, j_out))
 
 
 def solve_chol(ds: DeviceSystem, cfg, j_out: int) -> KernelOutput:

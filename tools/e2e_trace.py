@@ -47,7 +47,12 @@ def main():
         names = ["prepare", "batch_size", "ensure_pairs", "build_enq", "build_sync", "solve", "apply_enq", "download"]
         d = [1e3 * (h[i + 1] - h[i]) for i in range(len(h) - 1)]
         tot = sum(d)
-        print(f"rep {rep:2d} total {tot:6.1f} | " + " ".join(f"{n} {v:.1f}" for n, v in zip(names, d)), flush=True)
+        from pyimcom_b200 import coadd as _c
+        ms = torch.cuda.memory_stats()
+        print(f"rep {rep:2d} total {tot:6.1f} | " + " ".join(f"{n} {v:.1f}" for n, v in zip(names, d))
+              + f" | segs {ms.get('segment.all.allocated', 0)} reserved {ms.get('reserved_bytes.all.current', 0) / 2**30:.2f} "
+              f"pool@{gb._pool.data_ptr() if gb._pool is not None else 0:x} parked {[t.numel() for t in _c._PARKED_POOLS.get(0, [])]}",
+              flush=True)
         del live, kos, res, maps, gb
 
 
