@@ -7,9 +7,9 @@
 Workload (BASELINE.json configs[3], the configuration the metric is quoted on): a paper4-shaped synthetic
 block -- n2 = 32, FADE = 3 (m = 1444 output px per stamp incl. fade), dtheta = 0.0390625", NPIXPSF = 48,
 oversamp = 8 (395^2-entry padded PSF-overlap tables), INPAD = 1.24", KAPPAC = [6e-4], 6 input images,
-n_inframe = 6 layers, CholKernel; n ~ 6.5 k selected input pixels per stamp -- reduced to n1P x n1P = 4 x 4
-output stamps per block so that a step takes a fraction of a second.  One STEP = one block (16 OutStamps):
-gather -> A / mBhalf assembly -> batched FP64 Cholesky + triangular solves -> T apply -> overlap-add.
+n_inframe = 6 layers, CholKernel; n ~ 6.3 k selected input pixels per stamp -- reduced to n1P x n1P = 8 x 8
+output stamps per block so that a step takes about half a second.  One STEP = one block (64 OutStamps, four batches
+of 16): gather -> A / mBhalf assembly -> batched FP64 Cholesky + triangular solves -> T apply -> overlap-add.
 Every rank owns its own block (weak scaling, seed = 1000 + rank); the only collective is the final gather of
 the output cube to rank 0 (NCCL).
 
@@ -48,23 +48,23 @@ UNIT = "output px/s"
 SEED0 = 1000
 
 
-def workload_cfg(kernel="Cholesky"):
-    return StampConfig(n1=2, n2=32, dtheta_arcsec=0.0390625, fade_kernel=3, postage_pad=1, npixpsf=48, oversamp=8,
+def workload_cfg(kernel="Cholesky", n1=6):
+    return StampConfig(n1=n1, n2=32, dtheta_arcsec=0.0390625, fade_kernel=3, postage_pad=1, npixpsf=48, oversamp=8,
                        instamp_pad_arcsec=1.24, n_out=1, n_inframe=6, linear_algebra=kernel,
                        kappaC_arr=np.array([6e-4]), uctarget=1e-6, sigmamax=0.5)
 
 
-def make_block(rank):
-    cfg = workload_cfg()
+def make_block(rank, n1=6):
+    cfg = workload_cfg(n1=n1)
     return SynthBlock(cfg, n_image=6, seed=SEED0 + rank, psf_sigmas=(0.85, 0.9, 0.95, 1.0, 1.05, 1.1), star=True)
 
 
 def config_dict(cfg, n_stamps, extra=None):
-    d = {"workload": "paper4-shaped synthetic block (BASELINE.json configs[3]), CholKernel, reduced to n1P=4",
+    d = {"workload": f"paper4-shaped synthetic block (BASELINE.json configs[3]), CholKernel, reduced to n1P={cfg.n1P}",
          "n2": cfg.n2, "fade": cfg.fade_kernel, "n2f": cfg.n2f, "m": cfg.n2f**2, "stamps_per_block": n_stamps,
          "n_images": 6, "n_inframe": cfg.n_inframe, "kappaC": [6e-4], "npixpsf": cfg.npixpsf, "oversamp": cfg.oversamp,
          "inpad_arcsec": 1.24, "dtheta_arcsec": cfg.dtheta_arcsec, "blocks_per_gpu_per_step": 1,
-         "l2_policy": "per-stamp working set (A 0.35 GB + mBhalf 0.08 GB, fresh buffers every stamp) exceeds the 126 MB L2"}
+         "l2_policy": "per-stamp working set (A 0.31 GB + mBhalf 0.08 GB, fresh buffers every stamp) exceeds the 126 MB L2"}
     if extra:
         d.update(extra)
     return d
@@ -266,7 +266,6 @@ def run_gpu(args):
             step_resident()
         # ---- timed: resident inputs ----
         barrier()
-        _lib.profile(1)
         n0 = _lib.launch_count()
         clk.mark()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -278,6 +277,18 @@ def run_gpu(args):
         clk.mark_end()
     launches = _lib.launch_count() - n0
     t_res = e0.elapsed_time(e1) * 1e-3
+    # ---- the same K steps again with a pair of CUDA events around every launch of the library (per-kernel device
+    # time for the roofline): identical work and stream layout; the event records themselves cost a few percent, which
+    # is why the throughput above is taken without them ----
+    barrier()
+    _lib.profile(1)
+    e0p, e1p = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0p.record()
+    for _ in range(args.steps):
+        step_resident()
+    e1p.record()
+    barrier()
+    t_prof = e0p.elapsed_time(e1p) * 1e-3
     prof = _lib.profile_read()
     _lib.profile(0)
     # ---- one extra step with the solve groups serialised on one stream: per-launch event intervals of the timed
@@ -297,8 +308,9 @@ def run_gpu(args):
         _lib.profile(0)
         GL.SOLVE_STREAMS = n_streams
     # ---- timed: end to end from host buffers ----
-    for _ in range(6):  # warm-up: the caching allocators (device, per stream; pinned host) need a few steps to settle
-        step_e2e()      # on this path's block sizes -- a late cudaMalloc of a GB-sized segment costs 10-200 ms
+    for _ in range(4):  # warm-up, written exactly like the timed loop (the previous block stays referenced while the next
+        g2, maps = step_e2e()  # one is built): the caching allocators must have seen two coexisting blocks before the
+        # clock starts -- a late cudaMalloc of a GB-sized segment costs 10-200 ms
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -339,7 +351,7 @@ def run_gpu(args):
             fl = sum(pr[k][1] for k in pr if k.startswith(("chol_", "back_")))
             return ms, fl
 
-        stages = stage_table(prof, t_res)
+        stages = stage_table(prof, t_prof)
         dom = "chol_super_update"
         ms, work, cnt = prof.get(dom, (0.0, 0.0, 0))
         ach = work / (ms * 1e-3) / 1e12 if ms > 0 else 0.0
@@ -353,13 +365,14 @@ def run_gpu(args):
                                    "(MEASURED_PEAKS.json has no FP64 entry)",
                     "launches": cnt, "avg_launch_ms": round(ms / max(cnt, 1), 4),
                     "flops_per_launch": work / max(cnt, 1),
-                    "note": (f"timed region runs {n_streams} concurrent solve streams: a launch's event interval includes the "
-                             "time it shares the SMs with the other streams' kernels; 'serialized' repeats the step on "
-                             "one stream") if n_streams > 1 else "one stream",
+                    "note": (f"per-launch events are recorded on a repeat of the K timed steps (same work, same {n_streams} "
+                             "concurrent solve streams, batches pipelined): a launch's event interval includes the time it "
+                             "shares the SMs with the other streams' kernels; 'serialized' repeats one step on one stream"),
                     "all_dmma_kernels": {"achieved": round(tensor_fl / (tensor_ms * 1e-3) / 1e12, 3) if tensor_ms else 0,
-                                         "share_of_step": round(tensor_ms * 1e-3 / t_res, 4),
+                                         "share_of_step": round(tensor_ms * 1e-3 / t_prof, 4),
                                          "flops_per_step": tensor_fl / max(args.steps, 1),
                                          "achieved_wall": round(tensor_fl / t_res / 1e12, 3)},
+                    "ms_per_step_with_events": round(1e3 * t_prof / args.steps, 3),
                     "hbm_peak_gbs": hbm_peak, "hbm_peak_source": hbm_src, "stages": stages}
         if prof_serial:
             t_ser = sum(v[0] for v in prof_serial.values()) * 1e-3

@@ -231,16 +231,15 @@ def _chol_launch(items):
         per = min(_lib.MAXB, -(-n_items // nstream))
         pool = _side_streams(nstream)
         chunks = [(c0, min(c0 + per, n_items), pool[q % nstream]) for q, c0 in enumerate(range(0, n_items, per))]
-        for st in pool:
-            st.wait_stream(cur)
+    # right-hand sides are cloned on the caller's stream (whose allocator pool they return to after the T-apply stage);
+    # the solve streams only own what they allocate and free themselves (W, the inverted diagonal blocks)
+    for k, (ds, _, j) in enumerate(items):
+        Xs[k] = ds.mB[j].clone()
+    for st in pool:
+        st.wait_stream(cur)
     for c0, c1, st in chunks:
         with torch.cuda.stream(st):
             Ws = [_padded_system(ds, incs) for ds, incs, _ in items[c0:c1]]
-            for k in range(c0, c1):
-                ds, _, j = items[k]
-                Xs[k] = ds.mB[j].clone()
-                if st is not cur:
-                    Xs[k].record_stream(cur)  # consumed by the T-apply stage on the caller's stream
             info, _keep = chol_solve_batch(Ws, Xs[c0:c1])
             if st is not cur:
                 info.record_stream(cur)

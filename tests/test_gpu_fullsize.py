@@ -43,7 +43,7 @@ def rel(a, b):
 
 @pytest.fixture(scope="module")
 def block():
-    blk = bench.make_block(0)
+    blk = bench.make_block(0, n1=2)
     tab = PSFTables(blk, G.iD5512C, G.gridD5512C, dedup=True)
     return blk, tab
 

@@ -15,7 +15,7 @@ from pyimcom_b200.psfovl_host import PSFTables  # noqa: E402
 
 
 def main():
-    blk = bench.make_block(0)
+    blk = bench.make_block(0, n1=2)
     tab = PSFTables(blk, G.iD5512C, G.gridD5512C, dedup=True)
     for rep in range(8):
         torch.cuda.synchronize()

@@ -17,7 +17,7 @@ from pyimcom_b200.psfovl_host import PSFTables  # noqa: E402
 
 def main():
     nrep = int(sys.argv[1]) if len(sys.argv) > 1 else 30
-    blk = bench.make_block(0)
+    blk = bench.make_block(0, n1=2)
     tab = PSFTables(blk, G.iD5512C, G.gridD5512C, dedup=True)
     cfg = blk.cfg
     for rep in range(nrep):

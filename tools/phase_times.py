@@ -16,7 +16,7 @@ from pyimcom_b200.psfovl_host import PSFTables  # noqa: E402
 
 
 def main():
-    blk = bench.make_block(0)
+    blk = bench.make_block(0, n1=2)
     tab = PSFTables(blk, G.iD5512C, G.gridD5512C, dedup=True)
     t0 = time.perf_counter()
     gb = GpuBlock(blk, tab)
