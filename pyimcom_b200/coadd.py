@@ -68,6 +68,12 @@ class _Arena:
         self.stride = {}
         self.size = 0
 
+    def register(self, arr, poly=False):
+        """(base offset, stride between consecutive tables) of the table set arr inside the arena, in doubles."""
+        self.offset(arr, (0,) * (arr.ndim - 2), poly=poly)
+        key = (id(arr), self.poly if poly else 0)
+        return self.base[key], self.stride[key]
+
     def offset(self, arr, idx, poly=False):
         """Offset (in doubles) of table arr[idx] inside the arena; registers arr on first use."""
         P = self.poly if poly else 0
@@ -244,7 +250,11 @@ class GpuBlock:
         return p
 
     def _pair_lut(self, Ga, Gb) -> int:
-        """Index of the (nimg x nimg) table-reference block for pixels of group Ga (rows) against group Gb (columns)."""
+        """Index of the (nimg x nimg) table-reference block for pixels of group Ga (rows) against group Gb (columns).
+
+        Same rules as PSFTables.table_ii_ref (same group: triangle entry, flipped when a > b, psfutil.py:1652-1665;
+        different groups: dense table of the ordered pair, the reversed order being the flipped table), evaluated for
+        the whole image x image block at once."""
         key = (Ga, Gb)
         if key not in self._pair_lut_idx:
             tab, cfg, nimg = self.tab, self.cfg, self.blk.n_inimage
@@ -252,11 +262,29 @@ class GpuBlock:
             arr["offset"] = -1
             tab.group(Ga)
             tab.group(Gb)
-            n_in = len(tab.grp_imgs[Ga]) if Ga == Gb else (len(tab.grp_imgs[Ga]) * len(tab.grp_imgs[Gb])) ** 0.5
-            for ka in tab.grp_imgs[Ga]:
-                for kb in tab.grp_imgs[Gb]:
-                    t, tidx, flip = tab.table_ii_ref(Ga, ka, Gb, kb)
-                    arr[ka, kb] = (self.arena.offset(t, tidx, poly=True), int(flip), 0, cfg.flat_penalty / n_in)
+            ia, ib = np.asarray(tab.grp_imgs[Ga], dtype=np.int64), np.asarray(tab.grp_imgs[Gb], dtype=np.int64)
+            na, nb = ia.size, ib.size
+            if na and nb:
+                qa, qb = np.meshgrid(np.arange(na), np.arange(nb), indexing="ij")  # positions inside the groups
+                if Ga == Gb:
+                    base, stride = self.arena.register(tab.get_self(Ga), poly=True)
+                    lo, hi = np.minimum(qa, qb), np.maximum(qa, qb)
+                    flat = (2 * na - lo + 1) * lo // 2 + hi - lo  # tri_index(n_psf, lo, hi), psfutil.py:1139-1175
+                    flip = qa > qb
+                    n_in = float(na)
+                elif Ga < Gb:
+                    base, stride = self.arena.register(tab.get_cross(Ga, Gb), poly=True)
+                    flat, flip = qa * nb + qb, np.zeros_like(qa, dtype=bool)
+                    n_in = (na * nb) ** 0.5
+                else:
+                    base, stride = self.arena.register(tab.get_cross(Gb, Ga), poly=True)
+                    flat, flip = qb * na + qa, np.ones_like(qa, dtype=bool)
+                    n_in = (na * nb) ** 0.5
+                sub = np.zeros((na, nb), dtype=TABLEREF_DTYPE)
+                sub["offset"] = base + flat * stride
+                sub["flip"] = flip
+                sub["penalty_sub"] = cfg.flat_penalty / n_in
+                arr[np.ix_(ia, ib)] = sub
             self._pair_lut_idx[key] = len(self._pair_lut_list)
             self._pair_lut_list.append(arr)
         return self._pair_lut_idx[key]
