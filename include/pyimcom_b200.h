@@ -96,6 +96,13 @@ typedef struct b200_table_ref {
 int b200_dev_layout_tables(const double* src, int ntab, int ns, int pad, int ngrid, int poly, double* dst,
                            void* stream);
 
+/* PSF-overlap spectra (PSFOvl._build_psfovl, psfutil.py:1244-1294: rft1 * conj(rft2)): n1 spectra of `per` complex
+ * entries each, stored as separate real and imaginary planes, times the conjugate of spectrum t of the second stack
+ * (stride2 doubles apart; stride2 == 0 broadcasts one spectrum); im_sign = -1 returns the conjugate product
+ * conj(F1) * F2 instead. */
+int b200_dev_cmul_conj(const double* ar, const double* ai, const double* br, const double* bi, long long per,
+                       long long stride2, long long n1, double im_sign, double* gr, double* gi, void* stream);
+
 /* Gather the selected input pixels of one output stamp (coadd.py:969-977): out[k] = src[idx[k]] for positions,
  * codes (src_code/pcode may both be NULL) and the n_inframe float32 layers (src_data (n_inframe, src_ld) ->
  * indata (n_inframe, ldi), zero padded). */

@@ -94,6 +94,7 @@ PROTOTYPES = {
     "b200_dev_iD5512C_sym": [vp, i32, i32, i32, vp, vp, i64, vp, vp],
     "b200_dev_gridD5512C": [vp, i32, i32, vp, vp, i64, i32, i32, vp, vp],
     "b200_dev_layout_tables": [vp, i32, i32, i32, i32, i32, vp, vp],
+    "b200_dev_cmul_conj": [vp, vp, vp, vp, C.c_longlong, C.c_longlong, C.c_longlong, f64, vp, vp, vp],
     "b200_dev_gather_stamp": [vp, i32, i32, vp, vp, vp, vp, i64, i32, vp, vp, vp, vp, i32, vp],
     "b200_dev_build_A": [vp, vp, vp, i32, i32, vp, vp, i32, i32, i32, f64, f64, f64, vp, i32, f64, i32, vp],
     "b200_dev_pair_blocks": [vp, vp, vp, vp, vp, i32, i32, vp, vp, i32, i32, f64, f64, f64, i32, vp, f64, vp],

@@ -94,8 +94,11 @@ class _Arena:
         self.h2d_bytes = 0
         st = stream_handle()
         for arr, lead, P, base in self.sets:
-            src = h2d(np.asarray(arr, dtype=np.float64).reshape(lead, self.ns, self.ns))
-            self.h2d_bytes += src.numel() * 8
+            if torch.is_tensor(arr):  # built on the device (psfovl_device.DeviceTables): nothing crosses PCIe
+                src = arr.reshape(lead, self.ns, self.ns).contiguous()
+            else:
+                src = h2d(np.asarray(arr, dtype=np.float64).reshape(lead, self.ns, self.ns))
+                self.h2d_bytes += src.numel() * 8
             _lib.dev_layout_tables(ptr(src), lead, self.ns, 6, self.ngrid, P, C.c_void_p(dst.data_ptr() + 8 * base), st)
         return dst
 

@@ -300,6 +300,10 @@ int b200_dev_gridD5512C(const double* f, int ngy, int ngx, const double* x, cons
 int b200_dev_layout_tables(const double* src, int ntab, int ns, int pad, int ngrid, int poly, double* dst, void* s) {
     return launch_layout_tables(src, ntab, ns, pad, ngrid, poly, dst, ST(s));
 }
+int b200_dev_cmul_conj(const double* ar, const double* ai, const double* br, const double* bi, long long per,
+                       long long stride2, long long n1, double im_sign, double* gr, double* gi, void* s) {
+    return launch_cmul_conj(ar, ai, br, bi, per, stride2, n1, im_sign, gr, gi, ST(s));
+}
 int b200_dev_gather_stamp(const int* idx, int n, int npad, const double* sx, const double* sy, const int* scode,
                           const float* sdata, long src_ld, int n_inframe, double* px, double* py, int* pcode,
                           float* indata, int ldi, void* s) {

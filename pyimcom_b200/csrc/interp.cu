@@ -686,6 +686,21 @@ __global__ void __launch_bounds__(256) k_layout_tables(const double* __restrict_
     dst[e] = (sy >= 0 && sy < ns && sx >= 0 && sx < ns) ? src[((size_t)t * ns + sy) * ns + sx] : 0.0;
 }
 
+// PSF-overlap spectra: G = F1 * conj(F2) element by element on split real / imaginary planes.
+// F2 may be a single spectrum broadcast over the n1 spectra of F1 (stride2 == 0) or a matching stack.
+__global__ void __launch_bounds__(256) k_cmul_conj(const double* __restrict__ ar, const double* __restrict__ ai,
+                                                   const double* __restrict__ br, const double* __restrict__ bi,
+                                                   long long per, long long stride2, long long total, double im_sign,
+                                                   double* __restrict__ gr, double* __restrict__ gi) {
+    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= total) return;
+    const long long t = e / per, r = e - t * per;
+    const double xr = ar[e], xi = ai[e];
+    const double yr = br[t * stride2 + r], yi = bi[t * stride2 + r];
+    gr[e] = fma(xr, yr, xi * yi);
+    gi[e] = im_sign * fma(xi, yr, -(xr * yi));
+}
+
 __global__ void k_getw(double* __restrict__ w, double fh) {
     double t[10];
     d5512_getw(t, fh);
@@ -732,6 +747,15 @@ int launch_layout_tables(const double* src, int ntab, int ns, int pad, int ngrid
     const long long per = poly > 0 ? (long long)poly * poly * ncell * ncell : (long long)ngrid * ngrid;
     const long long tot = per * ntab;
     k_layout_tables<<<(unsigned)((tot + 255) / 256), 256, 0, s>>>(src, ntab, ns, pad, ngrid, poly, dst);
+    B200_LAUNCH_CHECK();
+    return 0;
+}
+
+int launch_cmul_conj(const double* ar, const double* ai, const double* br, const double* bi, long long per,
+                     long long stride2, long long n1, double im_sign, double* gr, double* gi, cudaStream_t s) {
+    const long long total = per * n1;
+    if (total <= 0) return 0;
+    k_cmul_conj<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(ar, ai, br, bi, per, stride2, total, im_sign, gr, gi);
     B200_LAUNCH_CHECK();
     return 0;
 }

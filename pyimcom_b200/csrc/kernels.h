@@ -37,6 +37,8 @@ int launch_gridD5512C(const double* f, int ngy, int ngx, const double* x, const 
                       double* out, cudaStream_t s);
 int launch_layout_tables(const double* src, int ntab, int ns, int pad, int ngrid, int poly, double* dst,
                          cudaStream_t s);
+int launch_cmul_conj(const double* ar, const double* ai, const double* br, const double* bi, long long per,
+                     long long stride2, long long n1, double im_sign, double* gr, double* gi, cudaStream_t s);
 int launch_gather_stamp(const int* idx, int n, int npad, const double* src_x, const double* src_y, const int* src_code,
                         const float* src_data, long src_ld, int n_inframe, double* px, double* py, int* pcode,
                         float* indata, int ldi, cudaStream_t s);

@@ -374,6 +374,43 @@ def test_pair_block_cache_is_bit_identical(name):
         assert cached.pair_points < tot
 
 
+@pytest.mark.parametrize("name", ["chol1", "pad4"])
+def test_device_tables(name):
+    """PSF-overlap tables built on the device (device iD5512C sampling + partial DFTs as DMMA
+    products) equal the NumPy-FFT tables of the host builder, and a block coadded from them equals the oracle."""
+    from pyimcom_b200.psfovl_device import DeviceTables
+
+    spec = cases.BLOCK_CASES[name]
+    blk = cases.make_block(spec)
+    host = PSFTables(blk, G.iD5512C, G.gridD5512C)
+    dev = DeviceTables(blk, G.iD5512C, G.gridD5512C)
+    assert rel(dev.outovlc, host.outovlc) < 1e-12
+    groups = sorted({(j >> 1 << 1, i >> 1 << 1) for j in range(blk.cfg.n1P + 2) for i in range(blk.cfg.n1P + 2)})
+    for Gk in groups:
+        host.group(Gk)
+        dev.group(Gk)
+        assert host.grp_imgs[Gk] == dev.grp_imgs[Gk]
+        if not host.grp_imgs[Gk]:
+            continue
+        assert rel(dev.get_self(Gk).cpu().numpy(), host.get_self(Gk)) < 1e-11
+        assert rel(dev.get_io(Gk).cpu().numpy(), host.get_io(Gk)) < 1e-11
+    for Ga in groups:
+        for Gb in groups:
+            if Ga < Gb and host.grp_imgs[Ga] and host.grp_imgs[Gb] and max(abs(Ga[0] - Gb[0]), abs(Ga[1] - Gb[1])) <= 2:
+                assert rel(dev.get_cross(Ga, Gb).cpu().numpy(), host.get_cross(Ga, Gb)) < 1e-11
+    gb = GpuBlock(blk, dev).prepare(stamps=spec["stamps"])
+    otab = PSFTables(blk, R.iD5512C, R.gridD5512C)
+    j, i = spec["stamps"][0]
+    s = GpuOutStamp(gb, j, i)
+    o = OracleOutStamp(blk, otab, j, i)
+    o.build_system_matrices()
+    OL.CholKernel(o)()
+    o.post_kernel()
+    o.perform_coaddition()
+    assert rel(s.sysmata, o.sysmata) < P64 and rel(s.mhalfb, o.mhalfb) < P64
+    assert rel(s.T, o.T) < P32 and rel(s.outimage, o.outimage) < 5 * P32
+
+
 def test_block_run_maps():
     """Whole-block loop: the accumulated maps equal the overlap-add of the per-stamp oracle results."""
     spec = cases.BLOCK_CASES["pad4"]
