@@ -221,6 +221,10 @@ int b200_dev_rowdot(const double* X, int ldx, const double* Y, int ldy, int m, i
  * UC = 1 + (E - 2D)/C; kappa map filled with the scalar. */
 int b200_dev_single_kappa_maps(const double* D, const double* N, const double* E, int m, double kappa, double C,
                                double* kappa_out, double* Sigma_out, double* UC_out, void* stream);
+/* EmpirKernel._call_single_kappa (lakernel.py:761-768): Ti[a, i] = max(rho_acc - hypot(dy, dx), 0), each row divided by
+ * its sum; T (mpad, ldt) with rows m.. and columns n..npad-1 zero-filled. */
+int b200_dev_empir_T(const double* inx, const double* iny, const double* outx, const double* outy, int m, int mpad, int n,
+                     int npad, double rho_acc, double* T, int ldt, void* stream);
 /* out[a] = scale * in[a] (kappa = out_kappa * C, lakernel.py:390, and the Eigen quirk lakernel.py:222) */
 int b200_dev_scale(const double* in, double scale, int m, double* out, void* stream);
 

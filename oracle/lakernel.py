@@ -246,3 +246,34 @@ class IterKernel(_Kernel):
             self._reduce_nodes(j, Tpi, kappa_arr, Cv[j], Epq)
             self.f64[j]["niter"] = nits
             self.f64[j]["relevant"] = rel
+
+
+class EmpirKernel(_Kernel):
+    """lakernel.py:747-805: no linear system -- T from the empirical weight max(rho_acc - distance, 0), row-normalised;
+    U/C from the exact quadratic form E = T A T^T (skipped with no_qlt_ctrl)."""
+
+    def _single(self):
+        o = self.outst
+        cfg = o.blk.cfg
+        dy = o.yx_val[0].ravel()[:, None] - o.iny_val[None, :]
+        dx = o.yx_val[1].ravel()[:, None] - o.inx_val[None, :]
+        Ti = np.maximum(rho_acc(cfg) - np.hypot(dy, dx), 0)
+        Ti /= np.sum(Ti, axis=-1)[:, None]
+        if getattr(o, "no_qlt_ctrl", False):
+            o.T[:, :, :] = Ti
+            for j in range(self.n_out):
+                self.f64[j] = dict(Ti=Ti)
+            return
+        A, mB, Cv = o.sysmata, o.mhalfb, o.outovlc
+        for j in range(self.n_out):
+            kap = self.kappaC_arr[0] * Cv[j]
+            D = np.einsum("ai,ai->a", mB[j], Ti)
+            N = np.einsum("ai,ai->a", Ti, Ti)
+            E = np.einsum("ij,ai,aj->a", A, Ti, Ti)
+            self.kappa_[j] = kap
+            self.Sigma_[j] = N
+            self.UC_[j] = 1.0 + (E - 2 * D) / Cv[j]
+            o.T[j] = Ti
+            self.f64[j] = dict(Ti=Ti, D=D, N=N, E=E, kappa=np.full(self.m, kap), Sigma=N, UC=1.0 + (E - 2 * D) / Cv[j])
+
+    _multi = _single  # lakernel.py:801-805

@@ -113,6 +113,7 @@ PROTOTYPES = {
     "b200_dev_node_stats": [vp, i32, vp, i32, szt, i32, i32, i32, C.POINTER(f64), f64, vp, vp, vp, vp, vp, vp, vp],
     "b200_dev_rowdot": [vp, i32, vp, i32, i32, i32, vp, i32, vp],
     "b200_dev_single_kappa_maps": [vp, vp, vp, i32, f64, f64, vp, vp, vp, vp],
+    "b200_dev_empir_T": [vp, vp, vp, vp, i32, i32, i32, i32, f64, vp, i32, vp],
     "b200_dev_scale": [vp, f64, i32, vp, vp],
     "b200_dev_iter_cg": [vp, i32, f64, vp, i32, i32, i32, vp, vp, vp, vp, f64, f64, i32, vp, i32, vp, vp, vp],
     "b200_dev_finalize": [C.POINTER(FinalizeArgs), vp],

@@ -135,7 +135,7 @@ class GpuBlock:
         self.cfg = blk.cfg
         self.kernel = kernel or self.cfg.linear_algebra
         if self.kernel not in SOLVERS:
-            raise ValueError(f"unsupported LAKERNEL {self.kernel!r} (Cholesky, Eigen, Iterative)")
+            raise ValueError(f"unsupported LAKERNEL {self.kernel!r} (Cholesky, Eigen, Iterative, Empirical)")
         self.plans = {}
         self.order = []
         self._uploaded = False
@@ -526,7 +526,7 @@ class GpuBlock:
                          mB.stride(1), mB.stride(0), st)
         ds = DeviceSystem(n=n, m=m, n2f=cfg.n2f, A=A, mB=mB, C=np.asarray(self.tab.outovlc, dtype=np.float64),
                           px=px, py=py, assemble=assemble)
-        if self.kernel == "Iterative":
+        if self.kernel in ("Iterative", "Empirical"):
             g = torch.arange(cfg.n2f, dtype=torch.float64, device="cuda")
             ds.outy = (p.y0out + g).repeat_interleave(cfg.n2f).contiguous()
             ds.outx = (p.x0out + g).repeat(cfg.n2f).contiguous()

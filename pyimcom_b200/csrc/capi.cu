@@ -390,6 +390,10 @@ int b200_dev_single_kappa_maps(const double* D, const double* N, const double* E
                                double* kappa_out, double* Sigma_out, double* UC_out, void* s) {
     return launch_single_kappa_maps(D, N, E, m, kappa, C, kappa_out, Sigma_out, UC_out, ST(s));
 }
+int b200_dev_empir_T(const double* inx, const double* iny, const double* outx, const double* outy, int m, int mpad, int n,
+                     int npad, double rho_acc, double* T, int ldt, void* s) {
+    return launch_empir_T(inx, iny, outx, outy, m, mpad, n, npad, rho_acc, T, ldt, ST(s));
+}
 int b200_dev_scale(const double* in, double scale, int m, double* out, void* s) {
     return launch_scale(in, scale, m, out, ST(s));
 }

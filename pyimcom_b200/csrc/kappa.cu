@@ -95,6 +95,28 @@ __global__ void __launch_bounds__(KT_THREADS) k_eigen_single(const double* __res
     }
 }
 
+// ---- EmpirKernel (lakernel.py:747-805): Ti[a, i] = max(rho - hypot(dy, dx), 0) / sum_i(...) -----------------------
+// One CTA per output pixel; the row is formed twice (sum, then normalised store) so nothing is staged.  The sum runs
+// over i in ascending order per thread and a fixed tree across threads (np.sum is pairwise: both are deterministic
+// float64 sums of non-negative terms, equal to a few ulp).  Columns n .. ldt-1 are zero-filled (solver padding).
+__global__ void __launch_bounds__(KT_THREADS) k_empir_T(const double* __restrict__ inx, const double* __restrict__ iny,
+                                                        const double* __restrict__ outx, const double* __restrict__ outy,
+                                                        int m, int n, int npad, double rho, double* __restrict__ T, int ldt) {
+    __shared__ double red[40];
+    const int a = blockIdx.x;
+    double* Trow = T + (size_t)a * ldt;
+    if (a >= m) {
+        for (int i = threadIdx.x; i < npad; i += blockDim.x) Trow[i] = 0.0;
+        return;
+    }
+    const double yo = outy[a], xo = outx[a];
+    double s = 0.0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) s += fmax(rho - hypot(yo - iny[i], xo - inx[i]), 0.0);
+    s = block_sum(s, red);
+    for (int i = threadIdx.x; i < npad; i += blockDim.x)
+        Trow[i] = i < n ? fmax(rho - hypot(yo - iny[i], xo - inx[i]), 0.0) / s : 0.0;
+}
+
 // ---- lsolve_sps: unblocked in-place lower Cholesky + two substitutions (destroys A) -----------------
 // Device helper used per thread for the tiny nv x nv systems of build_reduced_T.
 __device__ __forceinline__ void lsolve_small(int N, double* A, double* x, const double* b, double* p1) {
@@ -304,6 +326,14 @@ int launch_single_kappa_maps(const double* D, const double* N, const double* E, 
                              double* kappa_out, double* Sigma_out, double* UC_out, cudaStream_t s) {
     if (m <= 0) return 0;
     k_single_kappa_maps<<<(m + 255) / 256, 256, 0, s>>>(D, N, E, m, kappa, C, kappa_out, Sigma_out, UC_out);
+    B200_LAUNCH_CHECK();
+    return 0;
+}
+
+int launch_empir_T(const double* inx, const double* iny, const double* outx, const double* outy, int m, int mpad, int n,
+                   int npad, double rho, double* T, int ldt, cudaStream_t s) {
+    if (mpad <= 0 || npad <= 0) return 0;
+    k_empir_T<<<mpad, KT_THREADS, 0, s>>>(inx, iny, outx, outy, m, n, npad, rho, T, ldt);
     B200_LAUNCH_CHECK();
     return 0;
 }

@@ -81,6 +81,8 @@ int launch_rowdot(const double* X, int ldx, const double* Y, int ldy, int m, int
 
 int launch_single_kappa_maps(const double* D, const double* N, const double* E, int m, double kappa, double C,
                              double* kappa_out, double* Sigma_out, double* UC_out, cudaStream_t s);
+int launch_empir_T(const double* inx, const double* iny, const double* outx, const double* outy, int m, int mpad, int n,
+                   int npad, double rho, double* T, int ldt, cudaStream_t s);
 int launch_scale(const double* in, double scale, int m, double* out, cudaStream_t s);
 
 // iter.cu

@@ -463,7 +463,27 @@ def solve_iter(ds: DeviceSystem, cfg, j_out: int, exact_UC=None) -> KernelOutput
     return out
 
 
-SOLVERS = {"Cholesky": solve_chol, "Eigen": solve_eigen, "Iterative": solve_iter}
+def solve_empir(ds: DeviceSystem, cfg, j_out: int, no_qlt_ctrl: bool = False) -> KernelOutput:
+    """EmpirKernel for one output PSF (lakernel.py:747-805): no linear system; U/C from the exact E = T A T^T."""
+    assert ds.px is not None and ds.outx is not None, "EmpirKernel needs the pixel positions"
+    st = stream_handle()
+    m, n, mpad, npad = ds.m, ds.n, ds.mpad, ds.npad
+    T = _f64(mpad, npad)
+    _lib.dev_empir_T(ptr(ds.px), ptr(ds.py), ptr(ds.outx), ptr(ds.outy), m, mpad, n, npad, float(rho_acc(cfg)), ptr(T),
+                     T.stride(0), st)
+    if no_qlt_ctrl:  # the reference leaves kappa, Sigma, U/C at their zero initialisation (lakernel.py:770-774)
+        z = _zeros64(m)
+        return KernelOutput(Tpi=T.unsqueeze(0), w=None, kappa=z, Sigma=z.clone(), UC=z.clone())
+    A = ds.matrix()
+    AT = _f64(mpad, npad)  # T @ A (A symmetric: the NT product with A's rows)
+    _lib.dev_gemm_nt(ptr(T), T.stride(0), ptr(A), A.stride(0), ptr(AT), AT.stride(0), mpad, npad, npad, 0, st)
+    E = _f64(m)
+    _lib.dev_rowdot(ptr(AT), AT.stride(0), ptr(T), T.stride(0), m, n, ptr(E), 1, st)
+    kap = float(np.asarray(cfg.kappaC_arr, dtype=np.float64)[0] * float(ds.C[j_out]))
+    return KernelOutput(Tpi=T.unsqueeze(0), w=None, kappa_scalar=kap, E=E)
+
+
+SOLVERS = {"Cholesky": solve_chol, "Eigen": solve_eigen, "Iterative": solve_iter, "Empirical": solve_empir}
 
 
 # ------------------------------------------------------------------------------------------------------
@@ -643,6 +663,27 @@ class EigenKernel(_LAKernel):
         if self._eig is None:  # one decomposition serves every output PSF (lakernel.py:162, 201)
             self._eig = eigen_decompose(ds)
         return solve_eigen(ds, self.outst.blk.cfg, j_out, eig=self._eig)
+
+
+class EmpirKernel(_LAKernel):
+    """lakernel.py:747-805: empirical weights instead of a solve (fast approximation)."""
+
+    KIND = "Empirical"
+
+    def _device_system(self) -> DeviceSystem:
+        o = self.outst
+        if getattr(o, "no_qlt_ctrl", False):  # no system matrices exist in this mode (coadd.py:1020-1025)
+            n, m = self.n, self.m
+            A = np.eye(n)
+            mB = np.zeros((self.n_out, m, n))
+            Cv = np.ones(self.n_out)
+        else:
+            A, mB, Cv = o.sysmata, o.mhalfb, o.outovlc
+        return upload_system(A, mB, Cv, self.n2f, px=o.inx_val, py=o.iny_val, outx=np.asarray(o.yx_val[1]),
+                             outy=np.asarray(o.yx_val[0]))
+
+    def _solve(self, ds, j_out):
+        return solve_empir(ds, self.outst.blk.cfg, j_out, no_qlt_ctrl=bool(getattr(self.outst, "no_qlt_ctrl", False)))
 
 
 class IterKernel(_LAKernel):

@@ -140,6 +140,9 @@ BLOCK_CASES = {
     # 4x4 block with padding so that interior stamps have full 3x3 neighbourhoods and four PSF groups
     "pad4": dict(cfg=dict(_MINI, n1=2, postage_pad=1, n_inframe=2), n_image=3, seed=6, kernel="Cholesky",
                  kappaC=[5e-4], stamps=[(2, 2), (3, 2)], store_ab=True),
+    # EmpirKernel (lakernel.py:747-805): empirical weights, exact U/C
+    "empir": dict(cfg=dict(_MINI, n1=2, postage_pad=1, n_inframe=2, instamp_pad_arcsec=0.25), n_image=3, seed=8,
+                  kernel="Empirical", kappaC=[5e-4], stamps=[(2, 2), (3, 3)]),
     # truncated PSF support (npixpsf=12) makes A + kappa*I indefinite -> the eigen-shift repair branch
     # of CholKernel._cholesky_wrapper (lakernel.py:262-279) fires in the reference
     "repair": dict(cfg=dict(_MINI, n1=2, postage_pad=1, n_inframe=2, npixpsf=12), n_image=3, seed=6, kernel="Cholesky",

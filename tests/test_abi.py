@@ -65,7 +65,7 @@ def test_seams_expose_reference_names():
         assert callable(getattr(pc, name))
     from pyimcom_b200 import lakernel as lk
 
-    for name in ("CholKernel", "EigenKernel", "IterKernel"):  # coadd.py:839-844
+    for name in ("CholKernel", "EigenKernel", "IterKernel", "EmpirKernel"):  # coadd.py:839-844
         cls = getattr(lk, name)
         assert callable(cls) and hasattr(cls, "__call__")
 

@@ -291,7 +291,7 @@ def test_incr_repair():
 # ---------------------------------------------------------------------------------------------------
 # whole OutStamp path on the seeded synthetic blocks
 # ---------------------------------------------------------------------------------------------------
-KERN = {"Cholesky": OL.CholKernel, "Eigen": OL.EigenKernel, "Iterative": OL.IterKernel}
+KERN = {"Cholesky": OL.CholKernel, "Eigen": OL.EigenKernel, "Iterative": OL.IterKernel, "Empirical": OL.EmpirKernel}
 
 
 @pytest.mark.parametrize("name", list(cases.BLOCK_CASES))

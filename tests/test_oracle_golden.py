@@ -128,7 +128,7 @@ def test_la_vs_reference(name, golden_dir):
             assert (UC[j] < 1e-4 and 2e-3 < kap[j] < 4e-3) if j % 5 == 0 else (0.05 < UC[j] < 0.2 and 2e-4 < kap[j] < 4e-4)
 
 
-KERN = {"Cholesky": OL.CholKernel, "Eigen": OL.EigenKernel, "Iterative": OL.IterKernel}
+KERN = {"Cholesky": OL.CholKernel, "Eigen": OL.EigenKernel, "Iterative": OL.IterKernel, "Empirical": OL.EmpirKernel}
 
 
 @pytest.mark.parametrize("name", list(cases.BLOCK_CASES))
