@@ -28,6 +28,12 @@ import sys
 import threading
 import time
 
+if "reference" in sys.argv[1:]:
+    # torchrun exports OMP_NUM_THREADS=1 to every rank; the CPU arm is meant to use all host cores (BLAS included), and
+    # the thread pools read the variable when numpy / scipy are first imported
+    for _v in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+        os.environ[_v] = str(os.cpu_count() or 1)
+
 import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))

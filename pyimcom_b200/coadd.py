@@ -21,6 +21,7 @@ here every stamp's A and mBhalf are assembled directly from positions and tables
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import numpy as np
 import torch
@@ -638,7 +639,7 @@ class GpuBlock:
         free = hbm_free_estimate()
         return int(max(1, min(0.5 * free // per, self.max_batch)))
 
-    max_batch = 16
+    max_batch = int(os.environ.get("B200_MAX_BATCH", "16"))
 
     def run(self, batch: int | None = None):
         """coadd_output_stamps(sim_mode=False) (coadd.py:2056-2069): every planned stamp, in batches of
