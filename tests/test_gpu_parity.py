@@ -437,3 +437,25 @@ def test_block_run_maps():
         UC[:, b:b + cfg.n2f, l:l + cfg.n2f] += o.UC
     assert rel(maps["out_map"], out) < 5e-6
     assert rel(maps["UC_map"], UC) < 5e-6
+
+
+def test_pipelined_batches_equal_single_batch():
+    """GpuBlock.run(): four pipelined batches of 4 stamps (stage (a) of batch k+1 and the T-apply of batch k overlap the
+    factorisation) give bit-identical block maps to one batch of 16, with and without the concurrent solve streams."""
+    spec = cases.BLOCK_CASES["pad4"]
+    blk = cases.make_block(spec)
+    tab = PSFTables(blk, G.iD5512C, G.gridD5512C)
+    ref = GpuBlock(blk, tab).prepare()
+    ref.run(batch=16)
+    want = ref.download()
+    for streams in (3, 1):
+        old = GL.SOLVE_STREAMS
+        GL.SOLVE_STREAMS = streams
+        try:
+            gb = GpuBlock(blk, tab).prepare()
+            gb.run(batch=4)
+            got = gb.download()
+        finally:
+            GL.SOLVE_STREAMS = old
+        for k in want:
+            assert np.array_equal(got[k], want[k]), (k, streams)
