@@ -10,7 +10,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "lib", "libpyimcom_b200.so")
+LIB_PATH = os.environ.get("B200_LIB") or os.path.join(HERE, "lib", "libpyimcom_b200.so")  # B200_LIB: A/B builds
 
 
 class B200Error(RuntimeError):
