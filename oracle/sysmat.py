@@ -25,8 +25,11 @@ def anchor(ji):
 
 
 class OracleOutStamp:
-    def __init__(self, blk, tables, j_st, i_st):
+    def __init__(self, blk, tables, j_st, i_st, ii_cache=None):
+        """ii_cache: optional dict shared by the OutStamps of a block -- the reference's SysMatA cache of InStamp-pair
+        blocks (psfutil.py:1764-2092), so that a timed CPU run does not redo what the reference would reuse."""
         self.blk, self.tab, self.j_st, self.i_st = blk, tables, j_st, i_st
+        self.ii_cache = ii_cache
         cfg = blk.cfg
         self.ji_st_in_s = [(j_st + dj, i_st + di) for dj in range(-1, 2) for di in range(-1, 2)]
         self.bottom = (j_st - 1) * cfg.n2
@@ -55,6 +58,14 @@ class OracleOutStamp:
 
     # ---- psfutil.py:1401-1495 + 1597-1732: one InStamp-pair block of A ----
     def _ii_block(self, st1, st2):
+        if self.ii_cache is not None:
+            key = (st1.j_st, st1.i_st, st2.j_st, st2.i_st)
+            if key not in self.ii_cache:
+                self.ii_cache[key] = self._ii_block_compute(st1, st2)
+            return self.ii_cache[key]
+        return self._ii_block_compute(st1, st2)
+
+    def _ii_block_compute(self, st1, st2):
         cfg, tab = self.blk.cfg, self.tab
         same = st1 is st2
         G1, G2 = anchor((st1.j_st, st1.i_st)), anchor((st2.j_st, st2.i_st))

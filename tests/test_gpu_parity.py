@@ -459,3 +459,17 @@ def test_pipelined_batches_equal_single_batch():
             GL.SOLVE_STREAMS = old
         for k in want:
             assert np.array_equal(got[k], want[k]), (k, streams)
+
+
+@pytest.mark.parametrize("kern", ["CholKernel", "EigenKernel", "IterKernel", "EmpirKernel"])
+def test_kernel_without_input_pixels(kern):
+    """lakernel.py:110-119: a postage stamp with no input pixels gives an empty T, U/C = kappa = 1, Sigma = 0."""
+    outst = cases.la_outst([1e-2], iterative=True)
+    outst.inpix_cumsum = np.array([0])
+    outst.sysmata = np.zeros((0, 0))
+    outst.mhalfb = np.zeros((1, 16, 0))
+    outst.iny_val = outst.inx_val = np.zeros(0)
+    getattr(GL, kern)(outst)()
+    assert outst.T.shape == (1, 16, 0) and outst.T.dtype == np.float32
+    assert np.all(outst.UC == 1) and np.all(outst.kappa == 1) and np.all(outst.Sigma == 0)
+    assert outst.UC.shape == (1, 4, 4) and outst.UC.dtype == np.float32

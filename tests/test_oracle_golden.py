@@ -167,3 +167,18 @@ def test_block_vs_reference(name, golden_dir):
             # sums over ~n entries of an rtol-accurate T carry a few times its error
             assert rel(getattr(o, nm), g[tag + nm]) < (tol if nm == "T" or tol < 1e-3 else 5 * tol), nm
         assert np.abs(o.UC - g[tag + "UC"]).max() < tol * max(1.0, np.abs(g[tag + "UC"]).max())
+
+
+def test_oracle_ii_cache_is_transparent():
+    """The SysMatA-style block cache the timed CPU arm uses (bench.py) changes nothing in the matrices."""
+    spec = cases.BLOCK_CASES["pad4"]
+    blk = cases.make_block(spec)
+    tab = PSFTables(blk, R.iD5512C, R.gridD5512C)
+    cache = {}
+    for (j, i) in [(2, 2), (2, 3), (3, 2)]:
+        a = OracleOutStamp(blk, tab, j, i)
+        a.build_system_matrices()
+        b = OracleOutStamp(blk, tab, j, i, ii_cache=cache)
+        b.build_system_matrices()
+        assert np.array_equal(a.sysmata, b.sysmata) and np.array_equal(a.mhalfb, b.mhalfb)
+    assert len(cache) < 3 * 45  # neighbouring stamps share blocks
