@@ -349,25 +349,24 @@ __global__ void __launch_bounds__(256, 3) k_pair_blocks(const double* __restrict
     const int bi = t / ntj, bj = t - bi * ntj;
     if (d.same && bj < bi) return;  // self block: upper tiles only, mirrored below
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-    const int j = bj * 32 + tx;
-    double xj = 0, yj = 0;
-    int cj = 0;
-    if (j < d.nB) {
-        xj = gx[d.offB + j];
-        yj = gy[d.offB + j];
-        cj = gimg[d.offB + j];
-    }
+    // A warp covers a 4 x 8 patch of the tile (4 consecutive pixels i, 8 consecutive pixels j), not one row of 32:
+    // consecutive pixels of one image row are P table samples apart, so entry (i+1, j+1) reads (almost) the window of
+    // entry (i, j) -- the Toeplitz structure of the block -- and the 32 lanes of a load touch ~11 neighbouring doubles
+    // of one polyphase plane (1-2 cache lines) instead of 32 doubles spread over the 3-4 image rows a 32-pixel run spans.
+    const int pli = tx >> 3, plj = tx & 7;
     double* blk = pool + d.out;
     const TableRef* plut = lut + (size_t)d.lut * nimg * nimg;
 #pragma unroll
     for (int r = 0; r < 4; r++) {
-        const int li = ty + 8 * r;
-        const int i = bi * 32 + li;
+        const int sub = ty + 8 * r;             // 32 patches per tile: 8 patch rows x 4 patch columns
+        const int li = 4 * (sub >> 2) + pli;    // local row 0..31
+        const int lj = 8 * (sub & 3) + plj;     // local column 0..31
+        const int i = bi * 32 + li, j = bj * 32 + lj;
         double v = 0.0;
         if (i < d.nA && j < d.nB && (!d.same || i <= j)) {
-            const int ci = gimg[d.offA + i];
-            const double x = __dadd_rn(__dadd_rn(__ddiv_rn(__dadd_rn(gx[d.offA + i], -xj), dscale), nc), 6.0);
-            const double y = __dadd_rn(__dadd_rn(__ddiv_rn(__dadd_rn(gy[d.offA + i], -yj), dscale), nc), 6.0);
+            const int ci = gimg[d.offA + i], cj = gimg[d.offB + j];
+            const double x = __dadd_rn(__dadd_rn(__ddiv_rn(__dadd_rn(gx[d.offA + i], -gx[d.offB + j]), dscale), nc), 6.0);
+            const double y = __dadd_rn(__dadd_rn(__ddiv_rn(__dadd_rn(gy[d.offA + i], -gy[d.offB + j]), dscale), nc), 6.0);
             const TableRef tr = plut[ci * nimg + cj];
             const int xi = (int)x, yi = (int)y;
             if (tr.offset >= 0 && d5512_on_grid(xi, ngrid) && d5512_on_grid(yi, ngrid)) {
@@ -387,7 +386,7 @@ __global__ void __launch_bounds__(256, 3) k_pair_blocks(const double* __restrict
             }
             blk[(size_t)i * d.ld + j] = v;
         }
-        tile[li][tx] = v;
+        tile[li][lj] = v;
     }
     if (!d.same) return;
     __syncthreads();
