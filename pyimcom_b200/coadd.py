@@ -119,6 +119,12 @@ def hbm_free_estimate() -> int:
     return max(0, int(0.92 * _TOTAL_HBM[dev]) - torch.cuda.memory_allocated(dev))
 
 
+def release_parked_pools() -> None:
+    """Give the parked pair-block pools (at most two per device) back to the allocator."""
+    for parked in _PARKED_POOLS.values():
+        parked.clear()
+
+
 class StampPlan:
     """Host-side description of one OutStamp (what OutStamp.__init__ / _process_input_stamps derive)."""
 

@@ -448,17 +448,20 @@ def test_pipelined_batches_equal_single_batch():
     ref = GpuBlock(blk, tab).prepare()
     ref.run(batch=16)
     want = ref.download()
-    for streams in (3, 1):
+    for streams, tiny_pool in ((3, False), (1, False), (3, True)):
         old = GL.SOLVE_STREAMS
         GL.SOLVE_STREAMS = streams
         try:
-            gb = GpuBlock(blk, tab).prepare()
+            gb = GpuBlock(blk, tab)
+            if tiny_pool:
+                gb.pool_bytes = 8  # every batch evicts the pair-block cache while the previous batch is still in flight
+            gb.prepare()
             gb.run(batch=4)
             got = gb.download()
         finally:
             GL.SOLVE_STREAMS = old
         for k in want:
-            assert np.array_equal(got[k], want[k]), (k, streams)
+            assert np.array_equal(got[k], want[k]), (k, streams, tiny_pool)
 
 
 @pytest.mark.parametrize("kern", ["CholKernel", "EigenKernel", "IterKernel", "EmpirKernel"])
