@@ -170,6 +170,9 @@ typedef struct b200_solve_sys {
     double* Dinv; /* (2*npad/128, 128, 128) workspace: inverses of the diagonal blocks of L and their transposes */
     int* info;    /* device int, LAPACK dpotrf convention: 0 or 1 + index of the first non-positive pivot */
     int npad, mpad, ldw, ldx;
+    int mrows;    /* number of real rows of X (rows mrows..mpad-1 are zero padding and stay zero); 0 = treat all as real.
+                     A last row-tile with at most 64 real rows is solved at half cost. */
+    int pad_;
 } b200_solve_sys;
 
 /* scipy.linalg.cholesky + cho_solve (lakernel.py:263, 276, 304, 358) for up to B200_MAXB systems at once. */

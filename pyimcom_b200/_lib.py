@@ -45,7 +45,7 @@ class SolveSys(C.Structure):
     """b200_solve_sys"""
 
     _fields_ = [("W", vp), ("X", vp), ("Dinv", vp), ("info", vp), ("npad", i32), ("mpad", i32), ("ldw", i32),
-                ("ldx", i32)]
+                ("ldx", i32), ("mrows", i32), ("pad_", i32)]
 
 
 class PairDesc(C.Structure):

@@ -37,7 +37,7 @@ constexpr int STAGES = 3;
 #endif
 constexpr int WARPS_M = B200_GEMM_WARPS_M, WARPS_N = 4;  // warp grid over the 128x128 tile
 constexpr int GT = 32 * WARPS_M * WARPS_N;               // threads per GEMM CTA
-constexpr int MI = NB / WARPS_M / 8, NI = NB / WARPS_N / 8;  // m8n8 fragments per warp tile
+constexpr int NI = NB / WARPS_N / 8;  // n8 fragments per warp tile (m8 fragments: 8 for a full tile, 4 for a half tile)
 constexpr int SP = 4;            // block columns per super-panel (512 matrix columns)
 constexpr int STAGE_DOUBLES = 2 * NB * LDSM;
 constexpr size_t GEMM_SMEM = (size_t)STAGES * STAGE_DOUBLES * sizeof(double);  // 163840 B
@@ -49,13 +49,18 @@ enum TileMode { TILE_ASSIGN = 0, TILE_SUB = 1, TILE_ADD = 2 };
 //   TILE_SUB   : C = C - A B^T   (accumulators start at -C, result is the negated accumulator)
 //   TILE_ADD   : C = C + A B^T
 // Ct != nullptr additionally stores the tile transposed: Ct[c * ldct + r] = C[r][c].
-template <int MODE>
+// HALF: only rows 0..63 of the tile exist as work (the last row-tile of the right-hand sides when m mod 128 <= 64: rows
+// 64..127 are zero padding and stay zero); the eight warps then share a 64 x 128 tile (warp tile 32 x 32) and the A
+// operand is staged for 64 rows only, so the tile costs half the tensor instructions instead of idling half the warps.
+template <int MODE, bool HALF = false>
 __device__ __forceinline__ void gemm_tile_nt(const double* A, int lda, const double* B,
                                              int ldb, double* C, int ldc, int K, double* Ct, int ldct,
                                              double* smem) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int wm = warp / WARPS_N, wn = warp % WARPS_N;  // warp tile (8 MI) x (8 NI)
     const int g = lane >> 2, q = lane & 3;
+    constexpr int TM = HALF ? NB / 2 : NB;
+    constexpr int MI = TM / WARPS_M / 8;
     constexpr int WTM = 8 * MI, WTN = 8 * NI;
 
     double acc[MI][NI][2];
@@ -77,7 +82,7 @@ __device__ __forceinline__ void gemm_tile_nt(const double* A, int lda, const dou
             const int c = tid + GT * r;
             const int row = c / (KT / 2), kc = (c % (KT / 2)) * 2;
             if (k0 + kc < K) {
-                cp_async16(As + row * LDSM + kc, A + (size_t)row * lda + k0 + kc);
+                if (!HALF || row < TM) cp_async16(As + row * LDSM + kc, A + (size_t)row * lda + k0 + kc);
                 cp_async16(Bs + row * LDSM + kc, B + (size_t)row * ldb + k0 + kc);
             } else {  // K tail of the last stage (K is even): zero operands contribute nothing
                 *reinterpret_cast<double2*>(As + row * LDSM + kc) = make_double2(0.0, 0.0);
@@ -148,6 +153,11 @@ __global__ void __launch_bounds__(GT, 1) k_gemm_nt(const double* __restrict__ A,
                        C + (size_t)tm * NB * ldc + (size_t)tn * NB, ldc, K, nullptr, 0, smem);
 }
 
+// Row-tile r of the right-hand sides holds at most 64 real rows (mrows = number of real rows; 0 = unknown: all tiles full).
+__device__ __forceinline__ bool x_half_tile(const SolveSys& s, int r) {
+    return s.mrows > 0 && s.mrows - r * NB <= NB / 2;
+}
+
 // ---- factorisation phases ----------------------------------------------------------------------
 // The driver works on SUPER-PANELS of SP block columns [c0, c1): left-looking between super-panels (one
 // long-K GEMM launch brings the whole super-panel up to date: every output tile is read and written once
@@ -170,8 +180,12 @@ __global__ void __launch_bounds__(GT, 1) k_chol_super_update(SolveBatch bt, int 
                                s.W + (size_t)i * NB * s.ldw + (size_t)j * NB, s.ldw, K, nullptr, 0, smem);
     } else {
         const int r = t - nrow;
-        gemm_tile_nt<TILE_SUB>(s.X + (size_t)r * NB * s.ldx, s.ldx, Bp, s.ldw,
-                               s.X + (size_t)r * NB * s.ldx + (size_t)j * NB, s.ldx, K, nullptr, 0, smem);
+        if (x_half_tile(s, r))
+            gemm_tile_nt<TILE_SUB, true>(s.X + (size_t)r * NB * s.ldx, s.ldx, Bp, s.ldw,
+                                         s.X + (size_t)r * NB * s.ldx + (size_t)j * NB, s.ldx, K, nullptr, 0, smem);
+        else
+            gemm_tile_nt<TILE_SUB>(s.X + (size_t)r * NB * s.ldx, s.ldx, Bp, s.ldw,
+                                   s.X + (size_t)r * NB * s.ldx + (size_t)j * NB, s.ldx, K, nullptr, 0, smem);
     }
 }
 
@@ -192,7 +206,10 @@ __global__ void __launch_bounds__(GT, 1) k_chol_panel(SolveBatch bt, int k) {
                                   s.ldw, smem);
     } else {
         double* Cp = s.X + (size_t)(t - nrow) * NB * s.ldx + (size_t)k * NB;
-        gemm_tile_nt<TILE_ASSIGN>(Cp, s.ldx, Dk, NB, Cp, s.ldx, NB, nullptr, 0, smem);
+        if (x_half_tile(s, t - nrow))
+            gemm_tile_nt<TILE_ASSIGN, true>(Cp, s.ldx, Dk, NB, Cp, s.ldx, NB, nullptr, 0, smem);
+        else
+            gemm_tile_nt<TILE_ASSIGN>(Cp, s.ldx, Dk, NB, Cp, s.ldx, NB, nullptr, 0, smem);
     }
 }
 
@@ -214,8 +231,12 @@ __global__ void __launch_bounds__(GT, 1) k_chol_update(SolveBatch bt, int k, int
                                s.W + (size_t)i * NB * s.ldw + (size_t)j * NB, s.ldw, NB, nullptr, 0, smem);
     } else {
         const int r = t - nrow;
-        gemm_tile_nt<TILE_SUB>(s.X + (size_t)r * NB * s.ldx + (size_t)k * NB, s.ldx, Bp, s.ldw,
-                               s.X + (size_t)r * NB * s.ldx + (size_t)j * NB, s.ldx, NB, nullptr, 0, smem);
+        if (x_half_tile(s, r))
+            gemm_tile_nt<TILE_SUB, true>(s.X + (size_t)r * NB * s.ldx + (size_t)k * NB, s.ldx, Bp, s.ldw,
+                                         s.X + (size_t)r * NB * s.ldx + (size_t)j * NB, s.ldx, NB, nullptr, 0, smem);
+        else
+            gemm_tile_nt<TILE_SUB>(s.X + (size_t)r * NB * s.ldx + (size_t)k * NB, s.ldx, Bp, s.ldw,
+                                   s.X + (size_t)r * NB * s.ldx + (size_t)j * NB, s.ldx, NB, nullptr, 0, smem);
     }
 }
 
@@ -229,9 +250,14 @@ __global__ void __launch_bounds__(GT, 1) k_back_super_update(SolveBatch bt, int 
     const int hi = nb - e0;
     const int j = hi - 1 - (int)blockIdx.x, t = blockIdx.y;
     if (hi <= 0 || j < 0 || j < nb - e1 || t >= mb) return;
-    gemm_tile_nt<TILE_SUB>(s.X + (size_t)t * NB * s.ldx + (size_t)hi * NB, s.ldx,
-                           s.W + (size_t)j * NB * s.ldw + (size_t)hi * NB, s.ldw,
-                           s.X + (size_t)t * NB * s.ldx + (size_t)j * NB, s.ldx, e0 * NB, nullptr, 0, smem);
+    if (x_half_tile(s, t))
+        gemm_tile_nt<TILE_SUB, true>(s.X + (size_t)t * NB * s.ldx + (size_t)hi * NB, s.ldx,
+                                     s.W + (size_t)j * NB * s.ldw + (size_t)hi * NB, s.ldw,
+                                     s.X + (size_t)t * NB * s.ldx + (size_t)j * NB, s.ldx, e0 * NB, nullptr, 0, smem);
+    else
+        gemm_tile_nt<TILE_SUB>(s.X + (size_t)t * NB * s.ldx + (size_t)hi * NB, s.ldx,
+                               s.W + (size_t)j * NB * s.ldw + (size_t)hi * NB, s.ldw,
+                               s.X + (size_t)t * NB * s.ldx + (size_t)j * NB, s.ldx, e0 * NB, nullptr, 0, smem);
 }
 
 // Backward step k, part 1:  X[t][k] = X[t][k] inv(L_kk)   (B operand = inv(L_kk)^T)
@@ -242,7 +268,10 @@ __global__ void __launch_bounds__(GT, 1) k_back_diag(SolveBatch bt, int kfromtop
     const int k = nb - 1 - kfromtop;
     if (k < 0 || (int)blockIdx.x >= mb) return;
     double* Cp = s.X + (size_t)blockIdx.x * NB * s.ldx + (size_t)k * NB;
-    gemm_tile_nt<TILE_ASSIGN>(Cp, s.ldx, s.Dinv + (size_t)(nb + k) * NB * NB, NB, Cp, s.ldx, NB, nullptr, 0, smem);
+    if (x_half_tile(s, blockIdx.x))
+        gemm_tile_nt<TILE_ASSIGN, true>(Cp, s.ldx, s.Dinv + (size_t)(nb + k) * NB * NB, NB, Cp, s.ldx, NB, nullptr, 0, smem);
+    else
+        gemm_tile_nt<TILE_ASSIGN>(Cp, s.ldx, s.Dinv + (size_t)(nb + k) * NB * NB, NB, Cp, s.ldx, NB, nullptr, 0, smem);
 }
 
 // Backward step k, part 2, inside the super-panel:  X[t][j] -= X[t][k] L[k][j]  (lo <= j < k)
@@ -253,9 +282,14 @@ __global__ void __launch_bounds__(GT, 1) k_back_update(SolveBatch bt, int kfromt
     const int k = nb - 1 - kfromtop;
     const int j = k - 1 - (int)blockIdx.x, t = blockIdx.y;
     if (k < 0 || j < 0 || j < nb - e1 || t >= mb) return;
-    gemm_tile_nt<TILE_SUB>(s.X + (size_t)t * NB * s.ldx + (size_t)k * NB, s.ldx,
-                           s.W + (size_t)j * NB * s.ldw + (size_t)k * NB, s.ldw,
-                           s.X + (size_t)t * NB * s.ldx + (size_t)j * NB, s.ldx, NB, nullptr, 0, smem);
+    if (x_half_tile(s, t))
+        gemm_tile_nt<TILE_SUB, true>(s.X + (size_t)t * NB * s.ldx + (size_t)k * NB, s.ldx,
+                                     s.W + (size_t)j * NB * s.ldw + (size_t)k * NB, s.ldw,
+                                     s.X + (size_t)t * NB * s.ldx + (size_t)j * NB, s.ldx, NB, nullptr, 0, smem);
+    else
+        gemm_tile_nt<TILE_SUB>(s.X + (size_t)t * NB * s.ldx + (size_t)k * NB, s.ldx,
+                               s.W + (size_t)j * NB * s.ldw + (size_t)k * NB, s.ldw,
+                               s.X + (size_t)t * NB * s.ldx + (size_t)j * NB, s.ldx, NB, nullptr, 0, smem);
 }
 
 // ---- 128x128 diagonal block: Cholesky in shared memory + explicit triangular inverse -------------
@@ -484,10 +518,17 @@ int launch_chol_solve(const SolveSys* h_sys, int nsys, int do_factor, int do_sol
     }
     for (int i = nsys; i < MAXB; i++) bt.s[i] = bt.s[0];
     // algorithmic flop counts of the launches (profiling only): tiles actually computed x 2*128^2*K
+    // right-hand-side row tiles of system q, a half tile (x_half_tile) counting as half the work
+    auto mb_eff = [&](int q) {
+        const int mb = bt.s[q].mpad / NB;
+        const bool half = mb > 0 && bt.s[q].mrows > 0 && bt.s[q].mrows - (mb - 1) * NB <= NB / 2;
+        return mb - (half ? 0.5 : 0.0);
+    };
     auto tiles_fwd = [&](int c0, int c1, int rows_from) {  // W tiles (j <= i) + X tiles over all systems
         double t = 0;
         for (int q = 0; q < nsys; q++) {
-            const int nb = bt.s[q].npad / NB, mb = bt.s[q].mpad / NB;
+            const int nb = bt.s[q].npad / NB;
+            const double mb = mb_eff(q);
             for (int j = c0; j < c1 && j < nb; j++) {
                 const int ifrom = rows_from > j ? rows_from : j;
                 t += (nb - ifrom > 0 ? nb - ifrom : 0) + mb;
@@ -529,7 +570,7 @@ int launch_chol_solve(const SolveSys* h_sys, int nsys, int do_factor, int do_sol
     }
     if (do_solve && mbmax > 0) {
         double mbsum = 0;
-        for (int q = 0; q < nsys; q++) mbsum += bt.s[q].mpad / NB;
+        for (int q = 0; q < nsys; q++) mbsum += mb_eff(q);
         for (int e0 = 0; e0 < nbmax; e0 += SP) {
             const int e1 = e0 + SP < nbmax ? e0 + SP : nbmax;
             if (e0 > 0) {
@@ -539,7 +580,7 @@ int launch_chol_solve(const SolveSys* h_sys, int nsys, int do_factor, int do_sol
                 for (int q = 0; q < nsys; q++) {
                     const int nb = bt.s[q].npad / NB;
                     const int hi = nb - e0, lo = nb - e1 > 0 ? nb - e1 : 0;
-                    if (hi > lo) t += (double)(hi - lo) * (bt.s[q].mpad / NB);
+                    if (hi > lo) t += (double)(hi - lo) * mb_eff(q);
                 }
                 prof_end(t * tile_flops * e0 * NB, st);
                 B200_LAUNCHED(1);

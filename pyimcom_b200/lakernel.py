@@ -129,9 +129,11 @@ def _incs(vals):
 # ------------------------------------------------------------------------------------------------------
 # Cholesky: factor + solve of up to 16 padded systems per call
 # ------------------------------------------------------------------------------------------------------
-def chol_solve_batch(Ws, Xs, factor=True, solve=True):
+def chol_solve_batch(Ws, Xs, factor=True, solve=True, mrows=None):
     """In place: W_k -> L_k (and L_k^T above the diagonal blocks), X_k -> X_k (L_k L_k^T)^-1.
 
+    mrows[k] (optional): number of real rows of X_k; the rows beyond it must be zero (they stay zero) and a last
+    128-row tile with at most 64 real rows is then solved at half cost.
     Returns the device int32 tensor of LAPACK-style info codes (0 = success)."""
     nsys = len(Ws)
     assert 0 < nsys <= _lib.MAXB
@@ -150,6 +152,7 @@ def chol_solve_batch(Ws, Xs, factor=True, solve=True):
         s.npad, s.ldw = npad, W.stride(0)
         s.mpad = X.shape[0] if X is not None else 0
         s.ldx = X.stride(0) if X is not None else npad
+        s.mrows = int(mrows[k]) if (mrows is not None and X is not None) else 0
     _lib.dev_chol_solve(sysarr, nsys, int(factor), int(solve and Xs is not None), stream_handle())
     return info, keep
 
@@ -240,7 +243,7 @@ def _chol_launch(items):
     for c0, c1, st in chunks:
         with torch.cuda.stream(st):
             Ws = [_padded_system(ds, incs) for ds, incs, _ in items[c0:c1]]
-            info, _keep = chol_solve_batch(Ws, Xs[c0:c1])
+            info, _keep = chol_solve_batch(Ws, Xs[c0:c1], mrows=[it[0].m for it in items[c0:c1]])
             if st is not cur:
                 info.record_stream(cur)
             infos.append(info)
@@ -271,7 +274,7 @@ def _chol_finish(h):
             warnings.warn(f"CholKernel: repaired negative eigenvalue {w0:19.12e}", stacklevel=3)
             W = _padded_system(ds, list(incs) + [abs(w0) + 1e-16])
             Xs[k] = ds.mB[j].clone()
-            info2, _keep2 = chol_solve_batch([W], [Xs[k]])
+            info2, _keep2 = chol_solve_batch([W], [Xs[k]], mrows=[ds.m])
             if int(info2.item()) != 0:
                 raise np.linalg.LinAlgError("Cholesky failed after the eigenvalue repair")
     return Xs
