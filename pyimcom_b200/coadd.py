@@ -574,9 +574,15 @@ class GpuBlock:
         if self.kernel == "Eigen" and live:  # one decomposition per stamp serves every output PSF; all stamps together
             for (q, k, p, ds, indata), eig in zip(live, eigen_decompose_batch([t[3] for t in live])):
                 kept[q]["_eig"] = eig
+        # CholKernel: the factorisations of every output PSF are enqueued before the first one is waited for
+        # (kappa = kappa/C * C_j differs per output PSF, so each has its own systems: lakernel.py:295-299)
+        handles = ([solve_chol_launch([t[3] for t in live], cfg, j) for j in range(cfg.n_out)]
+                   if self.kernel == "Cholesky" and live else [])
         for j_out in range(cfg.n_out):
             if self.kernel == "Cholesky":
-                kos = solve_chol_batch([t[3] for t in live], cfg, j_out) if live else []
+                kos = solve_chol_finish(handles[j_out]) if live else []
+                if live:
+                    handles[j_out] = None
             for u, (q, k, p, ds, indata) in enumerate(live):
                 if self.kernel == "Cholesky":
                     ko = kos[u]
