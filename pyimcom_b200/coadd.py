@@ -22,6 +22,7 @@ from __future__ import annotations
 
 import ctypes as C
 import os
+import weakref
 
 import numpy as np
 import torch
@@ -105,6 +106,7 @@ class _Arena:
 
 
 _TOTAL_HBM = {}
+_MESH = {}  # (na, nb) -> index grids of an (na x nb) image-pair block
 # Pair-block pools outlive the GpuBlock that used them: a fresh block takes a parked pool instead of asking the
 # allocator for another multi-GB segment (a cudaMalloc of that size was measured to stall a step by > 100 ms).
 _PARKED_POOLS = {}
@@ -132,6 +134,21 @@ class StampPlan:
                  "lut", "lut_io", "insts")
 
 
+class _Plans(dict):
+    """StampPlans by (j_st, i_st); a stamp that has not been planned yet is planned (with its chunk) on first access."""
+
+    def __init__(self, gblk):
+        super().__init__()
+        self._gblk = weakref.ref(gblk)  # no reference cycle: a dropped GpuBlock frees its HBM at once
+
+    def __missing__(self, ji):
+        g = self._gblk()
+        if g is None or ji not in g._pos:
+            raise KeyError(ji)
+        g._ensure_planned(g._pos[ji])
+        return dict.__getitem__(self, ji)
+
+
 class GpuBlock:
     """One mosaic block on one GPU."""
 
@@ -143,8 +160,9 @@ class GpuBlock:
         self.kernel = kernel or self.cfg.linear_algebra
         if self.kernel not in SOLVERS:
             raise ValueError(f"unsupported LAKERNEL {self.kernel!r} (Cholesky, Eigen, Iterative, Empirical)")
-        self.plans = {}
+        self.plans = _Plans(self)
         self.order = []
+        self._pos = {}
         self._uploaded = False
         # period of the polyphase in-in tables = native pixel pitch in table samples = oversamp (psfutil.py:610)
         self.poly = int(getattr(self.cfg, "oversamp", 0))
@@ -237,7 +255,7 @@ class GpuBlock:
         for ca, (Ga, ka) in zip(present, gk):
             if (Ga, ka) not in io_c:
                 tab.group(Ga)
-                io = tab.get_io(Ga)
+                io = tab.get_io(Ga)  # registered already when the pair-block cache is on (_register_tables)
                 io_c[(Ga, ka)] = [self.arena.offset(io, (tab.grp_index(Ga, ka), o)) for o in range(cfg.n_out)]
             lut_io[ca, :] = io_c[(Ga, ka)]
             if self.a_cache:  # the per-stamp in-in look-up table is only read by the fused kernel
@@ -253,10 +271,6 @@ class GpuBlock:
         if rows:
             lut[np.ix_(present, present)] = np.array(rows, dtype=TABLEREF_DTYPE).reshape(len(present), len(present))
         p.lut, p.lut_io = lut, lut_io
-        if self.a_cache:  # table references of every (group_a, group_b) an InStamp pair of this stamp can need
-            for ga in range(len(groups)):
-                for gb in range(len(groups)):
-                    self._pair_lut(groups[ga], groups[gb])
         return p
 
     def _pair_lut(self, Ga, Gb) -> int:
@@ -275,7 +289,9 @@ class GpuBlock:
             ia, ib = np.asarray(tab.grp_imgs[Ga], dtype=np.int64), np.asarray(tab.grp_imgs[Gb], dtype=np.int64)
             na, nb = ia.size, ib.size
             if na and nb:
-                qa, qb = np.meshgrid(np.arange(na), np.arange(nb), indexing="ij")  # positions inside the groups
+                if (na, nb) not in _MESH:
+                    _MESH[(na, nb)] = np.meshgrid(np.arange(na), np.arange(nb), indexing="ij")
+                qa, qb = _MESH[(na, nb)]  # positions inside the groups
                 if Ga == Gb:
                     base, stride = self.arena.register(tab.get_self(Ga), poly=True)
                     lo, hi = np.minimum(qa, qb), np.maximum(qa, qb)
@@ -290,17 +306,21 @@ class GpuBlock:
                     base, stride = self.arena.register(tab.get_cross(Gb, Ga), poly=True)
                     flat, flip = qb * na + qa, np.ones_like(qa, dtype=bool)
                     n_in = (na * nb) ** 0.5
-                sub = np.zeros((na, nb), dtype=TABLEREF_DTYPE)
+                full = na == nimg and nb == nimg  # every image covers both groups: fill the block in place
+                sub = arr if full else np.zeros((na, nb), dtype=TABLEREF_DTYPE)
                 sub["offset"] = base + flat * stride
                 sub["flip"] = flip
                 sub["penalty_sub"] = cfg.flat_penalty / n_in
-                arr[np.ix_(ia, ib)] = sub
+                if not full:
+                    arr[np.ix_(ia, ib)] = sub
             self._pair_lut_idx[key] = len(self._pair_lut_list)
             self._pair_lut_list.append(arr)
         return self._pair_lut_idx[key]
 
     def prepare(self, stamps=None):
-        """Plan the requested OutStamps (default: the whole block in the reference's 2x2-group order) and upload."""
+        """Register the tables of the requested OutStamps (default: the whole block in the reference's 2x2-group
+        order), upload pixels and tables, and plan the first chunk of stamps.  Later chunks are planned when they are
+        first needed; the pipelined run asks for the next chunk while the device factorises the current one."""
         import time
 
         t0 = time.perf_counter()
@@ -309,15 +329,43 @@ class GpuBlock:
         self._pair_cache, self._io_cache = {}, {}
         self._pair_lut_idx, self._pair_lut_list = {}, []
         self.order = list(stamps) if stamps is not None else list(self.blk.stamp_order())
-        self.plans = {ji: self.plan_stamp(*ji) for ji in self.order}
+        self._pos = {ji: k for k, ji in enumerate(self.order)}
+        self.plans = _Plans(self)
+        self._chunks = {}
+        if self.a_cache:
+            self._register_tables()
+        else:  # the fused A kernel's per-stamp look-up tables register their table sets while the stamps are planned
+            for ji in self.order:
+                dict.__setitem__(self.plans, ji, self.plan_stamp(*ji))
         t1 = time.perf_counter()
         self.upload()
+        if self.order:
+            self._ensure_planned(0)
         self.host_seconds = {"plan": t1 - t0, "upload_enqueue": time.perf_counter() - t1}
         return self
 
+    def _register_tables(self):
+        """Every table set the planned OutStamps can touch (in-out tables per 2x2 group, in-in tables per ordered
+        group pair of one 3x3 neighbourhood) gets its place in the arena before the arena is uploaded."""
+        tab, seen = self.tab, set()
+        for (j_st, i_st) in self.order:
+            groups = []
+            for dj in (-1, 0, 1):
+                for di in (-1, 0, 1):
+                    G = anchor((j_st + dj, i_st + di))
+                    if G not in groups:
+                        groups.append(G)
+            for G in groups:
+                if G not in seen:
+                    seen.add(G)
+                    tab.group(G)
+                    self.arena.register(tab.get_io(G))
+            for Ga in groups:
+                for Gb in groups:
+                    self._pair_lut(Ga, Gb)
+
     def upload(self):
         cfg = self.cfg
-        dev = "cuda"
         self.d_x = h2d(self.h_x)
         self.d_y = h2d(self.h_y)
         self.d_data = h2d(self.h_data)
@@ -329,25 +377,48 @@ class GpuBlock:
         self._pool = None
         self._pool_used = 0
         self.pair_points = 0  # entries interpolated so far (vs sum of n^2/2 without the cache)
-        plans = [self.plans[ji] for ji in self.order]
-        # per-stamp metadata packed into a few arrays, one H2D copy each
-        self.off_pix = np.concatenate([[0], np.cumsum([p.n for p in plans])]).astype(np.int64)
-        self.off_seg = np.concatenate([[0], np.cumsum([p.seg_end.size for p in plans])]).astype(np.int64)
-        cat = lambda arrs, dt: np.concatenate(arrs).astype(dt) if arrs else np.zeros(0, dtype=dt)  # noqa: E731
-        self.d_idx = h2d(cat([p.idx for p in plans], np.int32))
-        self.d_pcode_all = h2d(cat([p.pcode for p in plans], np.int32))
-        self.d_seg_end = h2d(cat([p.seg_end for p in plans], np.int32))
-        self.d_seg_img = h2d(cat([p.seg_img for p in plans], np.int32))
-        lut = np.stack([p.lut for p in plans]) if plans else np.zeros((0, 1, 1), dtype=TABLEREF_DTYPE)
-        self.d_lut = h2d(lut.view(np.uint8).reshape(len(plans), -1))
-        lut_io = np.stack([p.lut_io for p in plans]) if plans else np.zeros((0, 1, 1), dtype=np.int64)
-        self.d_lut_io = h2d(np.ascontiguousarray(lut_io))
         self.d_fade_w = h2d(trapezoid_weights(cfg.fade_kernel)) if cfg.fade_kernel > 0 else None
         self.h2d_bytes = self.arena.h2d_bytes + sum(
-            t.numel() * t.element_size() for t in (self.d_x, self.d_y, self.d_data, self.d_idx, self.d_pcode_all,
-                                                   self.d_seg_end, self.d_seg_img, self.d_lut, self.d_lut_io, self.d_img, self.d_pair_lut))
+            t.numel() * t.element_size() for t in (self.d_x, self.d_y, self.d_data, self.d_img, self.d_pair_lut))
         self.reset_maps()
         self._uploaded = True
+
+    plan_chunk = 16  # OutStamps planned (and their metadata uploaded) together
+
+    def _ensure_planned(self, k: int):
+        """Plan the chunk of stamps that holds position k of self.order and upload its metadata (pixel indices, table
+        codes, segment ends, in-out look-ups), packed into a few arrays with one H2D copy each."""
+        c = k // self.plan_chunk
+        if c in self._chunks:
+            return self._chunks[c]
+        ks = range(c * self.plan_chunk, min((c + 1) * self.plan_chunk, len(self.order)))
+        plans = []
+        for q in ks:
+            ji = self.order[q]
+            if not dict.__contains__(self.plans, ji):
+                dict.__setitem__(self.plans, ji, self.plan_stamp(*ji))
+            plans.append(dict.__getitem__(self.plans, ji))
+        cat = lambda arrs, dt: np.concatenate(arrs).astype(dt) if arrs else np.zeros(0, dtype=dt)  # noqa: E731
+        ch = {
+            "off_pix": np.concatenate([[0], np.cumsum([p.n for p in plans])]).astype(np.int64),
+            "off_seg": np.concatenate([[0], np.cumsum([p.seg_end.size for p in plans])]).astype(np.int64),
+            "idx": h2d(cat([p.idx for p in plans], np.int32)),
+            "pcode": h2d(cat([p.pcode for p in plans], np.int32)),
+            "seg_end": h2d(cat([p.seg_end for p in plans], np.int32)),
+            "seg_img": h2d(cat([p.seg_img for p in plans], np.int32)),
+            "lut_io": h2d(np.ascontiguousarray(np.stack([p.lut_io for p in plans]))),
+        }
+        dev = ["idx", "pcode", "seg_end", "seg_img", "lut_io"]
+        if not self.a_cache:  # the per-stamp in-in look-up table is only read by the fused kernel
+            ch["lut"] = h2d(np.stack([p.lut for p in plans]).view(np.uint8).reshape(len(plans), -1))
+            dev.append("lut")
+        self.h2d_bytes += sum(ch[nm].numel() * ch[nm].element_size() for nm in dev)
+        self._chunks[c] = ch
+        return ch
+
+    def _meta(self, k: int):
+        """(chunk, position inside the chunk) of stamp k of self.order."""
+        return self._ensure_planned(k), k % self.plan_chunk
 
     def reset_cache(self):
         """Forget every cached InStamp-pair block (a new mosaic block starts with an empty SysMatA cache)."""
@@ -463,13 +534,11 @@ class GpuBlock:
         if self.pool_bytes:
             return int(self.pool_bytes)
         seen, tot = set(), 0
-        for ji in self.order:
-            p = self.plans[ji]
-            if p.n == 0:
-                continue
+        for (j_st, i_st) in self.order:  # (stamps still unplanned count too: only the InStamp sizes are needed)
+            insts = [(j_st + dj, i_st + di) for dj in (-1, 0, 1) for di in (-1, 0, 1)]
             for a in range(9):
                 for b in range(a, 9):
-                    key = (p.insts[a], p.insts[b])
+                    key = (insts[a], insts[b])
                     if key not in seen:
                         seen.add(key)
                         tot += self._inst_count(key[0]) * ((self._inst_count(key[1]) + 3) // 4 * 4)
@@ -501,9 +570,10 @@ class GpuBlock:
         px = torch.empty(npad, dtype=torch.float64, device="cuda")
         py = torch.empty(npad, dtype=torch.float64, device="cuda")
         indata = torch.empty((cfg.n_inframe, npad), dtype=torch.float32, device="cuda")
-        o = int(self.off_pix[k])
-        idx = self.d_idx[o:o + n]
-        pcode = self.d_pcode_all[o:o + n]
+        ch, q = self._meta(k)
+        o = int(ch["off_pix"][q])
+        idx = ch["idx"][o:o + n]
+        pcode = ch["pcode"][o:o + n]
         # positions and layers: gathered through idx; the table codes are per (stamp, pixel) and were planned on the host
         _lib.dev_gather_stamp(ptr(idx), n, npad, ptr(self.d_x), ptr(self.d_y), None, ptr(self.d_data),
                               self.d_data.stride(0), cfg.n_inframe, ptr(px), ptr(py), None, ptr(indata),
@@ -524,11 +594,11 @@ class GpuBlock:
                 A = assemble(0.0)
         else:
             A = torch.empty((npad, npad), dtype=torch.float64, device="cuda")
-            _lib.dev_build_A(ptr(px), ptr(py), ptr(pcode), n, npad, ptr(self.d_tables), ptr(self.d_lut[k]), nimg, ncode,
+            _lib.dev_build_A(ptr(px), ptr(py), ptr(pcode), n, npad, ptr(self.d_tables), ptr(ch["lut"][q]), nimg, ncode,
                              self.arena.ngrid, float(cfg.dscale), float(cfg.nc_ovl), float(cfg.flat_penalty), ptr(A),
                              A.stride(0), 0.0, self.arena.poly, st)
         mB = torch.empty((cfg.n_out, mpad, npad), dtype=torch.float64, device="cuda")
-        _lib.dev_build_B(ptr(px), ptr(py), ptr(pcode), n, npad, ptr(self.d_tables), ptr(self.d_lut_io[k]), cfg.n_out,
+        _lib.dev_build_B(ptr(px), ptr(py), ptr(pcode), n, npad, ptr(self.d_tables), ptr(ch["lut_io"][q]), cfg.n_out,
                          self.arena.ngrid, float(cfg.dscale), float(cfg.nc_ovl), cfg.n2f, mpad, p.x0out, p.y0out, ptr(mB),
                          mB.stride(1), mB.stride(0), st)
         ds = DeviceSystem(n=n, m=m, n2f=cfg.n2f, A=A, mB=mB, C=np.asarray(self.tab.outovlc, dtype=np.float64),
@@ -541,9 +611,10 @@ class GpuBlock:
 
     def apply_spec(self, k: int, indata, want_T32=True, want_Ti64=False) -> ApplySpec:
         cfg = self.cfg
-        a, b = int(self.off_seg[k]), int(self.off_seg[k + 1])
-        return ApplySpec(fade=cfg.fade_kernel, fade_w=self.d_fade_w, indata=indata, seg_end=self.d_seg_end[a:b],
-                         seg_img=self.d_seg_img[a:b], n_img=self.blk.n_inimage, n2=cfg.n2,
+        ch, q = self._meta(k)
+        a, b = int(ch["off_seg"][q]), int(ch["off_seg"][q + 1])
+        return ApplySpec(fade=cfg.fade_kernel, fade_w=self.d_fade_w, indata=indata, seg_end=ch["seg_end"][a:b],
+                         seg_img=ch["seg_img"][a:b], n_img=self.blk.n_inimage, n2=cfg.n2,
                          clamp_iter=(self.kernel == "Iterative"), want_T32=want_T32, want_Ti64=want_Ti64)
 
     def coadd_stamp(self, k: int, keep: bool = False):
@@ -645,7 +716,7 @@ class GpuBlock:
             return 1
         cfg = self.cfg
         nv = max(1, len(np.atleast_1d(cfg.kappaC_arr)))
-        nmax = max(self.plans[ji].n for ji in self.order)
+        nmax = max(p.n for p in self.plans.values())  # of the stamps planned so far (at least the first chunk)
         npad, mpad = rup(nmax), rup(cfg.n2f**2)
         per = 8.0 * ((1 + nv) * npad * npad + (cfg.n_out + nv) * mpad * npad)
         free = hbm_free_estimate()
@@ -681,7 +752,7 @@ class GpuBlock:
                 spec = self.apply_spec(k, indata, want_T32=False, want_Ti64=False)
                 self._overlap_add(p, 0, apply_T(ds, kos[u], 0, spec))
 
-        for ks in batches:
+        for b, ks in enumerate(batches):
             plans = [self.plans[self.order[k]] for k in ks]
             self.ensure_pairs([pl for pl in plans if pl.n > 0])
             live = []
@@ -692,6 +763,9 @@ class GpuBlock:
                 ds, indata = self.build_system(k, need_A=need_A)
                 live.append((k, p, ds, indata))
             handle = solve_chol_launch([t[2] for t in live], cfg, 0)
+            if b + 1 < len(batches):  # host planning of the next batch hides behind the work just enqueued
+                for k in (batches[b + 1][0], batches[b + 1][-1]):
+                    self._ensure_planned(k)
             if pending is not None:
                 finish(pending)
             pending = (live, handle)

@@ -526,8 +526,9 @@ def apply_T(ds: DeviceSystem, ko: KernelOutput, j_out: int, spec: ApplySpec):
     nfr = spec.indata.shape[0] if spec.indata is not None else 0
     nseg = spec.seg_end.numel() if spec.seg_end is not None else 0
     out = {}
-    T32 = torch.empty((m, npad), dtype=torch.float32, device="cuda") if spec.want_T32 else None
-    Ti64 = _f64(m, npad) if spec.want_Ti64 else None
+    # (k_finalize writes columns < n only: the padding columns n..npad-1 of the kept copies are zero by construction)
+    T32 = torch.zeros((m, npad), dtype=torch.float32, device="cuda") if spec.want_T32 else None
+    Ti64 = _zeros64(m, npad) if spec.want_Ti64 else None
     D, N = _f64(m), _f64(m)
     outimage = torch.zeros((max(nfr, 1), m), dtype=torch.float32, device="cuda")
     Tsum_image = _zeros64(m, max(spec.n_img, 1))
