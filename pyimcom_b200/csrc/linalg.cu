@@ -16,6 +16,8 @@
 // the X rows are simply extra panel rows below the matrix) followed by  Ti = Z L^-1  (backward).
 // Every product is  C (+)= A[.,K] * B[.,K]^T  with both operands K-contiguous, so one tile kernel
 // (128x128x16 stages, 4-stage cp.async ring, 8 warps of 64x32, DMMA.8x8x4) serves all phases.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -143,6 +145,124 @@ __device__ __forceinline__ void gemm_tile_nt(const double* A, int lda, const dou
         }
 }
 
+// ---- the 64x64 tile: several small independent CTAs per SM -------------------------------------
+// One 128x128 CTA per SM leaves the tensor pipe idle whenever its eight warps meet at the stage barrier (ncu: DMMA pipe
+// 87 % busy, 30.5 TFLOP/s).  The library DGEMM that sets the roofline (ncu on torch.matmul, tools/probe/dgemm_probe.py:
+// cutlass d884gemm 64x64_16x4, 128 threads, 120 registers, 64 KB, three CTAs per SM, DMMA pipe 97.5 % busy) hides that
+// barrier behind the other resident CTAs.  Same recipe here: 64x64 output tile, 4 warps of 32x32, K stages of 16 in a
+// 4-deep cp.async ring (64 KB, so three CTAs share an SM), rows of one stage are exactly 128 B and the 16-byte chunks of
+// a row are XOR-swizzled with (row & 7): cp.async keeps its 16-byte granularity and the fragment loads (8 rows x 4
+// consecutive doubles per instruction) touch every 8-byte bank word exactly twice, the minimum for 256 B.
+// Used by the four update kernels (operands and output never overlap there); the in-place products with inv(L_kk)
+// keep the 128x128 tile, which stages the whole K = 128 operand before it writes.
+constexpr int KT2 = 16, ST2 = 4, TB = 64, GT2 = 128;
+constexpr int STAGE2_DOUBLES = 2 * TB * KT2;
+constexpr size_t GEMM2_SMEM = (size_t)ST2 * STAGE2_DOUBLES * sizeof(double);  // 65536 B
+
+template <int MODE>
+__device__ __forceinline__ void gemm_tile64(const double* A, int lda, const double* B, int ldb, double* C, int ldc,
+                                            int K, double* smem) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int wm = warp >> 1, wn = warp & 1;  // 2 x 2 warps of 32 x 32
+    const int g = lane >> 2, q = lane & 3;
+    constexpr int MI = 4, NJ = 4;
+
+    double acc[MI][NJ][2];
+    if (MODE == TILE_ASSIGN) {
+#pragma unroll
+        for (int mi = 0; mi < MI; mi++)
+#pragma unroll
+            for (int ni = 0; ni < NJ; ni++) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
+    }
+    const int nk = (K + KT2 - 1) / KT2;
+    // loader: 512 16-byte chunks per operand per stage, 4 per thread; 8 consecutive threads fetch one 128-byte row
+    auto load_stage = [&](int slot, int kt) {
+        double* As = smem + (size_t)slot * STAGE2_DOUBLES;
+        double* Bs = As + TB * KT2;
+        const int k0 = kt * KT2;
+#pragma unroll
+        for (int r = 0; r < TB * (KT2 / 2) / GT2; r++) {
+            const int c = tid + GT2 * r;
+            const int row = c >> 3, ch = c & 7;
+            const int dst = row * KT2 + ((ch ^ (row & 7)) << 1);
+            if (k0 + 2 * ch < K) {
+                cp_async16(As + dst, A + (size_t)row * lda + k0 + 2 * ch);
+                cp_async16(Bs + dst, B + (size_t)row * ldb + k0 + 2 * ch);
+            } else {  // K tail (K is even): zero operands contribute nothing
+                *reinterpret_cast<double2*>(As + dst) = make_double2(0.0, 0.0);
+                *reinterpret_cast<double2*>(Bs + dst) = make_double2(0.0, 0.0);
+            }
+        }
+    };
+#pragma unroll
+    for (int s = 0; s < ST2 - 1; s++) {
+        if (s < nk) load_stage(s, s);
+        cp_async_commit();
+    }
+    if (MODE != TILE_ASSIGN) {  // overlaps with the pipeline fill
+#pragma unroll
+        for (int mi = 0; mi < MI; mi++)
+#pragma unroll
+            for (int ni = 0; ni < NJ; ni++) {
+                const double2 v = *reinterpret_cast<const double2*>(
+                    C + (size_t)(wm * 32 + mi * 8 + g) * ldc + wn * 32 + ni * 8 + q * 2);
+                acc[mi][ni][0] = (MODE == TILE_SUB) ? -v.x : v.x;
+                acc[mi][ni][1] = (MODE == TILE_SUB) ? -v.y : v.y;
+            }
+    }
+    // element (row, 4 kk + q) of a stage sits at row * 16 + (off0 ^ 4 kk): all fragment rows have row & 7 == g
+    const int off0 = ((((q >> 1) ^ g)) << 1) | (q & 1);
+    const int arow = (wm * 32 + g) * KT2, brow = TB * KT2 + (wn * 32 + g) * KT2;
+    for (int kt = 0; kt < nk; kt++) {
+        cp_async_wait<ST2 - 2>();
+        __syncthreads();
+        if (kt + ST2 - 1 < nk) load_stage((kt + ST2 - 1) % ST2, kt + ST2 - 1);
+        cp_async_commit();
+        const double* St = smem + (size_t)(kt % ST2) * STAGE2_DOUBLES;
+#pragma unroll
+        for (int kk = 0; kk < KT2 / 4; kk++) {
+            const double* As = St + arow + (off0 ^ (4 * kk));
+            const double* Bs = St + brow + (off0 ^ (4 * kk));
+            double a[MI], b[NJ];
+#pragma unroll
+            for (int mi = 0; mi < MI; mi++) a[mi] = As[mi * 8 * KT2];
+#pragma unroll
+            for (int ni = 0; ni < NJ; ni++) b[ni] = Bs[ni * 8 * KT2];
+#pragma unroll
+            for (int mi = 0; mi < MI; mi++)
+#pragma unroll
+                for (int ni = 0; ni < NJ; ni++) dmma884(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
+        }
+    }
+    cp_async_wait<0>();
+#pragma unroll
+    for (int mi = 0; mi < MI; mi++)
+#pragma unroll
+        for (int ni = 0; ni < NJ; ni++) {
+            const int r = wm * 32 + mi * 8 + g, c = wn * 32 + ni * 8 + q * 2;
+            double2 v;
+            v.x = (MODE == TILE_SUB) ? -acc[mi][ni][0] : acc[mi][ni][0];
+            v.y = (MODE == TILE_SUB) ? -acc[mi][ni][1] : acc[mi][ni][1];
+            *reinterpret_cast<double2*>(C + (size_t)r * ldc + c) = v;
+        }
+}
+
+// One 128x128 output tile of an update kernel, either by one 256-thread CTA (T64 = false) or as four 64x64 quadrants
+// (qm, qn) by four 128-thread CTAs.  half: only rows 0..63 of the tile are real (x_half_tile).
+template <int MODE, bool T64>
+__device__ __forceinline__ void update_tile(bool half, int qm, int qn, const double* A, int lda, const double* B,
+                                            int ldb, double* C, int ldc, int K, double* smem) {
+    if (T64) {
+        if (half && qm) return;
+        gemm_tile64<MODE>(A + (size_t)qm * TB * lda, lda, B + (size_t)qn * TB * ldb, ldb,
+                          C + (size_t)qm * TB * ldc + qn * TB, ldc, K, smem);
+    } else if (half) {
+        gemm_tile_nt<MODE, true>(A, lda, B, ldb, C, ldc, K, nullptr, 0, smem);
+    } else {
+        gemm_tile_nt<MODE, false>(A, lda, B, ldb, C, ldc, K, nullptr, 0, smem);
+    }
+}
+
 // ---- generic C (+)= A B^T over a grid of tiles (also the public DGEMM of the library) ----------
 template <int MODE>
 __global__ void __launch_bounds__(GT, 1) k_gemm_nt(const double* __restrict__ A, int lda,
@@ -151,6 +271,15 @@ __global__ void __launch_bounds__(GT, 1) k_gemm_nt(const double* __restrict__ A,
     const int tn = blockIdx.x, tm = blockIdx.y;
     gemm_tile_nt<MODE>(A + (size_t)tm * NB * lda, lda, B + (size_t)tn * NB * ldb, ldb,
                        C + (size_t)tm * NB * ldc + (size_t)tn * NB, ldc, K, nullptr, 0, smem);
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(GT2, 3) k_gemm64_nt(const double* __restrict__ A, int lda,
+                                                      const double* __restrict__ B, int ldb, double* C, int ldc, int K) {
+    extern __shared__ __align__(16) double smem[];
+    const int tn = blockIdx.x, tm = blockIdx.y;
+    gemm_tile64<MODE>(A + (size_t)tm * TB * lda, lda, B + (size_t)tn * TB * ldb, ldb,
+                      C + (size_t)tm * TB * ldc + (size_t)tn * TB, ldc, K, smem);
 }
 
 // Row-tile r of the right-hand sides holds at most 64 real rows (mrows = number of real rows; 0 = unknown: all tiles full).
@@ -164,11 +293,13 @@ __device__ __forceinline__ bool x_half_tile(const SolveSys& s, int r) {
 // per super-panel, so the tile kernel runs at its large-K rate), right-looking with K = 128 inside.
 //
 // Super-panel update:  W[i][j] -= W[i][0:c0] W[j][0:c0]^T  (c0 <= j < c1, j <= i)  and the same for the X rows.
-__global__ void __launch_bounds__(GT, 1) k_chol_super_update(SolveBatch bt, int c0, int c1) {
+template <bool T64>
+__global__ void __launch_bounds__(T64 ? GT2 : GT, T64 ? 3 : 1) k_chol_super_update(SolveBatch bt, int c0, int c1) {
     extern __shared__ __align__(16) double smem[];
     const SolveSys& s = bt.s[blockIdx.z];
     const int nb = s.npad / NB, mb = s.mpad / NB;
-    const int j = c0 + blockIdx.x, t = blockIdx.y;
+    const int qn = T64 ? blockIdx.x & 1 : 0, qm = T64 ? blockIdx.y & 1 : 0;
+    const int j = c0 + (T64 ? blockIdx.x >> 1 : blockIdx.x), t = T64 ? blockIdx.y >> 1 : blockIdx.y;
     const int nrow = nb - c0;
     if (j >= nb || j >= c1 || t >= nrow + mb) return;
     const double* Bp = s.W + (size_t)j * NB * s.ldw;
@@ -176,16 +307,12 @@ __global__ void __launch_bounds__(GT, 1) k_chol_super_update(SolveBatch bt, int 
     if (t < nrow) {
         const int i = c0 + t;
         if (j > i) return;
-        gemm_tile_nt<TILE_SUB>(s.W + (size_t)i * NB * s.ldw, s.ldw, Bp, s.ldw,
-                               s.W + (size_t)i * NB * s.ldw + (size_t)j * NB, s.ldw, K, nullptr, 0, smem);
+        update_tile<TILE_SUB, T64>(false, qm, qn, s.W + (size_t)i * NB * s.ldw, s.ldw, Bp, s.ldw,
+                                   s.W + (size_t)i * NB * s.ldw + (size_t)j * NB, s.ldw, K, smem);
     } else {
         const int r = t - nrow;
-        if (x_half_tile(s, r))
-            gemm_tile_nt<TILE_SUB, true>(s.X + (size_t)r * NB * s.ldx, s.ldx, Bp, s.ldw,
-                                         s.X + (size_t)r * NB * s.ldx + (size_t)j * NB, s.ldx, K, nullptr, 0, smem);
-        else
-            gemm_tile_nt<TILE_SUB>(s.X + (size_t)r * NB * s.ldx, s.ldx, Bp, s.ldw,
-                                   s.X + (size_t)r * NB * s.ldx + (size_t)j * NB, s.ldx, K, nullptr, 0, smem);
+        update_tile<TILE_SUB, T64>(x_half_tile(s, r), qm, qn, s.X + (size_t)r * NB * s.ldx, s.ldx, Bp, s.ldw,
+                                   s.X + (size_t)r * NB * s.ldx + (size_t)j * NB, s.ldx, K, smem);
     }
 }
 
@@ -215,49 +342,44 @@ __global__ void __launch_bounds__(GT, 1) k_chol_panel(SolveBatch bt, int k) {
 
 // Update inside the super-panel after panel k:  W[i][j] -= W[i][k] W[j][k]^T (k < j < c1, j <= i)  and
 // X[t][j] -= X[t][k] W[j][k]^T.
-__global__ void __launch_bounds__(GT, 1) k_chol_update(SolveBatch bt, int k, int c1) {
+template <bool T64>
+__global__ void __launch_bounds__(T64 ? GT2 : GT, T64 ? 3 : 1) k_chol_update(SolveBatch bt, int k, int c1) {
     extern __shared__ __align__(16) double smem[];
     const SolveSys& s = bt.s[blockIdx.z];
     const int nb = s.npad / NB, mb = s.mpad / NB;
     const int nrow = nb - 1 - k;
-    const int jj = blockIdx.x, t = blockIdx.y;
+    const int qn = T64 ? blockIdx.x & 1 : 0, qm = T64 ? blockIdx.y & 1 : 0;
+    const int jj = T64 ? blockIdx.x >> 1 : blockIdx.x, t = T64 ? blockIdx.y >> 1 : blockIdx.y;
     const int j = k + 1 + jj;
     if (k >= nb || j >= nb || j >= c1 || t >= nrow + mb) return;
     const double* Bp = s.W + (size_t)j * NB * s.ldw + (size_t)k * NB;
     if (t < nrow) {
         const int i = k + 1 + t;
         if (j > i) return;
-        gemm_tile_nt<TILE_SUB>(s.W + (size_t)i * NB * s.ldw + (size_t)k * NB, s.ldw, Bp, s.ldw,
-                               s.W + (size_t)i * NB * s.ldw + (size_t)j * NB, s.ldw, NB, nullptr, 0, smem);
+        update_tile<TILE_SUB, T64>(false, qm, qn, s.W + (size_t)i * NB * s.ldw + (size_t)k * NB, s.ldw, Bp, s.ldw,
+                                   s.W + (size_t)i * NB * s.ldw + (size_t)j * NB, s.ldw, NB, smem);
     } else {
         const int r = t - nrow;
-        if (x_half_tile(s, r))
-            gemm_tile_nt<TILE_SUB, true>(s.X + (size_t)r * NB * s.ldx + (size_t)k * NB, s.ldx, Bp, s.ldw,
-                                         s.X + (size_t)r * NB * s.ldx + (size_t)j * NB, s.ldx, NB, nullptr, 0, smem);
-        else
-            gemm_tile_nt<TILE_SUB>(s.X + (size_t)r * NB * s.ldx + (size_t)k * NB, s.ldx, Bp, s.ldw,
-                                   s.X + (size_t)r * NB * s.ldx + (size_t)j * NB, s.ldx, NB, nullptr, 0, smem);
+        update_tile<TILE_SUB, T64>(x_half_tile(s, r), qm, qn, s.X + (size_t)r * NB * s.ldx + (size_t)k * NB, s.ldx, Bp,
+                                   s.ldw, s.X + (size_t)r * NB * s.ldx + (size_t)j * NB, s.ldx, NB, smem);
     }
 }
 
 // Backward substitution Ti = Z L^-1, super-panels taken from the right.  In "from the end" coordinates
 // [e0, e1) the super-panel of a system with nb blocks is lo = max(0, nb - e1) <= k < hi = nb - e0.
 // Super-panel update:  X[t][j] -= X[t][hi:nb] L[hi:nb][j]  (lo <= j < hi); L[k][j]^T lives at W[j][k] (upper triangle).
-__global__ void __launch_bounds__(GT, 1) k_back_super_update(SolveBatch bt, int e0, int e1) {
+template <bool T64>
+__global__ void __launch_bounds__(T64 ? GT2 : GT, T64 ? 3 : 1) k_back_super_update(SolveBatch bt, int e0, int e1) {
     extern __shared__ __align__(16) double smem[];
     const SolveSys& s = bt.s[blockIdx.z];
     const int nb = s.npad / NB, mb = s.mpad / NB;
     const int hi = nb - e0;
-    const int j = hi - 1 - (int)blockIdx.x, t = blockIdx.y;
+    const int qn = T64 ? blockIdx.x & 1 : 0, qm = T64 ? blockIdx.y & 1 : 0;
+    const int j = hi - 1 - (int)(T64 ? blockIdx.x >> 1 : blockIdx.x), t = T64 ? blockIdx.y >> 1 : blockIdx.y;
     if (hi <= 0 || j < 0 || j < nb - e1 || t >= mb) return;
-    if (x_half_tile(s, t))
-        gemm_tile_nt<TILE_SUB, true>(s.X + (size_t)t * NB * s.ldx + (size_t)hi * NB, s.ldx,
-                                     s.W + (size_t)j * NB * s.ldw + (size_t)hi * NB, s.ldw,
-                                     s.X + (size_t)t * NB * s.ldx + (size_t)j * NB, s.ldx, e0 * NB, nullptr, 0, smem);
-    else
-        gemm_tile_nt<TILE_SUB>(s.X + (size_t)t * NB * s.ldx + (size_t)hi * NB, s.ldx,
+    update_tile<TILE_SUB, T64>(x_half_tile(s, t), qm, qn, s.X + (size_t)t * NB * s.ldx + (size_t)hi * NB, s.ldx,
                                s.W + (size_t)j * NB * s.ldw + (size_t)hi * NB, s.ldw,
-                               s.X + (size_t)t * NB * s.ldx + (size_t)j * NB, s.ldx, e0 * NB, nullptr, 0, smem);
+                               s.X + (size_t)t * NB * s.ldx + (size_t)j * NB, s.ldx, e0 * NB, smem);
 }
 
 // Backward step k, part 1:  X[t][k] = X[t][k] inv(L_kk)   (B operand = inv(L_kk)^T)
@@ -275,21 +397,18 @@ __global__ void __launch_bounds__(GT, 1) k_back_diag(SolveBatch bt, int kfromtop
 }
 
 // Backward step k, part 2, inside the super-panel:  X[t][j] -= X[t][k] L[k][j]  (lo <= j < k)
-__global__ void __launch_bounds__(GT, 1) k_back_update(SolveBatch bt, int kfromtop, int e1) {
+template <bool T64>
+__global__ void __launch_bounds__(T64 ? GT2 : GT, T64 ? 3 : 1) k_back_update(SolveBatch bt, int kfromtop, int e1) {
     extern __shared__ __align__(16) double smem[];
     const SolveSys& s = bt.s[blockIdx.z];
     const int nb = s.npad / NB, mb = s.mpad / NB;
     const int k = nb - 1 - kfromtop;
-    const int j = k - 1 - (int)blockIdx.x, t = blockIdx.y;
+    const int qn = T64 ? blockIdx.x & 1 : 0, qm = T64 ? blockIdx.y & 1 : 0;
+    const int j = k - 1 - (int)(T64 ? blockIdx.x >> 1 : blockIdx.x), t = T64 ? blockIdx.y >> 1 : blockIdx.y;
     if (k < 0 || j < 0 || j < nb - e1 || t >= mb) return;
-    if (x_half_tile(s, t))
-        gemm_tile_nt<TILE_SUB, true>(s.X + (size_t)t * NB * s.ldx + (size_t)k * NB, s.ldx,
-                                     s.W + (size_t)j * NB * s.ldw + (size_t)k * NB, s.ldw,
-                                     s.X + (size_t)t * NB * s.ldx + (size_t)j * NB, s.ldx, NB, nullptr, 0, smem);
-    else
-        gemm_tile_nt<TILE_SUB>(s.X + (size_t)t * NB * s.ldx + (size_t)k * NB, s.ldx,
+    update_tile<TILE_SUB, T64>(x_half_tile(s, t), qm, qn, s.X + (size_t)t * NB * s.ldx + (size_t)k * NB, s.ldx,
                                s.W + (size_t)j * NB * s.ldw + (size_t)k * NB, s.ldw,
-                               s.X + (size_t)t * NB * s.ldx + (size_t)j * NB, s.ldx, NB, nullptr, 0, smem);
+                               s.X + (size_t)t * NB * s.ldx + (size_t)j * NB, s.ldx, NB, smem);
 }
 
 // ---- 128x128 diagonal block: Cholesky in shared memory + explicit triangular inverse -------------
@@ -481,17 +600,29 @@ __global__ void k_transpose(const double* __restrict__ A, int lda, double* __res
 }
 
 bool g_attr_done = false;
+bool g_tile64 = true;
 int gemm_attrs() {
     if (g_attr_done) return 0;
     B200_CUDA(cudaFuncSetAttribute(k_gemm_nt<TILE_ASSIGN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM));
     B200_CUDA(cudaFuncSetAttribute(k_gemm_nt<TILE_SUB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM));
     B200_CUDA(cudaFuncSetAttribute(k_gemm_nt<TILE_ADD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM));
     B200_CUDA(cudaFuncSetAttribute(k_chol_panel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM));
-    B200_CUDA(cudaFuncSetAttribute(k_chol_update, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM));
-    B200_CUDA(cudaFuncSetAttribute(k_chol_super_update, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM));
-    B200_CUDA(cudaFuncSetAttribute(k_back_super_update, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM));
     B200_CUDA(cudaFuncSetAttribute(k_back_diag, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM));
-    B200_CUDA(cudaFuncSetAttribute(k_back_update, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM));
+#define B200_ATTR2(kern)                                                                                          \
+    B200_CUDA(cudaFuncSetAttribute(kern<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM));  \
+    B200_CUDA(cudaFuncSetAttribute(kern<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM2_SMEM));
+    B200_ATTR2(k_chol_update)
+    B200_ATTR2(k_chol_super_update)
+    B200_ATTR2(k_back_super_update)
+    B200_ATTR2(k_back_update)
+#undef B200_ATTR2
+    B200_CUDA(cudaFuncSetAttribute(k_gemm64_nt<TILE_ASSIGN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM2_SMEM));
+    B200_CUDA(cudaFuncSetAttribute(k_gemm64_nt<TILE_SUB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM2_SMEM));
+    B200_CUDA(cudaFuncSetAttribute(k_gemm64_nt<TILE_ADD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM2_SMEM));
+    {
+        const char* e = getenv("B200_TILE64");  // 0: the 128x128 one-CTA-per-SM tile everywhere (A/B comparisons)
+        g_tile64 = !(e && e[0] == '0');
+    }
     B200_CUDA(cudaFuncSetAttribute(k_potrf_diag, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)POTRF_SMEM));
     g_attr_done = true;
     return 0;
@@ -542,7 +673,10 @@ int launch_chol_solve(const SolveSys* h_sys, int nsys, int do_factor, int do_sol
             const int c1 = c0 + SP < nbmax ? c0 + SP : nbmax;
             if (c0 > 0) {
                 prof_begin(PROF_CHOL_SUPER, st);
-                k_chol_super_update<<<dim3(c1 - c0, nbmax - c0 + mbmax, nsys), GT, GEMM_SMEM, st>>>(bt, c0, c1);
+                if (g_tile64)
+                    k_chol_super_update<true><<<dim3(2 * (c1 - c0), 2 * (nbmax - c0 + mbmax), nsys), GT2, GEMM2_SMEM, st>>>(bt, c0, c1);
+                else
+                    k_chol_super_update<false><<<dim3(c1 - c0, nbmax - c0 + mbmax, nsys), GT, GEMM_SMEM, st>>>(bt, c0, c1);
                 prof_end(tiles_fwd(c0, c1, c0) * tile_flops * c0 * NB, st);
                 B200_LAUNCHED(1);
             }
@@ -560,7 +694,10 @@ int launch_chol_solve(const SolveSys* h_sys, int nsys, int do_factor, int do_sol
                 }
                 if (c1 - 1 - k > 0) {
                     prof_begin(PROF_CHOL_INNER, st);
-                    k_chol_update<<<dim3(c1 - 1 - k, nrow + mbmax, nsys), GT, GEMM_SMEM, st>>>(bt, k, c1);
+                    if (g_tile64)
+                        k_chol_update<true><<<dim3(2 * (c1 - 1 - k), 2 * (nrow + mbmax), nsys), GT2, GEMM2_SMEM, st>>>(bt, k, c1);
+                    else
+                        k_chol_update<false><<<dim3(c1 - 1 - k, nrow + mbmax, nsys), GT, GEMM_SMEM, st>>>(bt, k, c1);
                     prof_end(tiles_fwd(k + 1, c1, k + 1) * tile_flops * NB, st);
                     B200_LAUNCHED(1);
                 }
@@ -575,7 +712,10 @@ int launch_chol_solve(const SolveSys* h_sys, int nsys, int do_factor, int do_sol
             const int e1 = e0 + SP < nbmax ? e0 + SP : nbmax;
             if (e0 > 0) {
                 prof_begin(PROF_BACK_SUPER, st);
-                k_back_super_update<<<dim3(e1 - e0, mbmax, nsys), GT, GEMM_SMEM, st>>>(bt, e0, e1);
+                if (g_tile64)
+                    k_back_super_update<true><<<dim3(2 * (e1 - e0), 2 * mbmax, nsys), GT2, GEMM2_SMEM, st>>>(bt, e0, e1);
+                else
+                    k_back_super_update<false><<<dim3(e1 - e0, mbmax, nsys), GT, GEMM_SMEM, st>>>(bt, e0, e1);
                 double t = 0;
                 for (int q = 0; q < nsys; q++) {
                     const int nb = bt.s[q].npad / NB;
@@ -592,7 +732,10 @@ int launch_chol_solve(const SolveSys* h_sys, int nsys, int do_factor, int do_sol
                 B200_LAUNCHED(1);
                 if (e1 - 1 - kk > 0) {
                     prof_begin(PROF_BACK_INNER, st);
-                    k_back_update<<<dim3(e1 - 1 - kk, mbmax, nsys), GT, GEMM_SMEM, st>>>(bt, kk, e1);
+                    if (g_tile64)
+                        k_back_update<true><<<dim3(2 * (e1 - 1 - kk), 2 * mbmax, nsys), GT2, GEMM2_SMEM, st>>>(bt, kk, e1);
+                    else
+                        k_back_update<false><<<dim3(e1 - 1 - kk, mbmax, nsys), GT, GEMM_SMEM, st>>>(bt, kk, e1);
                     prof_end(mbsum * (e1 - 1 - kk) * tile_flops * NB, st);
                     B200_LAUNCHED(1);
                 }
@@ -613,7 +756,15 @@ int launch_gemm_nt(const double* A, int lda, const double* B, int ldb, double* C
     if (int rc = gemm_attrs()) return rc;
     dim3 grid(N / NB, M / NB);
     prof_begin(PROF_GEMM, st);
-    if (accumulate == 0)
+    if (g_tile64) {
+        dim3 grid2(N / TB, M / TB);
+        if (accumulate == 0)
+            k_gemm64_nt<TILE_ASSIGN><<<grid2, GT2, GEMM2_SMEM, st>>>(A, lda, B, ldb, C, ldc, K);
+        else if (accumulate > 0)
+            k_gemm64_nt<TILE_ADD><<<grid2, GT2, GEMM2_SMEM, st>>>(A, lda, B, ldb, C, ldc, K);
+        else
+            k_gemm64_nt<TILE_SUB><<<grid2, GT2, GEMM2_SMEM, st>>>(A, lda, B, ldb, C, ldc, K);
+    } else if (accumulate == 0)
         k_gemm_nt<TILE_ASSIGN><<<grid, GT, GEMM_SMEM, st>>>(A, lda, B, ldb, C, ldc, K);
     else if (accumulate > 0)
         k_gemm_nt<TILE_ADD><<<grid, GT, GEMM_SMEM, st>>>(A, lda, B, ldb, C, ldc, K);
