@@ -43,12 +43,12 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 from pyimcom_b200.synth import StampConfig, SynthBlock  # noqa: E402
 
 # DRAM traffic of the dominant kernel from the committed ncu capture (profiles/ncu_r01.txt: k_chol_super_update,
-# grid (4,25,6) = super-panel c0=24 of 49 block columns for the 6 systems of one solve stream, 2.78 ms under ncu):
+# grid (8,74,6) = super-panel c0=24 of 49 block columns for the 6 systems of one solve stream, 2.48 ms under ncu):
 # dram__bytes_read.sum + dram__bytes_write.sum of that launch
-NCU_TRAFFIC_BYTES = 844.2944e6 + 66.368e6
+NCU_TRAFFIC_BYTES = 844.72192e6 + 102.279936e6
 NCU_TRAFFIC_NOTE = ("ncu --set full, one launch of k_chol_super_update (super-panel c0=24 of 49 block columns, 6 systems of one "
-                    "solve stream): 0.844 GB read + 0.066 GB written vs 8.8e10 flop => 96 flop/B, far above the FP64 ridge "
-                    "(~5.5 flop/B); tensor pipe 87.4 % busy")
+                    "solve stream): 0.845 GB read + 0.102 GB written vs 8.8e10 flop => 93 flop/B, far above the FP64 ridge "
+                    "(~5.5 flop/B); tensor pipe 93.1 % busy")
 METRIC = "coadd_output_pixels_per_sec"
 UNIT = "output px/s"
 SEED0 = 1000

@@ -153,7 +153,8 @@ int b200_dev_assemble_A(const b200_asm_desc* desc, const int* gidx, int n, int n
                         int lda, double diag_add, void* stream);
 /* mBhalf (n_out, mpad, ldb) for one output stamp: replaces PSFOvl._call_io_cross (psfutil.py:1497-1595) and
  * coadd.py:1075-1082.  lut_io (ncode*n_out) table offsets (<0 absent); output pixel (iy,ix) sits at
- * (x0out + ix, y0out + iy) (coadd.py:879-882).  Padding rows/columns are zero-filled. */
+ * (x0out + ix, y0out + iy) (coadd.py:879-882).  Padding rows/columns are zero-filled.  tables must be 16-byte aligned
+ * and readable one double past its last table (aligned 16-byte loads). */
 int b200_dev_build_B(const double* px, const double* py, const int* pcode, int n, int npad, const double* tables,
                      const long long* lut_io, int n_out, int ngrid, double dscale, double nc, int n2f, int mpad,
                      double x0out, double y0out, double* B, int ldb, size_t strideB, void* stream);

@@ -92,7 +92,8 @@ class _Arena:
 
     def upload(self):
         """Raw tables go up as they are (one pinned copy per table set); padding and re-layout happen on the device."""
-        dst = torch.empty(max(1, self.size), dtype=torch.float64, device="cuda")
+        # (+2: the strip stage of k_build_B_sep reads aligned 16-byte pairs and may touch the double after a window)
+        dst = torch.empty(max(1, self.size) + 2, dtype=torch.float64, device="cuda")
         self.h2d_bytes = 0
         st = stream_handle()
         for arr, lead, P, base in self.sets:

@@ -161,7 +161,7 @@ constexpr size_t GEMM2_SMEM = (size_t)ST2 * STAGE2_DOUBLES * sizeof(double);  //
 
 template <int MODE>
 __device__ __forceinline__ void gemm_tile64(const double* A, int lda, const double* B, int ldb, double* C, int ldc,
-                                            int K, double* smem) {
+                                            int K, double* smem, double* Ct = nullptr, int ldct = 0) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int wm = warp >> 1, wn = warp & 1;  // 2 x 2 warps of 32 x 32
     const int g = lane >> 2, q = lane & 3;
@@ -244,7 +244,31 @@ __device__ __forceinline__ void gemm_tile64(const double* A, int lda, const doub
             v.x = (MODE == TILE_SUB) ? -acc[mi][ni][0] : acc[mi][ni][0];
             v.y = (MODE == TILE_SUB) ? -acc[mi][ni][1] : acc[mi][ni][1];
             *reinterpret_cast<double2*>(C + (size_t)r * ldc + c) = v;
+            if (Ct) {
+                Ct[(size_t)c * ldct + r] = v.x;
+                Ct[(size_t)(c + 1) * ldct + r] = v.y;
+            }
         }
+}
+
+// In-place product of a 64-row strip with one of the triangular 128x128 inverses:  C = C D^T, C = Cp[0:64, 0:128].
+//   LOWER  (panel step, D = inv(L_kk), D[c][k] = 0 for k > c): columns 64..127 need all 128 k, columns 0..63 only k < 64;
+//   !LOWER (backward step, D = inv(L_kk)^T, D[c][k] = 0 for k < c): columns 0..63 need all k, columns 64..127 only k >= 64.
+// Two passes of the 64x64 tile in that order: the first pass has every operand chunk in shared memory before it writes
+// its own columns, and the second pass never reads the columns the first one wrote.  The structural zeros are skipped
+// (a quarter of the products), which does not change any sum.
+template <bool LOWER>
+__device__ __forceinline__ void trsm_strip64(double* Cp, int ldc, const double* D, double* Ct, int ldct, double* smem) {
+    if (LOWER) {
+        gemm_tile64<TILE_ASSIGN>(Cp, ldc, D + (size_t)TB * NB, NB, Cp + TB, ldc, NB, smem,
+                                 Ct ? Ct + (size_t)TB * ldct : nullptr, ldct);
+        __syncthreads();
+        gemm_tile64<TILE_ASSIGN>(Cp, ldc, D, NB, Cp, ldc, TB, smem, Ct, ldct);
+    } else {
+        gemm_tile64<TILE_ASSIGN>(Cp, ldc, D, NB, Cp, ldc, NB, smem);
+        __syncthreads();
+        gemm_tile64<TILE_ASSIGN>(Cp + TB, ldc, D + (size_t)TB * NB + TB, NB, Cp + TB, ldc, TB, smem);
+    }
 }
 
 // One 128x128 output tile of an update kernel, either by one 256-thread CTA (T64 = false) or as four 64x64 quadrants
@@ -318,25 +342,34 @@ __global__ void __launch_bounds__(T64 ? GT2 : GT, T64 ? 3 : 1) k_chol_super_upda
 
 // Panel step k: rows below the diagonal block (and all X rows) times inv(L_kk)^T; the W part is also
 // stored transposed into the upper block triangle.
-__global__ void __launch_bounds__(GT, 1) k_chol_panel(SolveBatch bt, int k) {
+template <bool T64>
+__global__ void __launch_bounds__(T64 ? GT2 : GT, T64 ? 3 : 1) k_chol_panel(SolveBatch bt, int k) {
     extern __shared__ __align__(16) double smem[];
     const SolveSys& s = bt.s[blockIdx.y];
     const int nb = s.npad / NB, mb = s.mpad / NB;
     const int nrow = nb - 1 - k;
-    const int t = blockIdx.x;
+    const int t = T64 ? blockIdx.x >> 1 : blockIdx.x, qm = T64 ? blockIdx.x & 1 : 0;
     if (k >= nb || t >= nrow + mb) return;
     const double* Dk = s.Dinv + (size_t)k * NB * NB;
     if (t < nrow) {
         const int i = k + 1 + t;
         double* Cp = s.W + (size_t)i * NB * s.ldw + (size_t)k * NB;
-        gemm_tile_nt<TILE_ASSIGN>(Cp, s.ldw, Dk, NB, Cp, s.ldw, NB, s.W + (size_t)k * NB * s.ldw + (size_t)i * NB,
-                                  s.ldw, smem);
+        double* Ctp = s.W + (size_t)k * NB * s.ldw + (size_t)i * NB;
+        if (T64)
+            trsm_strip64<true>(Cp + (size_t)qm * TB * s.ldw, s.ldw, Dk, Ctp + qm * TB, s.ldw, smem);
+        else
+            gemm_tile_nt<TILE_ASSIGN>(Cp, s.ldw, Dk, NB, Cp, s.ldw, NB, Ctp, s.ldw, smem);
     } else {
         double* Cp = s.X + (size_t)(t - nrow) * NB * s.ldx + (size_t)k * NB;
-        if (x_half_tile(s, t - nrow))
+        const bool half = x_half_tile(s, t - nrow);
+        if (T64) {
+            if (half && qm) return;
+            trsm_strip64<true>(Cp + (size_t)qm * TB * s.ldx, s.ldx, Dk, nullptr, 0, smem);
+        } else if (half) {
             gemm_tile_nt<TILE_ASSIGN, true>(Cp, s.ldx, Dk, NB, Cp, s.ldx, NB, nullptr, 0, smem);
-        else
+        } else {
             gemm_tile_nt<TILE_ASSIGN>(Cp, s.ldx, Dk, NB, Cp, s.ldx, NB, nullptr, 0, smem);
+        }
     }
 }
 
@@ -383,17 +416,25 @@ __global__ void __launch_bounds__(T64 ? GT2 : GT, T64 ? 3 : 1) k_back_super_upda
 }
 
 // Backward step k, part 1:  X[t][k] = X[t][k] inv(L_kk)   (B operand = inv(L_kk)^T)
-__global__ void __launch_bounds__(GT, 1) k_back_diag(SolveBatch bt, int kfromtop) {
+template <bool T64>
+__global__ void __launch_bounds__(T64 ? GT2 : GT, T64 ? 3 : 1) k_back_diag(SolveBatch bt, int kfromtop) {
     extern __shared__ __align__(16) double smem[];
     const SolveSys& s = bt.s[blockIdx.y];
     const int nb = s.npad / NB, mb = s.mpad / NB;
     const int k = nb - 1 - kfromtop;
-    if (k < 0 || (int)blockIdx.x >= mb) return;
-    double* Cp = s.X + (size_t)blockIdx.x * NB * s.ldx + (size_t)k * NB;
-    if (x_half_tile(s, blockIdx.x))
-        gemm_tile_nt<TILE_ASSIGN, true>(Cp, s.ldx, s.Dinv + (size_t)(nb + k) * NB * NB, NB, Cp, s.ldx, NB, nullptr, 0, smem);
-    else
-        gemm_tile_nt<TILE_ASSIGN>(Cp, s.ldx, s.Dinv + (size_t)(nb + k) * NB * NB, NB, Cp, s.ldx, NB, nullptr, 0, smem);
+    const int t = T64 ? blockIdx.x >> 1 : blockIdx.x, qm = T64 ? blockIdx.x & 1 : 0;
+    if (k < 0 || t >= mb) return;
+    double* Cp = s.X + (size_t)t * NB * s.ldx + (size_t)k * NB;
+    const double* Dk = s.Dinv + (size_t)(nb + k) * NB * NB;
+    const bool half = x_half_tile(s, t);
+    if (T64) {
+        if (half && qm) return;
+        trsm_strip64<false>(Cp + (size_t)qm * TB * s.ldx, s.ldx, Dk, nullptr, 0, smem);
+    } else if (half) {
+        gemm_tile_nt<TILE_ASSIGN, true>(Cp, s.ldx, Dk, NB, Cp, s.ldx, NB, nullptr, 0, smem);
+    } else {
+        gemm_tile_nt<TILE_ASSIGN>(Cp, s.ldx, Dk, NB, Cp, s.ldx, NB, nullptr, 0, smem);
+    }
 }
 
 // Backward step k, part 2, inside the super-panel:  X[t][j] -= X[t][k] L[k][j]  (lo <= j < k)
@@ -606,11 +647,11 @@ int gemm_attrs() {
     B200_CUDA(cudaFuncSetAttribute(k_gemm_nt<TILE_ASSIGN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM));
     B200_CUDA(cudaFuncSetAttribute(k_gemm_nt<TILE_SUB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM));
     B200_CUDA(cudaFuncSetAttribute(k_gemm_nt<TILE_ADD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM));
-    B200_CUDA(cudaFuncSetAttribute(k_chol_panel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM));
-    B200_CUDA(cudaFuncSetAttribute(k_back_diag, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM));
 #define B200_ATTR2(kern)                                                                                          \
     B200_CUDA(cudaFuncSetAttribute(kern<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM));  \
     B200_CUDA(cudaFuncSetAttribute(kern<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM2_SMEM));
+    B200_ATTR2(k_chol_panel)
+    B200_ATTR2(k_back_diag)
     B200_ATTR2(k_chol_update)
     B200_ATTR2(k_chol_super_update)
     B200_ATTR2(k_back_super_update)
@@ -668,6 +709,7 @@ int launch_chol_solve(const SolveSys* h_sys, int nsys, int do_factor, int do_sol
         return t;
     };
     const double tile_flops = 2.0 * NB * NB;
+    const double tri = g_tile64 ? 0.75 : 1.0;  // the strip kernels skip the zero quarter of the triangular inverse
     if (do_factor) {
         for (int c0 = 0; c0 < nbmax; c0 += SP) {
             const int c1 = c0 + SP < nbmax ? c0 + SP : nbmax;
@@ -688,8 +730,11 @@ int launch_chol_solve(const SolveSys* h_sys, int nsys, int do_factor, int do_sol
                 const int nrow = nbmax - 1 - k;
                 if (nrow + mbmax > 0) {
                     prof_begin(PROF_CHOL_PANEL, st);
-                    k_chol_panel<<<dim3(nrow + mbmax, nsys), GT, GEMM_SMEM, st>>>(bt, k);
-                    prof_end(tiles_fwd(k, k + 1, k + 1) * tile_flops * NB, st);
+                    if (g_tile64)
+                        k_chol_panel<true><<<dim3(2 * (nrow + mbmax), nsys), GT2, GEMM2_SMEM, st>>>(bt, k);
+                    else
+                        k_chol_panel<false><<<dim3(nrow + mbmax, nsys), GT, GEMM_SMEM, st>>>(bt, k);
+                    prof_end(tiles_fwd(k, k + 1, k + 1) * tile_flops * NB * tri, st);
                     B200_LAUNCHED(1);
                 }
                 if (c1 - 1 - k > 0) {
@@ -727,8 +772,11 @@ int launch_chol_solve(const SolveSys* h_sys, int nsys, int do_factor, int do_sol
             }
             for (int kk = e0; kk < e1; kk++) {
                 prof_begin(PROF_BACK_DIAG, st);
-                k_back_diag<<<dim3(mbmax, nsys), GT, GEMM_SMEM, st>>>(bt, kk);
-                prof_end(mbsum * tile_flops * NB, st);
+                if (g_tile64)
+                    k_back_diag<true><<<dim3(2 * mbmax, nsys), GT2, GEMM2_SMEM, st>>>(bt, kk);
+                else
+                    k_back_diag<false><<<dim3(mbmax, nsys), GT, GEMM_SMEM, st>>>(bt, kk);
+                prof_end(mbsum * tile_flops * NB * tri, st);
                 B200_LAUNCHED(1);
                 if (e1 - 1 - kk > 0) {
                     prof_begin(PROF_BACK_INNER, st);
