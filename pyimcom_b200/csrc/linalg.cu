@@ -40,7 +40,7 @@ constexpr int STAGES = 3;
 constexpr int WARPS_M = B200_GEMM_WARPS_M, WARPS_N = 4;  // warp grid over the 128x128 tile
 constexpr int GT = 32 * WARPS_M * WARPS_N;               // threads per GEMM CTA
 constexpr int NI = NB / WARPS_N / 8;  // n8 fragments per warp tile (m8 fragments: 8 for a full tile, 4 for a half tile)
-constexpr int SP = 4;            // block columns per super-panel (512 matrix columns)
+constexpr int SP_DEFAULT = 4;    // block columns per super-panel (512 matrix columns); B200_SP overrides (tuning)
 constexpr int STAGE_DOUBLES = 2 * NB * LDSM;
 constexpr size_t GEMM_SMEM = (size_t)STAGES * STAGE_DOUBLES * sizeof(double);  // 163840 B
 
@@ -330,7 +330,7 @@ __global__ void __launch_bounds__(T64 ? GT2 : GT, T64 ? 3 : 1) k_chol_super_upda
     const int K = c0 * NB;
     if (t < nrow) {
         const int i = c0 + t;
-        if (j > i) return;
+        if (j > i || (T64 && i == j && qn > qm)) return;  // (the upper quadrant of a diagonal tile is never read)
         update_tile<TILE_SUB, T64>(false, qm, qn, s.W + (size_t)i * NB * s.ldw, s.ldw, Bp, s.ldw,
                                    s.W + (size_t)i * NB * s.ldw + (size_t)j * NB, s.ldw, K, smem);
     } else {
@@ -388,7 +388,7 @@ __global__ void __launch_bounds__(T64 ? GT2 : GT, T64 ? 3 : 1) k_chol_update(Sol
     const double* Bp = s.W + (size_t)j * NB * s.ldw + (size_t)k * NB;
     if (t < nrow) {
         const int i = k + 1 + t;
-        if (j > i) return;
+        if (j > i || (T64 && i == j && qn > qm)) return;
         update_tile<TILE_SUB, T64>(false, qm, qn, s.W + (size_t)i * NB * s.ldw + (size_t)k * NB, s.ldw, Bp, s.ldw,
                                    s.W + (size_t)i * NB * s.ldw + (size_t)j * NB, s.ldw, NB, smem);
     } else {
@@ -642,6 +642,7 @@ __global__ void k_transpose(const double* __restrict__ A, int lda, double* __res
 
 bool g_attr_done = false;
 bool g_tile64 = true;
+int g_sp = SP_DEFAULT;
 int gemm_attrs() {
     if (g_attr_done) return 0;
     B200_CUDA(cudaFuncSetAttribute(k_gemm_nt<TILE_ASSIGN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM));
@@ -663,6 +664,8 @@ int gemm_attrs() {
     {
         const char* e = getenv("B200_TILE64");  // 0: the 128x128 one-CTA-per-SM tile everywhere (A/B comparisons)
         g_tile64 = !(e && e[0] == '0');
+        const char* sp = getenv("B200_SP");
+        if (sp && atoi(sp) >= 1 && atoi(sp) <= 64) g_sp = atoi(sp);
     }
     B200_CUDA(cudaFuncSetAttribute(k_potrf_diag, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)POTRF_SMEM));
     g_attr_done = true;
@@ -704,6 +707,7 @@ int launch_chol_solve(const SolveSys* h_sys, int nsys, int do_factor, int do_sol
             for (int j = c0; j < c1 && j < nb; j++) {
                 const int ifrom = rows_from > j ? rows_from : j;
                 t += (nb - ifrom > 0 ? nb - ifrom : 0) + mb;
+                if (g_tile64 && ifrom == j && nb > j) t -= 0.25;  // diagonal tile: three of its four quadrants
             }
         }
         return t;
@@ -711,6 +715,7 @@ int launch_chol_solve(const SolveSys* h_sys, int nsys, int do_factor, int do_sol
     const double tile_flops = 2.0 * NB * NB;
     const double tri = g_tile64 ? 0.75 : 1.0;  // the strip kernels skip the zero quarter of the triangular inverse
     if (do_factor) {
+        const int SP = g_sp;
         for (int c0 = 0; c0 < nbmax; c0 += SP) {
             const int c1 = c0 + SP < nbmax ? c0 + SP : nbmax;
             if (c0 > 0) {
@@ -753,6 +758,7 @@ int launch_chol_solve(const SolveSys* h_sys, int nsys, int do_factor, int do_sol
     if (do_solve && mbmax > 0) {
         double mbsum = 0;
         for (int q = 0; q < nsys; q++) mbsum += mb_eff(q);
+        const int SP = g_sp;
         for (int e0 = 0; e0 < nbmax; e0 += SP) {
             const int e1 = e0 + SP < nbmax ? e0 + SP : nbmax;
             if (e0 > 0) {
