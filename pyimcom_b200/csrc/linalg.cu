@@ -14,8 +14,9 @@
 //
 // With rows as right-hand sides the solve is   Z = X L^-T  (forward, fused into the factorisation:
 // the X rows are simply extra panel rows below the matrix) followed by  Ti = Z L^-1  (backward).
-// Every product is  C (+)= A[.,K] * B[.,K]^T  with both operands K-contiguous, so one tile kernel
-// (128x128x16 stages, 4-stage cp.async ring, 8 warps of 64x32, DMMA.8x8x4) serves all phases.
+// Every product is  C (+)= A[.,K] * B[.,K]^T  with both operands K-contiguous, so one tile routine serves all
+// phases: gemm_tile64 (64x64 output, 4 warps of 32x32, K stages of 16 in a 4-deep cp.async ring, three CTAs per SM,
+// DMMA.8x8x4).  gemm_tile_nt is the 128x128 / 256-thread tile it replaced, kept selectable (B200_TILE64=0).
 #include <cstdlib>
 
 #include "common.cuh"
