@@ -179,9 +179,10 @@ def test_build_reduced_T(gr):
 # ---------------------------------------------------------------------------------------------------
 # dense linear algebra building blocks
 # ---------------------------------------------------------------------------------------------------
-def test_gemm_nt():
+@pytest.mark.parametrize("K", [208, 210, 8, 1042])  # whole stages, a K tail, less than one stage, a long ring
+def test_gemm_nt(K):
     rng = np.random.default_rng(1)
-    M, N, K = 256, 384, 208
+    M, N = 256, 384
     A, B, Cm = rng.standard_normal((M, K)), rng.standard_normal((N, K)), rng.standard_normal((M, N))
     dA, dB = torch.from_numpy(A).cuda(), torch.from_numpy(B).cuda()
     for acc, want in ((0, A @ B.T), (1, Cm + A @ B.T), (-1, Cm - A @ B.T)):
@@ -212,6 +213,19 @@ def test_chol_solve_random(n, m):
     assert rel(got, ref) < 1e-9
     L = np.tril(W[:n, :n].cpu().numpy())
     assert rel(L @ L.T, A) < 1e-13
+
+
+def test_legacy_tile_path():
+    """B200_TILE64=0 (the 128x128 one-CTA-per-SM tile, kept for A/B comparisons) is read once per process: run the dense
+    linear-algebra tests again in a child process with it."""
+    import subprocess
+    import sys
+
+    env = dict(os.environ, B200_TILE64="0")
+    r = subprocess.run([sys.executable, "-m", "pytest", __file__, "-q", "-x", "-m", "gpu", "-p", "no:cacheprovider", "-k",
+                        "test_gemm_nt or test_chol_solve_random or test_chol_info_nonpd"], env=env, capture_output=True,
+                       text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
 
 
 def test_chol_info_nonpd():
