@@ -275,6 +275,17 @@ int b200_dev_stamp_maps(const double* kappa, const double* Sigma, const double* 
 int b200_dev_accumulate(const void* src, int src_is_f64, int nlayer, int n2f, float* dst, int side, int y0, int x0,
                         void* stream);
 
+/* ---- 6. device: block output assembly (Block.build_output_file, coadd.py:2139-2176) ---------- */
+/* out (nlayer, side-2fk, side-2fk) = in (nlayer, side, side) without its fade margin.  recover != 0 first divides the
+ * trapezoid weights fade_w[0 .. 2fk-1] back out of the block boundary exactly as OutStamp.trapezoid(arr, fk,
+ * recover_mode=True, pad_widths=(pb, pt, pl, pr)) does (coadd.py:1262-1292: sides B, T, L, R in turn, each division in
+ * float64 rounded to float32).  in is not modified. */
+int b200_dev_unfade_crop(const float* in, int nlayer, int side, int fk, int recover, int pb, int pt, int pl, int pr,
+                         const double* fade_w, float* out, void* stream);
+/* Block.compress_map (coadd.py:2086-2137): out[i] = clip(floor(coef * log10(max(in[i], 1e-32)) + 0.5), lo, hi) as
+ * uint16 (is_unsigned, range 0..65535) or int16 (-32768..32767); float32 arithmetic as NumPy's, log10 correctly rounded. */
+int b200_dev_compress_map(const float* in, long n, int coef, int is_unsigned, void* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -119,6 +119,8 @@ PROTOTYPES = {
     "b200_dev_finalize": [C.POINTER(FinalizeArgs), vp],
     "b200_dev_stamp_maps": [vp, vp, vp, i32, i32, i32, i32, vp, vp, vp, vp, vp, i32, i32, vp, vp, vp, vp],
     "b200_dev_accumulate": [vp, i32, i32, i32, vp, i32, i32, i32, vp],
+    "b200_dev_unfade_crop": [vp, i32, i32, i32, i32, i32, i32, i32, i32, vp, vp, vp],
+    "b200_dev_compress_map": [vp, C.c_long, i32, i32, vp, vp],
 }
 
 lib.b200_last_error.restype = C.c_char_p

@@ -774,11 +774,71 @@ class GpuBlock:
             finish(pending)
         return self
 
+    def build_output(self, is_final: bool = True, pad_sides: str = "", download: bool = True):
+        """Block.build_output_file up to the FITS container for this block's maps: see assemble_output."""
+        names = ("out_map", "T_weightmap", "UC_map", "Sigma_map", "kappa_map", "Tsum_map", "Neff_map")
+        return assemble_output({nm: getattr(self, nm) for nm in names}, self.cfg, self.blk.n_inimage, is_final,
+                               pad_sides, download)
+
     def download(self):
         """Block maps to host (the final gather of the output cube starts from these)."""
         torch.cuda.current_stream().synchronize()
         names = ("out_map", "T_weightmap", "UC_map", "Sigma_map", "kappa_map", "Tsum_map", "Neff_map")
         return {nm: getattr(self, nm).cpu().numpy() for nm in names}
+
+
+# quality maps of cfg.outmaps: letter -> (block map, EXTNAME, coefficient, unsigned) (coadd.py:2245-2303)
+OUTPUT_ENCODING = {"U": ("UC_map", "FIDELITY", -5000, True), "S": ("Sigma_map", "SIGMA", -10000, False),
+                   "K": ("kappa_map", "KAPPA", -5000, True), "T": ("Tsum_map", "INWTSUM", 200000, False),
+                   "N": ("Neff_map", "EFFCOVER", 50000, True)}
+
+
+def assemble_output(maps, cfg, n_inimage: int, is_final: bool = True, pad_sides: str = "", download: bool = True):
+    """Block.build_output_file up to the FITS container (coadd.py:2139-2303), on the device.
+
+    maps: float32 CUDA tensors out_map (n_out, n_inframe, side, side), T_weightmap (n_out, n_inimage, n1P, n1P) and the
+    quality maps UC_map / Sigma_map / kappa_map / Tsum_map / Neff_map (n_out, side, side), side = NsideP + 2 fade_kernel.
+    The faded block boundary is recovered (is_final), the fade margin cropped, and the quality maps named in
+    cfg.outmaps are log-encoded to (u)int16.  Returns {EXTNAME: array}: PRIMARY, INWEIGHT, INWTFLAT, FIDELITY, SIGMA,
+    KAPPA, INWTSUM, EFFCOVER, as NumPy arrays (download=True: 2 bytes per quality-map pixel cross PCIe instead of 4)
+    or device tensors (the unsigned codes then sit in int16 storage).  The input maps are not modified.
+    pad_sides: the sides this block pads ("BTLR" subset, Block._handle_postage_pad, coadd.py:1810-1837)."""
+    st = stream_handle()
+    fk = cfg.fade_kernel
+    side = cfg.NsideP + 2 * fk
+    so = side - 2 * fk
+    width = cfg.postage_pad * cfg.n2
+    d_w = h2d(trapezoid_weights(fk)) if fk > 0 else None
+
+    def crop(src, pads):
+        flat = src.contiguous().reshape(-1, side, side)
+        dst = torch.empty((flat.shape[0], so, so), dtype=torch.float32, device="cuda")
+        _lib.dev_unfade_crop(ptr(flat), flat.shape[0], side, fk, int(bool(is_final)), *pads, ptr(d_w), ptr(dst), st)
+        return dst.reshape(tuple(src.shape[:-2]) + (so, so))
+
+    T_w = maps["T_weightmap"]
+    n_out = T_w.shape[0]
+    out = {"PRIMARY": crop(maps["out_map"], (0, 0, 0, 0)), "INWEIGHT": T_w.clone(),
+           "INWTFLAT": T_w.permute(0, 2, 1, 3).reshape(n_out * cfg.n1P, n_inimage * cfg.n1P)}
+    pads = tuple(width * (sd not in pad_sides) for sd in "BTLR")
+    outmaps = getattr(cfg, "outmaps", "USKTN")
+    for letter in "USKTN":
+        if letter not in outmaps:
+            continue
+        name, ext, coef, unsigned = OUTPUT_ENCODING[letter]
+        cropped = crop(maps[name], pads)
+        # (torch has no uint16 arithmetic: unsigned codes are written into int16 storage and re-viewed on the host)
+        codes = torch.empty(cropped.shape, dtype=torch.int16, device="cuda")
+        _lib.dev_compress_map(ptr(cropped), cropped.numel(), coef, int(unsigned), ptr(codes), st)
+        out[ext] = codes
+    if not download:
+        return out
+    torch.cuda.current_stream().synchronize()
+    host = {k: v.contiguous().cpu().numpy() for k, v in out.items()}
+    for name, ext, coef, unsigned in OUTPUT_ENCODING.values():
+        if unsigned and ext in host:
+            host[ext] = host[ext].view(np.uint16)
+    return host
 
 
 class GpuOutStamp:

@@ -422,5 +422,12 @@ int b200_dev_accumulate(const void* src, int src_is_f64, int nlayer, int n2f, fl
                         void* s) {
     return launch_accumulate(src, src_is_f64, nlayer, n2f, dst, side, y0, x0, ST(s));
 }
+int b200_dev_unfade_crop(const float* in, int nlayer, int side, int fk, int recover, int pb, int pt, int pl, int pr,
+                         const double* fade_w, float* out, void* s) {
+    return launch_unfade_crop(in, nlayer, side, fk, recover, pb, pt, pl, pr, fade_w, out, ST(s));
+}
+int b200_dev_compress_map(const float* in, long n, int coef, int is_unsigned, void* out, void* s) {
+    return launch_compress_map(in, n, coef, is_unsigned, out, ST(s));
+}
 
 }  // extern "C"

@@ -3,6 +3,9 @@
 //                  (fade T, float32 cast, Tsum per input image, outimage = T . indata)
 //   k_stamp_maps   coadd.py:1104-1122, 1339-1350 (clamp, fade the U/S/K maps, Tsum_stamp/inpix, Neff)
 //   k_accumulate   coadd.py:1976-1994 (overlap-add of one stamp into the block cube / maps)
+//   k_unfade_crop  coadd.py:2156-2176, 1284-1292 (block output assembly, SURVEY 8f row f3: recover the faded block
+//                  boundary, crop the fade margin)
+//   k_compress_map coadd.py:2086-2137 (log-integer encoding of the quality maps)
 //
 // k_finalize is the HBM-bound T-apply: it reads the f64 node solutions once (8*nv*m*n B) plus -B/2
 // (8*m*n B), writes the float32 T (4*m*n B) and produces everything else from registers/shared memory.
@@ -246,6 +249,54 @@ __global__ void __launch_bounds__(256) k_accumulate64(const double* __restrict__
     }
 }
 
+
+// ---- block output assembly (coadd.py:2086-2328) -----------------------------------
+// Block.build_output_file(is_final=True) divides the trapezoid weights back out of the block boundary
+// (OutStamp.trapezoid(recover_mode=True): sides B, T, L, R in that order, each "arr /= s" computed in float64 and rounded
+// back to float32, coadd.py:1284-1292) and stores the maps without the fade margin [fk : side - fk].  One pass: read
+// the (nlayer, side, side) map, write the cropped (nlayer, side - 2 fk, side - 2 fk) map; the block map itself is not
+// modified.  recover = 0 only crops (intermediate outputs).
+__global__ void __launch_bounds__(256) k_unfade_crop(const float* __restrict__ in, int nlayer, int side, int fk,
+                                                     int recover, int pb, int pt, int pl, int pr,
+                                                     const double* __restrict__ s, float* __restrict__ out) {
+    const int so = side - 2 * fk, fk2 = 2 * fk;
+    const int it = side - pt - 1, ir = side - pr - 1;
+    const long tot = (long)nlayer * so * so;
+    for (long t = (long)blockIdx.x * blockDim.x + threadIdx.x; t < tot; t += (long)gridDim.x * blockDim.x) {
+        const int l = (int)(t / ((long)so * so));
+        const int a = (int)(t - (long)l * so * so);
+        const int iy = a / so + fk, ix = a - (a / so) * so + fk;
+        float v = in[((size_t)l * side + iy) * side + ix];
+        if (recover && fk2 > 0) {
+            if (iy >= pb && iy < pb + fk2) v = (float)((double)v / s[iy - pb]);
+            if (iy <= it && iy > it - fk2) v = (float)((double)v / s[it - iy]);
+            if (ix >= pl && ix < pl + fk2) v = (float)((double)v / s[ix - pl]);
+            if (ix <= ir && ix > ir - fk2) v = (float)((double)v / s[ir - ix]);
+        }
+        out[t] = v;
+    }
+}
+
+// Block.compress_map (coadd.py:2129-2131):  clip(floor(coef * log10(clip(x, 1e-32, None)) + 0.5), lo, hi).astype(int16 or
+// uint16), every step in float32 as NumPy evaluates it for a float32 map.  log10 is taken in float64 and rounded to
+// float32 (the correctly rounded float32 logarithm); NumPy's own float32 log10 is whatever libm / SVML kernel the host
+// dispatches to (< 1 ulp, not always correctly rounded), so codes can differ from a given host by one count on the few
+// pixels whose scaled logarithm lies within a float32 ulp of a rounding boundary -- the tests bound both the size (1)
+// and the rate of such differences.
+__global__ void __launch_bounds__(256) k_compress_map(const float* __restrict__ in, long n, float coef, float lo, float hi,
+                                                      int is_unsigned, void* __restrict__ out) {
+    for (long t = (long)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (long)gridDim.x * blockDim.x) {
+        const float x = fmaxf(in[t], 1e-32f);
+        const float lg = (float)log10((double)x);
+        float v = floorf(__fadd_rn(__fmul_rn(coef, lg), 0.5f));
+        v = fminf(fmaxf(v, lo), hi);
+        if (is_unsigned)
+            ((unsigned short*)out)[t] = (unsigned short)(int)v;
+        else
+            ((short*)out)[t] = (short)(int)v;
+    }
+}
+
 }  // namespace
 
 size_t finalize_smem(int nseg) {
@@ -294,6 +345,30 @@ int launch_accumulate(const void* src, int src_is_f64, int nlayer, int n2f, floa
         k_accumulate64<<<grid, 256, 0, s>>>((const double*)src, nlayer, n2f, dst, side, y0, x0);
     else
         k_accumulate<<<grid, 256, 0, s>>>((const float*)src, nlayer, n2f, dst, side, y0, x0);
+    B200_LAUNCH_CHECK();
+    return 0;
+}
+
+int launch_unfade_crop(const float* in, int nlayer, int side, int fk, int recover, int pb, int pt, int pl, int pr,
+                       const double* fade_w, float* out, cudaStream_t s) {
+    const int so = side - 2 * fk;
+    if (nlayer <= 0 || so <= 0) return 0;
+    B200_REQUIRE(fk >= 0 && pb >= 0 && pt >= 0 && pl >= 0 && pr >= 0, "unfade_crop: negative widths");
+    B200_REQUIRE(!recover || fk == 0 || (fade_w != nullptr && side > 4 * fk + pb + pt && side > 4 * fk + pl + pr),
+                 "unfade_crop: map too small for its fade and padding widths");
+    const long tot = (long)nlayer * so * so;
+    const long grid = (tot + 255) / 256;
+    k_unfade_crop<<<(unsigned)(grid < 148 * 32 ? grid : 148 * 32), 256, 0, s>>>(in, nlayer, side, fk, recover, pb, pt, pl,
+                                                                            pr, fade_w, out);
+    B200_LAUNCH_CHECK();
+    return 0;
+}
+
+int launch_compress_map(const float* in, long n, int coef, int is_unsigned, void* out, cudaStream_t s) {
+    if (n <= 0) return 0;
+    const long grid = (n + 255) / 256;
+    k_compress_map<<<(unsigned)(grid < 148 * 32 ? grid : 148 * 32), 256, 0, s>>>(
+        in, n, (float)coef, is_unsigned ? 0.0f : -32768.0f, is_unsigned ? 65535.0f : 32767.0f, is_unsigned, out);
     B200_LAUNCH_CHECK();
     return 0;
 }

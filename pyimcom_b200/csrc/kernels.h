@@ -103,5 +103,8 @@ int launch_stamp_maps(const double* kappa, const double* Sigma, const double* UC
                       cudaStream_t s);
 int launch_accumulate(const void* src, int src_is_f64, int nlayer, int n2f, float* dst, int side, int y0, int x0,
                       cudaStream_t s);
+int launch_unfade_crop(const float* in, int nlayer, int side, int fk, int recover, int pb, int pt, int pl, int pr,
+                       const double* fade_w, float* out, cudaStream_t s);
+int launch_compress_map(const float* in, long n, int coef, int is_unsigned, void* out, cudaStream_t s);
 
 }  // namespace b200

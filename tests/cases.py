@@ -159,3 +159,51 @@ def make_block(spec):
             kw[k] = spec[k]
     cfg = StampConfig(**kw)
     return SynthBlock(cfg, n_image=spec["n_image"], seed=spec["seed"])
+
+
+# ---------------------------------------------------------------------------------------------------
+# block output assembly: seeded block maps as they stand after coadd_output_stamps
+# ---------------------------------------------------------------------------------------------------
+OUTPUT_CASES = {  # name -> (config overrides, n_inimage, pad_sides of the block, is_final)
+    "final_nopad": (dict(n1=2, n2=8, fade_kernel=2, postage_pad=1, n_out=2, n_inframe=3), 4, "", True),
+    "final_BL": (dict(n1=2, n2=8, fade_kernel=2, postage_pad=1, n_out=1, n_inframe=2), 3, "BL", True),
+    "final_all_fk1": (dict(n1=3, n2=6, fade_kernel=1, postage_pad=2, n_out=1, n_inframe=1, outmaps="USK"), 2, "BTLR", True),
+    "intermediate": (dict(n1=2, n2=8, fade_kernel=2, postage_pad=1, n_out=1, n_inframe=2), 3, "", False),
+}
+
+
+def output_case(name):
+    """(cfg, maps, n_inimage, pad_sides, is_final): float32 block maps with the value ranges of real ones plus the
+    corners of the encoding (zeros, negatives, values that saturate the 16-bit codes)."""
+    from pyimcom_b200.synth import StampConfig
+
+    over, n_inimage, pad_sides, is_final = OUTPUT_CASES[name]
+    cfg = StampConfig(**over)
+    rng = np.random.default_rng(sum(map(ord, name)))
+    side = cfg.NsideP + 2 * cfg.fade_kernel
+    q = (cfg.n_out, side, side)
+    maps = {
+        "out_map": rng.standard_normal((cfg.n_out, cfg.n_inframe, side, side)),
+        "T_weightmap": rng.uniform(0.0, 0.4, (cfg.n_out, n_inimage, cfg.n1P, cfg.n1P)),
+        "UC_map": 10.0 ** rng.uniform(-9.0, 0.2, q),
+        "Sigma_map": 10.0 ** rng.uniform(-3.5, 3.5, q),
+        "kappa_map": 10.0 ** rng.uniform(-14.0, -1.0, q),
+        "Tsum_map": 1.0 + 0.05 * rng.standard_normal(q),
+        "Neff_map": rng.uniform(0.3, 8.0, q),
+    }
+    for k in ("UC_map", "Sigma_map", "kappa_map", "Tsum_map", "Neff_map"):  # encoding corners
+        maps[k][:, 5, 7] = 0.0
+        maps[k][:, 6, 7] = -3.0
+        maps[k][:, 7, 7] = 1e30
+        maps[k][:, 8, 7] = 1e-40
+        maps[k][:, 9, 7] = 1.0
+    return cfg, {k: v.astype(np.float32) for k, v in maps.items()}, n_inimage, pad_sides, is_final
+
+
+def codes_match(got, want, max_frac=0.005):
+    """Log-integer quality-map codes: identical except for at most max_frac of the pixels, and those by one count
+    (the float32 log10 of the host that produced `want` is not necessarily correctly rounded; see k_compress_map)."""
+    got, want = np.asarray(got), np.asarray(want)
+    assert got.dtype == want.dtype and got.shape == want.shape, (got.dtype, want.dtype, got.shape, want.shape)
+    d = np.abs(got.astype(np.int64) - want.astype(np.int64))
+    return d.max() <= 1 and (d > 0).mean() <= max_frac

@@ -101,9 +101,37 @@ def block_vectors():
         print("wrote", name, {k: v.shape for k, v in out.items() if k.endswith("_T")})
 
 
+def output_vectors(ref):
+    """Block.build_output_file's array work (coadd.py:2156-2303) by the reference's own OutStamp.trapezoid and
+    Block.compress_map on the seeded block maps of cases.output_case."""
+    trap, comp = ref.coadd.OutStamp.trapezoid, ref.coadd.Block.compress_map
+    enc = {"U": ("UC_map", "FIDELITY", -5000, np.uint16), "S": ("Sigma_map", "SIGMA", -10000, np.int16),
+           "K": ("kappa_map", "KAPPA", -5000, np.uint16), "T": ("Tsum_map", "INWTSUM", 200000, np.int16),
+           "N": ("Neff_map", "EFFCOVER", 50000, np.uint16)}
+    out = {}
+    for name in cases.OUTPUT_CASES:
+        cfg, maps, n_inimage, pad_sides, is_final = cases.output_case(name)
+        fk = cfg.fade_kernel
+        NsidePf = cfg.NsideP + fk * 2
+        if is_final:  # coadd.py:2161-2176
+            trap(maps["out_map"], fk, recover_mode=True)
+            width = cfg.postage_pad * cfg.n2
+            pads = tuple(width * (sd not in pad_sides) for sd in "BTLR")
+            for letter in cfg.outmaps:
+                trap(maps[enc[letter][0]], fk, True, pads)
+        out[name + "_PRIMARY"] = maps["out_map"][:, :, fk:NsidePf - fk, fk:NsidePf - fk]
+        out[name + "_INWTFLAT"] = np.transpose(maps["T_weightmap"], axes=(0, 2, 1, 3)).reshape(
+            (cfg.n_out * cfg.n1P, n_inimage * cfg.n1P))  # coadd.py:2238-2241
+        for letter in cfg.outmaps:
+            mname, ext, coef, dt = enc[letter]
+            out[name + "_" + ext] = comp(maps[mname][:, fk:NsidePf - fk, fk:NsidePf - fk], coef, dt)
+    return out
+
+
 if __name__ == "__main__":
     assert refhost.available(), "needs /root/reference (build container)"
     ref = refhost.load()
     np.savez_compressed(os.path.join(HERE, "routine.npz"), **routine_vectors(ref))
     np.savez_compressed(os.path.join(HERE, "la.npz"), **la_vectors(ref))
+    np.savez_compressed(os.path.join(HERE, "output.npz"), **output_vectors(ref))
     block_vectors()

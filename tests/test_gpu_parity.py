@@ -490,3 +490,50 @@ def test_kernel_without_input_pixels(kern):
     assert outst.T.shape == (1, 16, 0) and outst.T.dtype == np.float32
     assert np.all(outst.UC == 1) and np.all(outst.kappa == 1) and np.all(outst.Sigma == 0)
     assert outst.UC.shape == (1, 4, 4) and outst.UC.dtype == np.float32
+
+
+# ---------------------------------------------------------------------------------------------------
+# block output assembly
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", list(cases.OUTPUT_CASES))
+def test_output_assembly(name, golden_dir):
+    """Device un-fade + crop + log-integer encoding against the oracle and against the arrays the reference itself
+    produced (tests/golden/output.npz).  P-f32 here is exact (same float64 division rounded to float32); the 16-bit
+    codes are identical up to one count on <= 0.5 % of the pixels (float32 log10 of the host, cases.codes_match)."""
+    from oracle import output as OO
+    from pyimcom_b200.coadd import assemble_output
+
+    g = np.load(os.path.join(golden_dir, "output.npz"))
+    cfg, maps, n_inimage, pad_sides, is_final = cases.output_case(name)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        want = OO.build_output(maps, cfg, n_inimage, is_final, pad_sides)
+    dmaps = {k: torch.from_numpy(v).cuda() for k, v in maps.items()}
+    got = assemble_output(dmaps, cfg, n_inimage, is_final, pad_sides)
+    assert all(torch.equal(dmaps[k].cpu(), torch.from_numpy(maps[k])) for k in maps)  # block maps untouched
+    assert set(got) == set(want)
+    for k in ("PRIMARY", "INWEIGHT", "INWTFLAT"):
+        assert got[k].dtype == np.float32 and np.array_equal(got[k], want[k]), k
+    assert np.array_equal(got["PRIMARY"], g[name + "_PRIMARY"])
+    for e in set(got) - {"PRIMARY", "INWEIGHT", "INWTFLAT"}:
+        assert cases.codes_match(got[e], want[e]), e
+        assert cases.codes_match(got[e], g[name + "_" + e]), e
+
+
+def test_output_assembly_of_a_block(golden_dir):
+    """GpuBlock.build_output on the maps of a coadded block equals the oracle's assembly of the downloaded maps."""
+    from oracle import output as OO
+
+    spec = cases.BLOCK_CASES["chol1"]
+    blk = cases.make_block(spec)
+    tab = PSFTables(blk, G.iD5512C, G.gridD5512C)
+    gb = GpuBlock(blk, tab).prepare().run()
+    maps = gb.download()
+    got = gb.build_output(is_final=True, pad_sides="")
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        want = OO.build_output(maps, blk.cfg, blk.n_inimage, True, "")
+    assert np.array_equal(got["PRIMARY"], want["PRIMARY"]) and np.array_equal(got["INWTFLAT"], want["INWTFLAT"])
+    for e in ("FIDELITY", "SIGMA", "KAPPA", "INWTSUM", "EFFCOVER"):
+        assert cases.codes_match(got[e], want[e], max_frac=0.01), e
+    assert np.array_equal(gb.download()["out_map"], maps["out_map"])

@@ -182,3 +182,32 @@ def test_oracle_ii_cache_is_transparent():
         b.build_system_matrices()
         assert np.array_equal(a.sysmata, b.sysmata) and np.array_equal(a.mhalfb, b.mhalfb)
     assert len(cache) < 3 * 45  # neighbouring stamps share blocks
+
+
+@pytest.mark.parametrize("name", list(cases.OUTPUT_CASES))
+def test_output_assembly_vs_reference(name, golden_dir):
+    """oracle/output.py against what the reference's OutStamp.trapezoid(recover_mode=True) and
+    Block.compress_map produced on the same block maps (coadd.py:2086-2303)."""
+    from oracle import output as OO
+
+    g = np.load(os.path.join(golden_dir, "output.npz"))
+    cfg, maps, n_inimage, pad_sides, is_final = cases.output_case(name)
+    before = {k: v.copy() for k, v in maps.items()}
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        out = OO.build_output(maps, cfg, n_inimage, is_final, pad_sides)
+    assert all(np.array_equal(maps[k], before[k]) for k in maps)  # inputs untouched
+    assert np.array_equal(out["PRIMARY"], g[name + "_PRIMARY"])  # float32 divisions in the reference's order: identical
+    assert np.array_equal(out["INWTFLAT"], g[name + "_INWTFLAT"])
+    exts = [e for e in ("FIDELITY", "SIGMA", "KAPPA", "INWTSUM", "EFFCOVER") if name + "_" + e in g.files]
+    assert len(exts) == len(cfg.outmaps) and set(exts) == set(out) - {"PRIMARY", "INWEIGHT", "INWTFLAT"}
+    for e in exts:
+        assert cases.codes_match(out[e], g[name + "_" + e]), e
+    # the corners of the encoding: x <= 1e-32 saturates, 1.0 encodes as 0
+    fk = cfg.fade_kernel
+    if "T" in cfg.outmaps and not is_final:
+        col = out["INWTSUM"][0, :, 7 - fk]
+        assert col[5 - fk] == -32768 and col[6 - fk] == -32768 and col[7 - fk] == 32767 and col[9 - fk] == 0
+    if not is_final:
+        col = out["FIDELITY"][0, :, 7 - fk]
+        assert col[5 - fk] == 65535 and col[7 - fk] == 0 and col[9 - fk] == 0
