@@ -286,6 +286,35 @@ int b200_dev_unfade_crop(const float* in, int nlayer, int side, int fk, int reco
  * uint16 (is_unsigned, range 0..65535) or int16 (-32768..32767); float32 arithmetic as NumPy's, log10 correctly rounded. */
 int b200_dev_compress_map(const float* in, long n, int coef, int is_unsigned, void* out, void* stream);
 
+/* ---- 7. device: input-pixel partitioning (InImage.partition_pixels / extract_layers,
+ *         coadd.py:333-360, 382-408) ------------------------------------------------------------------------ */
+#define B200_PART_MAXSLOT 256 /* postage stamps one sparse-grid cell may touch */
+/* One relevant cell of the sparse grid: detector rows bottom .. bottom+h-1, columns left .. left+w-1; its h*w output
+ * positions start at ox[off], oy[off] in raster order (row by row), as _inpix2world2outpix returns them. */
+typedef struct b200_part_cell {
+    int bottom, left, h, w;
+    long long off;
+} b200_part_cell;
+/* The double loop of coadd.py:333-360 for the ncell relevant cells, in the order given (the reference's traversal).
+ * A pixel is kept when lower < x < upper and lower < y < upper (lower = -n2 - 0.5, upper = NsideP + n2 - 0.5), its
+ * mask byte (sca x sca) is non-zero and its stamp (j_st, i_st) = ((y - lower) // n2, (x - lower) // n2) has use[] set
+ * (ns x ns, ns = n1P + 2).  Outputs with the reference's layout: pix_count (ns*ns) u32; y_idx, x_idx (ns*ns, npixmax)
+ * u16; y_val, x_val (ns*ns, npixmax) f64, each stamp's list in traversal order (entries beyond pix_count are left
+ * untouched: pass zero-filled arrays).  Scratch: sid_tmp (int) and rank_tmp (u32) per position, cellmeta (4 ints),
+ * cellcnt and cellbase (B200_PART_MAXSLOT u32) per cell, run (ns*ns u32).  err (device int) is 0 on success, 1 if a
+ * cell touches more than B200_PART_MAXSLOT stamps, 2 if a stamp receives more than npixmax pixels (the reference would
+ * raise IndexError). */
+int b200_dev_partition(const b200_part_cell* cells, int ncell, const double* ox, const double* oy,
+                       const unsigned char* mask, int sca, const unsigned char* use, int ns, int n2, double lower,
+                       double upper, int npixmax, int* sid_tmp, unsigned* rank_tmp, int* cellmeta, unsigned* cellcnt,
+                       unsigned* cellbase, unsigned* run, unsigned* pix_count, unsigned short* y_idx,
+                       unsigned short* x_idx, double* y_val, double* x_val, int* err, void* stream);
+/* InImage.extract_layers (coadd.py:396-404): data (n_inframe, nstamp, max_count) f32 = indata (n_inframe, sca, sca) at
+ * the listed pixels, zero beyond pix_count. */
+int b200_dev_extract_layers(const float* indata, int n_inframe, int sca, const unsigned short* y_idx,
+                            const unsigned short* x_idx, const unsigned* pix_count, int nstamp, int npixmax,
+                            int max_count, float* data, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

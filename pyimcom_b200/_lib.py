@@ -55,6 +55,13 @@ class PairDesc(C.Structure):
                 ("lut", i32), ("same", i32), ("pad_", i32)]
 
 
+PART_MAXSLOT = 256  # B200_PART_MAXSLOT
+
+
+class PartCell(C.Structure):
+    _fields_ = [("bottom", C.c_int), ("left", C.c_int), ("h", C.c_int), ("w", C.c_int), ("off", C.c_longlong)]
+
+
 class AsmDesc(C.Structure):
     """b200_asm_desc"""
 
@@ -121,6 +128,9 @@ PROTOTYPES = {
     "b200_dev_accumulate": [vp, i32, i32, i32, vp, i32, i32, i32, vp],
     "b200_dev_unfade_crop": [vp, i32, i32, i32, i32, i32, i32, i32, i32, vp, vp, vp],
     "b200_dev_compress_map": [vp, C.c_long, i32, i32, vp, vp],
+    "b200_dev_partition": [vp, i32, vp, vp, vp, i32, vp, i32, i32, f64, f64, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp,
+                           vp, vp, vp],
+    "b200_dev_extract_layers": [vp, i32, i32, vp, vp, vp, i32, i32, i32, vp, vp],
 }
 
 lib.b200_last_error.restype = C.c_char_p

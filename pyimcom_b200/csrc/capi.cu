@@ -429,5 +429,18 @@ int b200_dev_unfade_crop(const float* in, int nlayer, int side, int fk, int reco
 int b200_dev_compress_map(const float* in, long n, int coef, int is_unsigned, void* out, void* s) {
     return launch_compress_map(in, n, coef, is_unsigned, out, ST(s));
 }
+int b200_dev_partition(const b200_part_cell* cells, int ncell, const double* ox, const double* oy,
+                       const unsigned char* mask, int sca, const unsigned char* use, int ns, int n2, double lower,
+                       double upper, int npixmax, int* sid_tmp, unsigned* rank_tmp, int* cellmeta, unsigned* cellcnt,
+                       unsigned* cellbase, unsigned* run, unsigned* pix_count, unsigned short* y_idx,
+                       unsigned short* x_idx, double* y_val, double* x_val, int* err, void* s) {
+    return launch_partition(cells, ncell, ox, oy, mask, sca, use, ns, n2, lower, upper, npixmax, sid_tmp, rank_tmp,
+                            cellmeta, cellcnt, cellbase, run, pix_count, y_idx, x_idx, y_val, x_val, err, ST(s));
+}
+int b200_dev_extract_layers(const float* indata, int n_inframe, int sca, const unsigned short* y_idx,
+                            const unsigned short* x_idx, const unsigned* pix_count, int nstamp, int npixmax,
+                            int max_count, float* data, void* s) {
+    return launch_extract_layers(indata, n_inframe, sca, y_idx, x_idx, pix_count, nstamp, npixmax, max_count, data, ST(s));
+}
 
 }  // extern "C"

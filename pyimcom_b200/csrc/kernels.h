@@ -14,6 +14,7 @@ using SolveSys = ::b200_solve_sys;
 using FinalizeArgs = ::b200_finalize_args;
 using PairDesc = ::b200_pair_desc;
 using AsmDesc = ::b200_asm_desc;
+using PartCell = ::b200_part_cell;
 using EighProblem = ::b200_eigh_problem;
 
 constexpr int NB = B200_NB;      // Cholesky/TRSM block size == DMMA GEMM tile edge
@@ -106,5 +107,13 @@ int launch_accumulate(const void* src, int src_is_f64, int nlayer, int n2f, floa
 int launch_unfade_crop(const float* in, int nlayer, int side, int fk, int recover, int pb, int pt, int pl, int pr,
                        const double* fade_w, float* out, cudaStream_t s);
 int launch_compress_map(const float* in, long n, int coef, int is_unsigned, void* out, cudaStream_t s);
+int launch_partition(const PartCell* cells, int ncell, const double* ox, const double* oy, const unsigned char* mask,
+                     int sca, const unsigned char* use, int ns, int n2, double lower, double upper, int npixmax,
+                     int* sid_tmp, unsigned* rank_tmp, int* cellmeta, unsigned* cellcnt, unsigned* cellbase,
+                     unsigned* run, unsigned* pix_count, unsigned short* y_idx, unsigned short* x_idx, double* y_val,
+                     double* x_val, int* err, cudaStream_t s);
+int launch_extract_layers(const float* indata, int n_inframe, int sca, const unsigned short* y_idx,
+                          const unsigned short* x_idx, const unsigned* pix_count, int nstamp, int npixmax, int max_count,
+                          float* data, cudaStream_t s);
 
 }  // namespace b200

@@ -207,3 +207,43 @@ def codes_match(got, want, max_frac=0.005):
     assert got.dtype == want.dtype and got.shape == want.shape, (got.dtype, want.dtype, got.shape, want.shape)
     d = np.abs(got.astype(np.int64) - want.astype(np.int64))
     return d.max() <= 1 and (d > 0).mean() <= max_frac
+
+
+# ---------------------------------------------------------------------------------------------------
+# input-pixel partitioning
+# ---------------------------------------------------------------------------------------------------
+PARTITION_CASES = {  # name -> (config overrides, detector side, sp_res, centre of the block on the detector, rotation)
+    "small_cells": (dict(n1=4, n2=8, postage_pad=1), 600, 40, (301.3, 287.9), 0.31),
+    "uneven_cells": (dict(n1=2, n2=24, postage_pad=0), 1000, 90, (520.4, 610.2), -1.1),
+    "edge_of_detector": (dict(n1=4, n2=8, postage_pad=1), 600, 40, (8.0, 590.0), 2.0),
+    "not_relevant": (dict(n1=2, n2=8, postage_pad=0), 600, 40, (-900.0, 200.0), 0.0),
+}
+
+
+def partition_case(name):
+    """(cfg, outpix, mask_a, mask_b, use_instamps, indata, sca_nside, sp_res): a rotated, slightly distorted pixel map in
+    place of the WCS composition, two random masks (the reference ANDs its permanent / cosmic-ray / file masks), a few
+    postage stamps switched off."""
+    from pyimcom_b200.synth import StampConfig
+
+    over, sca, sp_res, ctr, rot = PARTITION_CASES[name]
+    cfg = StampConfig(dtheta_arcsec=0.04, fade_kernel=1, n_inframe=2, **over)
+    rng = np.random.default_rng(sum(map(ord, name)) + 7)
+    s = 0.11 / 0.04  # output pixels per detector pixel
+    cs, sn = s * np.cos(rot), s * np.sin(rot)
+    mid = cfg.NsideP / 2.0 - 0.5
+
+    def outpix(inxys):
+        d = np.asarray(inxys, dtype=np.float64) - np.asarray(ctr)
+        dx, dy = d[:, 0], d[:, 1]
+        x = cs * dx - sn * dy + 3e-5 * dx * dy + mid
+        y = sn * dx + cs * dy - 2e-5 * dx * dx + mid
+        return np.stack([x, y], axis=1)
+
+    ns = cfg.n1P + 2
+    use = np.ones((ns, ns), dtype=bool)
+    use[0, 0] = use[ns // 2, ns // 2 + 1] = use[ns - 1, 1] = False
+    mask_a = rng.random((sca, sca)) < 0.93
+    mask_b = rng.random((sca, sca)) < 0.97
+    indata = rng.standard_normal((cfg.n_inframe, sca, sca)).astype(np.float32)
+    return cfg, outpix, mask_a, mask_b, use, indata, sca, sp_res

@@ -128,10 +128,46 @@ def output_vectors(ref):
     return out
 
 
+def partition_vectors(ref):
+    """InImage.partition_pixels + extract_layers (coadd.py:174-408) run by the reference itself on a bare InImage whose
+    WCS composition, masks and layer reader are the seeded stand-ins of cases.partition_case."""
+    import types
+
+    co = ref.coadd
+    out = {}
+    saved = (co.Stn.sca_nside, co.get_all_data, co.Mask)
+    try:
+        for name in cases.PARTITION_CASES:
+            cfg, outpix, mask_a, mask_b, use, indata, sca, sp_res = cases.partition_case(name)
+            cfg.inlayercache = None
+            co.Stn.sca_nside = sca
+            co.get_all_data = lambda self, indata=indata: setattr(self, "indata", indata)
+            co.Mask = types.SimpleNamespace(load_cr_mask=lambda self, m=mask_a: m.copy(),
+                                            load_mask_from_maskfile=lambda cfg_, obs, idsca, m=mask_b: m.copy())
+            im = object.__new__(co.InImage)
+            im.blk = types.SimpleNamespace(cfg=cfg, use_instamps=use, pmask=None, timer=ref.config.Timer(), obsdata=None)
+            im.idsca, im.exists_ = (1, 1), True
+            im._inpix2world2outpix = outpix
+            with contextlib.redirect_stdout(io.StringIO()):
+                im.partition_pixels(sp_res=sp_res)
+            out[name + "_is_relevant"] = np.array(im.is_relevant)
+            if not im.is_relevant:
+                continue
+            for k in ("pix_count", "y_idx", "x_idx", "y_val", "x_val"):
+                out[name + "_" + k] = getattr(im, k).copy()
+            with contextlib.redirect_stdout(io.StringIO()):
+                im.extract_layers()
+            out[name + "_data"] = im.data
+    finally:
+        co.Stn.sca_nside, co.get_all_data, co.Mask = saved
+    return out
+
+
 if __name__ == "__main__":
     assert refhost.available(), "needs /root/reference (build container)"
     ref = refhost.load()
     np.savez_compressed(os.path.join(HERE, "routine.npz"), **routine_vectors(ref))
     np.savez_compressed(os.path.join(HERE, "la.npz"), **la_vectors(ref))
     np.savez_compressed(os.path.join(HERE, "output.npz"), **output_vectors(ref))
+    np.savez_compressed(os.path.join(HERE, "partition.npz"), **partition_vectors(ref))
     block_vectors()

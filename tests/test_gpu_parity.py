@@ -537,3 +537,60 @@ def test_output_assembly_of_a_block(golden_dir):
     for e in ("FIDELITY", "SIGMA", "KAPPA", "INWTSUM", "EFFCOVER"):
         assert cases.codes_match(got[e], want[e], max_frac=0.01), e
     assert np.array_equal(gb.download()["out_map"], maps["out_map"])
+
+
+# ---------------------------------------------------------------------------------------------------
+# input-pixel partitioning
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", list(cases.PARTITION_CASES))
+def test_partition(name, golden_dir):
+    """Device binning + layer extraction: identical (index work) to the oracle and to the reference's own arrays."""
+    from oracle import partition as OP
+    from pyimcom_b200.partition import DevicePartition, to_host
+
+    g = np.load(os.path.join(golden_dir, "partition.npz"))
+    cfg, outpix, mask_a, mask_b, use, indata, sca, sp_res = cases.partition_case(name)
+    dp = DevicePartition(cfg, use, sca_nside=sca, sp_res=sp_res)
+    got = to_host(dp.partition(outpix, mask_a & mask_b, indata))
+    assert got["is_relevant"] == bool(g[name + "_is_relevant"])
+    if not got["is_relevant"]:
+        return
+    want = OP.partition_pixels(outpix, mask_a & mask_b, cfg, use, sca_nside=sca, sp_res=sp_res)
+    assert dp.npixmax == want["y_idx"].shape[-1]
+    for k in ("pix_count", "y_idx", "x_idx", "y_val", "x_val"):
+        assert got[k].dtype == want[k].dtype, (k, got[k].dtype)
+        assert np.array_equal(got[k], want[k]), k
+        assert np.array_equal(got[k], g[name + "_" + k]), k
+    assert got["max_count"] == want["max_count"]
+    assert np.array_equal(got["data"], g[name + "_data"])
+
+
+def test_partition_large_cells_and_overflow():
+    """Default-sized cells (45 x 45 detector pixels: several 256-pixel chunks per cell, many pixels per stamp and cell) on
+    a 4088-pixel detector, against the oracle; and the reference's overflow (IndexError) when npixmax is too small."""
+    from oracle import partition as OP
+    from pyimcom_b200.partition import DevicePartition, to_host
+    from pyimcom_b200.synth import StampConfig
+
+    cfg = StampConfig(n1=2, n2=40, postage_pad=1, dtheta_arcsec=0.04, fade_kernel=1)
+    rng = np.random.default_rng(5)
+    s, rot, ctr = 0.11 / 0.04, 0.7, np.array([2010.3, 1977.1])
+    cs, sn = s * np.cos(rot), s * np.sin(rot)
+
+    def outpix(inxys):
+        d = np.asarray(inxys, dtype=np.float64) - ctr
+        return np.stack([cs * d[:, 0] - sn * d[:, 1] + 79.5, sn * d[:, 0] + cs * d[:, 1] + 1e-5 * d[:, 0] ** 2 + 79.5], axis=1)
+
+    ns = cfg.n1P + 2
+    use = np.ones((ns, ns), dtype=bool)
+    use[1, 2] = False
+    mask = rng.random((4088, 4088)) < 0.9
+    dp = DevicePartition(cfg, use)
+    got = to_host(dp.partition(outpix, mask))
+    want = OP.partition_pixels(outpix, mask, cfg, use)
+    assert want["pix_count"].sum() > 5000 and got["n_cells"] >= 9
+    for k in ("pix_count", "y_idx", "x_idx", "y_val", "x_val"):
+        assert np.array_equal(got[k], want[k]), k
+    small = DevicePartition(cfg, use, relax_coef=0.5)
+    with pytest.raises(IndexError):
+        small.partition(outpix, mask)

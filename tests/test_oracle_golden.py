@@ -211,3 +211,28 @@ def test_output_assembly_vs_reference(name, golden_dir):
     if not is_final:
         col = out["FIDELITY"][0, :, 7 - fk]
         assert col[5 - fk] == 65535 and col[7 - fk] == 0 and col[9 - fk] == 0
+
+
+@pytest.mark.parametrize("name", list(cases.PARTITION_CASES))
+def test_partition_vs_reference(name, golden_dir):
+    """oracle/partition.py against the arrays the reference's own InImage.partition_pixels and
+    extract_layers produced (coadd.py:174-408); index work, so everything is identical.  The host-side sparse-grid pass
+    of the product (pyimcom_b200.partition.sparse_relevance) must select the same cells."""
+    from oracle import partition as OP
+    from pyimcom_b200.partition import sparse_relevance
+
+    g = np.load(os.path.join(golden_dir, "partition.npz"))
+    cfg, outpix, mask_a, mask_b, use, indata, sca, sp_res = cases.partition_case(name)
+    part = OP.partition_pixels(outpix, mask_a & mask_b, cfg, use, sca_nside=sca, sp_res=sp_res)
+    assert part["is_relevant"] == bool(g[name + "_is_relevant"])
+    sp_arr = np.linspace(0, sca, sp_res + 1, dtype=np.uint16)
+    rel_p, is_rel_p = sparse_relevance(cfg, use, sp_arr, outpix)
+    assert is_rel_p == part["is_relevant"]
+    if not part["is_relevant"]:
+        return
+    assert np.array_equal(rel_p, part["relevant"])
+    for k in ("pix_count", "y_idx", "x_idx", "y_val", "x_val"):
+        assert part[k].dtype == g[name + "_" + k].dtype and np.array_equal(part[k], g[name + "_" + k]), k
+    assert part["pix_count"].sum() > 300 and not part["pix_count"][~use].any()
+    data = OP.extract_layers(indata, part, cfg)
+    assert np.array_equal(data, g[name + "_data"])
