@@ -64,18 +64,20 @@ class DeviceTables(PSFTables):
             raise RuntimeError("pyimcom_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
         cfg = blk.cfg
         ns, nfft, nc = cfg.nsamp, cfg.nfft, cfg.nc_ovl
-        assert cfg.nsamp_ovl == ns and 2 * nc + 1 == ns, "PSF splitting (doubled overlap sampling) uses the host builder"
+        nl = cfg.nsamp_ovl      # lags kept per axis: ns, or 2 ns + 1 with PSF splitting (psfutil.py:1075-1083)
+        assert 2 * nc + 1 == nl and nl < nfft
         nv = nfft // 2 + 1
-        self.ns, self.nfft, self.nv = ns, nfft, nv
+        self.ns, self.nfft, self.nv, self.nl = ns, nfft, nv, nl
         self.nsp = rup(ns)      # rows / K extent of the PSF samples
         self.nvp = rup(nv)      # half spectrum along x
         self.nup = rup(nfft)    # full spectrum along y
-        key = (ns, nfft, nc, torch.cuda.current_device())
+        self.nlp = rup(nl)      # kept lags
+        key = (ns, nfft, nc, nl, torch.cuda.current_device())
         if key not in _DFT_CACHE:  # the partial DFT matrices depend on the geometry only
             x = np.arange(ns)
             v = np.arange(nv)
             u = np.arange(nfft)
-            lag = np.arange(ns) - nc
+            lag = np.arange(nl) - nc
             cvx, svx = _phase(v, x, nfft)       # forward along x: e^{-i 2 pi v x / nfft}
             cuy, suy = _phase(u, x, nfft)       # forward along y
             cdu, sdu = _phase(lag, u, nfft)     # inverse along y at the kept lags
@@ -87,9 +89,17 @@ class DeviceTables(PSFTables):
             alpha /= float(nfft) ** 2
             _DFT_CACHE[key] = (_pad(cvx, self.nvp, self.nsp), _pad(-svx, self.nvp, self.nsp),
                                _pad(cuy, self.nup, self.nsp), _pad(suy, self.nup, self.nsp),
-                               _pad(cdu, self.nsp, self.nup), _pad(sdu, self.nsp, self.nup),
-                               _pad(cdv * alpha[None, :], self.nsp, self.nvp), _pad(sdv * alpha[None, :], self.nsp, self.nvp))
+                               _pad(cdu, self.nlp, self.nup), _pad(sdu, self.nlp, self.nup),
+                               _pad(cdv * alpha[None, :], self.nlp, self.nvp), _pad(sdv * alpha[None, :], self.nlp, self.nvp))
         self.Cx, self.Sxn, self.Cu, self.Su, self.Cd, self.Sd, self.Cv, self.Sv = _DFT_CACHE[key]
+        self.amp = None
+        if 0.0 not in cfg.amp_penalty:  # psfutil.py:650-671: real factor on the spectra, here in the transposed layout
+            uu = np.linspace(0, 1 - 1 / nfft, nfft)
+            uu = np.where(uu > 0.5, uu - 1, uu)
+            u2 = np.square(uu)
+            ut2 = u2[None, : nfft // 2 + 1] + u2[:, None]  # [u (full, along y), v (half, along x)]
+            fac = 1.0 + cfg.amp_penalty[0] * np.exp(-2.0 * np.pi**2 * ut2 * (cfg.amp_penalty[1] * cfg.oversamp) ** 2)
+            self.amp = _pad(np.ascontiguousarray(fac.T), self.nvp, self.nup)
         super().__init__(blk, iC, gridC, dedup=dedup)
 
     # ---- dense products on the tensor pipe -------------------------------------------------------------------
@@ -121,18 +131,18 @@ class DeviceTables(PSFTables):
         return _Spectrum(re, im)
 
     def _inverse(self, gr, gi):
-        """Product spectra (n, nvp, nup) -> central (ns, ns) lags of irfft2, as a contiguous (n, ns, ns) tensor.
+        """Product spectra (n, nvp, nup) -> central (nl, nl) lags of irfft2, as a contiguous (n, nl, nl) tensor.
 
         All n tables go through each product together (stacked along M), so the tile grids fill the GPU."""
         n = gr.shape[0]
-        out = torch.empty((n, self.ns, self.ns), dtype=torch.float64, device="cuda")
+        out = torch.empty((n, self.nl, self.nl), dtype=torch.float64, device="cuda")
         CH = 32
         for k0 in range(0, n, CH):
             k1 = min(k0 + CH, n)
             nb = k1 - k0
             g_r = gr[k0:k1].reshape(nb * self.nvp, self.nup)
             g_i = gi[k0:k1].reshape(nb * self.nvp, self.nup)
-            htr = torch.empty((nb * self.nvp, self.nsp), dtype=torch.float64, device="cuda")
+            htr = torch.empty((nb * self.nvp, self.nlp), dtype=torch.float64, device="cuda")
             hti = torch.empty_like(htr)
             # along y:  HT[v, dy] = sum_u G[v, u] (cos + i sin)[dy, u]
             self._gemm(g_r, self.Cd, htr, 0)
@@ -140,13 +150,13 @@ class DeviceTables(PSFTables):
             self._gemm(g_r, self.Sd, hti, 0)
             self._gemm(g_i, self.Cd, hti, 1)
             # (v, dy) -> (dy, v) per table, so that v is the contiguous K of the last product
-            hr = htr.view(nb, self.nvp, self.nsp).transpose(1, 2).contiguous().view(nb * self.nsp, self.nvp)
-            hi = hti.view(nb, self.nvp, self.nsp).transpose(1, 2).contiguous().view(nb * self.nsp, self.nvp)
+            hr = htr.view(nb, self.nvp, self.nlp).transpose(1, 2).contiguous().view(nb * self.nlp, self.nvp)
+            hi = hti.view(nb, self.nvp, self.nlp).transpose(1, 2).contiguous().view(nb * self.nlp, self.nvp)
             # along x (Hermitian half):  ovl[dy, dx] = sum_v alpha_v (Hr cos - Hi sin)[dy, v ; dx, v]
-            ovl = torch.empty((nb * self.nsp, self.nsp), dtype=torch.float64, device="cuda")
+            ovl = torch.empty((nb * self.nlp, self.nlp), dtype=torch.float64, device="cuda")
             self._gemm(hr, self.Cv, ovl, 0)
             self._gemm(hi, self.Sv, ovl, -1)
-            out[k0:k1].copy_(ovl.view(nb, self.nsp, self.nsp)[:, : self.ns, : self.ns])
+            out[k0:k1].copy_(ovl.view(nb, self.nlp, self.nlp)[:, : self.nl, : self.nl])
         return out
 
     def _cmul_conj(self, a: _Spectrum, b: _Spectrum, b_index=None, conj_a=False):
@@ -169,10 +179,15 @@ class DeviceTables(PSFTables):
         ny, nx = psf.shape
         xctr, yctr = (nx - 1) / 2.0, (ny - 1) / 2.0
         pt = np.asarray(inst.psf_compute_point_pix, dtype=np.float64)
-        xyo = np.flip(self.yxo, axis=0).reshape((2, -1)).T * cfg.dscale
-        yxco = image.outpix2world2inpix(xyo + pt)
-        yxco -= image.outpix2world2inpix(pt[None, :])
-        yxco = np.flip(yxco * cfg.oversamp, axis=-1).T.reshape(2, cfg.nsamp, cfg.nsamp)
+        if cfg.psfsplit:  # linearised distortion from the four cardinal offsets (psfutil.py:739-753)
+            card = np.flip(image.outpix2world2inpix(pt[None, :] + np.array([[1, 0], [0, 1], [-1, 0], [0, -1]]) * cfg.oversamp),
+                           axis=-1) / 2.0 * cfg.dscale
+            yxco = np.tensordot(card[0] - card[2], self.yxo[1], axes=0) + np.tensordot(card[1] - card[3], self.yxo[0], axes=0)
+        else:
+            xyo = np.flip(self.yxo, axis=0).reshape((2, -1)).T * cfg.dscale
+            yxco = image.outpix2world2inpix(xyo + pt)
+            yxco -= image.outpix2world2inpix(pt[None, :])
+            yxco = np.flip(yxco * cfg.oversamp, axis=-1).T.reshape(2, cfg.nsamp, cfg.nsamp)
         tab = torch.from_numpy(np.pad(psf, 6)).cuda()
         xs = torch.from_numpy(np.ascontiguousarray(yxco[1].ravel() + xctr + 6)).cuda()
         ys = torch.from_numpy(np.ascontiguousarray(yxco[0].ravel() + yctr + 6)).cuda()
@@ -190,8 +205,11 @@ class DeviceTables(PSFTables):
             psf_arr = psf_arr * mask
         if cfg.psf_norm:
             psf_arr = psf_arr / psf_arr.sum(dim=(-2, -1), keepdim=True)
-        assert 0.0 in cfg.amp_penalty, "amplitude penalty: use the host builder"
-        return self._forward(psf_arr.contiguous())
+        spec = self._forward(psf_arr.contiguous())
+        if self.amp is not None:
+            spec.re.mul_(self.amp)
+            spec.im.mul_(self.amp)
+        return spec
 
     def _build_out(self):
         """Output PSFs (psfutil.py:874-877, 784-794) -> spectra; C = out (*) out at zero lag (psfutil.py:1290)."""
@@ -273,7 +291,7 @@ class DeviceTables(PSFTables):
                 gr, gi = self._cmul_conj(s2, s1, b_index=j, conj_a=True)  # rft1[j] * conj(rft2[i])
                 grs.append(gr)
                 gis.append(gi)
-            return self._inverse(torch.cat(grs), torch.cat(gis)).view(s1.n, s2.n, self.ns, self.ns)
+            return self._inverse(torch.cat(grs), torch.cat(gis)).view(s1.n, s2.n, self.nl, self.nl)
 
         return self._memo(self.cross, (G1, G2), ("cross", tuple(self.grp_imgs[G1]), tuple(self.grp_imgs[G2])), build)
 
@@ -287,6 +305,6 @@ class DeviceTables(PSFTables):
                 gr, gi = self._cmul_conj(so, s1, b_index=j, conj_a=True)  # rft1[j] * conj(out[o])
                 grs.append(gr)
                 gis.append(gi)
-            return self._inverse(torch.cat(grs), torch.cat(gis)).view(s1.n, so.n, self.ns, self.ns)
+            return self._inverse(torch.cat(grs), torch.cat(gis)).view(s1.n, so.n, self.nl, self.nl)
 
         return self._memo(self.io, G, ("io", tuple(self.grp_imgs[G])), build)

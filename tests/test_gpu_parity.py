@@ -388,13 +388,16 @@ def test_pair_block_cache_is_bit_identical(name):
         assert cached.pair_points < tot
 
 
-@pytest.mark.parametrize("name", ["chol1", "pad4"])
+@pytest.mark.parametrize("name", ["chol1", "pad4", "nout2split", "amp"])
 def test_device_tables(name):
     """PSF-overlap tables built on the device (device iD5512C sampling + partial DFTs as DMMA
     products) equal the NumPy-FFT tables of the host builder, and a block coadded from them equals the oracle."""
     from pyimcom_b200.psfovl_device import DeviceTables
 
-    spec = cases.BLOCK_CASES[name]
+    if name == "amp":  # amplitude penalty on the Fourier modes (psfutil.py:661-671) + circular cut + normalisation
+        spec = dict(cases.BLOCK_CASES["chol1"], cfg=dict(cases._MINI, amp_penalty=(0.5, 0.8), psf_circ=True, psf_norm=True))
+    else:
+        spec = cases.BLOCK_CASES[name]  # "nout2split": PSF splitting, kept lags 2 ns + 1, two output PSFs
     blk = cases.make_block(spec)
     host = PSFTables(blk, G.iD5512C, G.gridD5512C)
     dev = DeviceTables(blk, G.iD5512C, G.gridD5512C)
