@@ -309,6 +309,12 @@ int b200_dev_partition(const b200_part_cell* cells, int ncell, const double* ox,
                        double upper, int npixmax, int* sid_tmp, unsigned* rank_tmp, int* cellmeta, unsigned* cellcnt,
                        unsigned* cellbase, unsigned* run, unsigned* pix_count, unsigned short* y_idx,
                        unsigned short* x_idx, double* y_val, double* x_val, int* err, void* stream);
+/* InStamp.__init__ (coadd.py:682-707) for input image number `image`: its per-stamp lists (x_val, y_val (nstamp, npixmax),
+ * data (n_inframe, nstamp, max_count), pix_count (nstamp)) are copied to dst_off[sid] .. dst_off[sid] + pix_count[sid] - 1
+ * of the block's concatenated pixel arrays gx, gy (npix) f64, gimg (npix) i32, gdata (n_inframe, npix) f32. */
+int b200_dev_assemble_instamps(const double* x_val, const double* y_val, const float* data, int n_inframe, int nstamp,
+                               int npixmax, int max_count, const unsigned* pix_count, const long long* dst_off, int image,
+                               long long npix, double* gx, double* gy, int* gimg, float* gdata, void* stream);
 /* InImage.extract_layers (coadd.py:396-404): data (n_inframe, nstamp, max_count) f32 = indata (n_inframe, sca, sca) at
  * the listed pixels, zero beyond pix_count. */
 int b200_dev_extract_layers(const float* indata, int n_inframe, int sca, const unsigned short* y_idx,

@@ -131,6 +131,7 @@ PROTOTYPES = {
     "b200_dev_partition": [vp, i32, vp, vp, vp, i32, vp, i32, i32, f64, f64, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp,
                            vp, vp, vp],
     "b200_dev_extract_layers": [vp, i32, i32, vp, vp, vp, i32, i32, i32, vp, vp],
+    "b200_dev_assemble_instamps": [vp, vp, vp, i32, i32, i32, i32, vp, vp, i32, C.c_longlong, vp, vp, vp, vp, vp],
 }
 
 lib.b200_last_error.restype = C.c_char_p

@@ -178,6 +178,12 @@ class GpuBlock:
     def _global_pixels(self):
         blk, cfg = self.blk, self.cfg
         ns = cfg.n1P + 2
+        dp = getattr(blk, "device_pixels", None)
+        if dp is not None:  # InStamps binned on the device (partition.PartitionedBlock): the pixels are already in HBM
+            self.inst_off = np.asarray(dp["inst_off"], dtype=np.int64)
+            self.h_x, self.h_y, self.h_img, self.h_data = dp["h_x"], dp["h_y"], dp["h_img"], None
+            self.npix_total = int(dp["npix_total"])
+            return
         self.inst_off = np.zeros((ns, ns), dtype=np.int64)
         xs, ys, imgs, datas = [], [], [], []
         off = 0
@@ -367,11 +373,16 @@ class GpuBlock:
 
     def upload(self):
         cfg = self.cfg
-        self.d_x = h2d(self.h_x)
-        self.d_y = h2d(self.h_y)
-        self.d_data = h2d(self.h_data)
-        self.d_tables = self.arena.upload()
-        self.d_img = h2d(self.h_img)
+        dp = getattr(self.blk, "device_pixels", None)
+        if dp is not None:
+            self.d_x, self.d_y, self.d_data, self.d_img = dp["d_x"], dp["d_y"], dp["d_data"], dp["d_img"]
+            self.d_tables = self.arena.upload()
+        else:
+            self.d_x = h2d(self.h_x)
+            self.d_y = h2d(self.h_y)
+            self.d_data = h2d(self.h_data)
+            self.d_tables = self.arena.upload()
+            self.d_img = h2d(self.h_img)
         plut = np.stack(self._pair_lut_list) if self._pair_lut_list else np.zeros((1, 1, 1), dtype=TABLEREF_DTYPE)
         self.d_pair_lut = h2d(plut.view(np.uint8).reshape(-1))
         self._pairs = {}  # (inst_a, inst_b) -> (pool offset in doubles, ld)
@@ -379,8 +390,8 @@ class GpuBlock:
         self._pool_used = 0
         self.pair_points = 0  # entries interpolated so far (vs sum of n^2/2 without the cache)
         self.d_fade_w = h2d(trapezoid_weights(cfg.fade_kernel)) if cfg.fade_kernel > 0 else None
-        self.h2d_bytes = self.arena.h2d_bytes + sum(
-            t.numel() * t.element_size() for t in (self.d_x, self.d_y, self.d_data, self.d_img, self.d_pair_lut))
+        crossed = (self.d_pair_lut,) if dp is not None else (self.d_x, self.d_y, self.d_data, self.d_img, self.d_pair_lut)
+        self.h2d_bytes = self.arena.h2d_bytes + sum(t.numel() * t.element_size() for t in crossed)
         self.reset_maps()
         self._uploaded = True
 

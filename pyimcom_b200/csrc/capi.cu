@@ -437,6 +437,12 @@ int b200_dev_partition(const b200_part_cell* cells, int ncell, const double* ox,
     return launch_partition(cells, ncell, ox, oy, mask, sca, use, ns, n2, lower, upper, npixmax, sid_tmp, rank_tmp,
                             cellmeta, cellcnt, cellbase, run, pix_count, y_idx, x_idx, y_val, x_val, err, ST(s));
 }
+int b200_dev_assemble_instamps(const double* x_val, const double* y_val, const float* data, int n_inframe, int nstamp,
+                               int npixmax, int max_count, const unsigned* pix_count, const long long* dst_off, int image,
+                               long long npix, double* gx, double* gy, int* gimg, float* gdata, void* s) {
+    return launch_assemble_instamps(x_val, y_val, data, n_inframe, nstamp, npixmax, max_count, pix_count, dst_off, image,
+                                    npix, gx, gy, gimg, gdata, ST(s));
+}
 int b200_dev_extract_layers(const float* indata, int n_inframe, int sca, const unsigned short* y_idx,
                             const unsigned short* x_idx, const unsigned* pix_count, int nstamp, int npixmax,
                             int max_count, float* data, void* s) {

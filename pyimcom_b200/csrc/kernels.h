@@ -115,5 +115,8 @@ int launch_partition(const PartCell* cells, int ncell, const double* ox, const d
 int launch_extract_layers(const float* indata, int n_inframe, int sca, const unsigned short* y_idx,
                           const unsigned short* x_idx, const unsigned* pix_count, int nstamp, int npixmax, int max_count,
                           float* data, cudaStream_t s);
+int launch_assemble_instamps(const double* x_val, const double* y_val, const float* data, int n_inframe, int nstamp,
+                             int npixmax, int max_count, const unsigned* pix_count, const long long* dst_off, int image,
+                             long long npix, double* gx, double* gy, int* gimg, float* gdata, cudaStream_t s);
 
 }  // namespace b200

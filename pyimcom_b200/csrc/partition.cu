@@ -196,7 +196,38 @@ __global__ void __launch_bounds__(PT) k_part_extract(const float* __restrict__ i
     }
 }
 
+// InStamp.__init__ (coadd.py:682-707) for one input image: the image's per-stamp lists go to their place in the block's
+// concatenated pixel arrays (stamp-major, images in order inside a stamp): dst_off[sid] = first slot of this image's
+// pixels of stamp sid.
+__global__ void __launch_bounds__(PT) k_part_assemble(const double* __restrict__ x_val, const double* __restrict__ y_val,
+                                                      const float* __restrict__ data, int n_inframe, int nstamp,
+                                                      int npixmax, int max_count, const unsigned* __restrict__ pix_count,
+                                                      const long long* __restrict__ dst_off, int image, long long npix,
+                                                      double* __restrict__ gx, double* __restrict__ gy,
+                                                      int* __restrict__ gimg, float* __restrict__ gdata) {
+    const int sid = blockIdx.x;
+    const unsigned n = pix_count[sid];
+    const long long o = dst_off[sid];
+    for (unsigned t = threadIdx.x; t < n; t += PT) {
+        gx[o + t] = x_val[(size_t)sid * npixmax + t];
+        gy[o + t] = y_val[(size_t)sid * npixmax + t];
+        gimg[o + t] = image;
+        for (int f = 0; f < n_inframe; f++)
+            gdata[(size_t)f * npix + o + t] = data[((size_t)f * nstamp + sid) * max_count + t];
+    }
+}
+
 }  // namespace
+
+int launch_assemble_instamps(const double* x_val, const double* y_val, const float* data, int n_inframe, int nstamp,
+                             int npixmax, int max_count, const unsigned* pix_count, const long long* dst_off, int image,
+                             long long npix, double* gx, double* gy, int* gimg, float* gdata, cudaStream_t s) {
+    if (nstamp <= 0 || npix <= 0) return 0;
+    k_part_assemble<<<nstamp, PT, 0, s>>>(x_val, y_val, data, n_inframe, nstamp, npixmax, max_count, pix_count, dst_off,
+                                          image, npix, gx, gy, gimg, gdata);
+    B200_LAUNCH_CHECK();
+    return 0;
+}
 
 int launch_partition(const PartCell* cells, int ncell, const double* ox, const double* oy, const unsigned char* mask,
                      int sca, const unsigned char* use, int ns, int n2, double lower, double upper, int npixmax,

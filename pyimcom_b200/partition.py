@@ -129,7 +129,7 @@ class DevicePartition:
             raise IndexError(f"partition: a postage stamp received more than npixmax = {self.npixmax} input pixels "
                              "(the reference's arrays overflow at the same point, coadd.py:354-358)")
         res = dict(is_relevant=True, pix_count=counts, y_idx=y_idx, x_idx=x_idx, y_val=y_val, x_val=x_val,
-                   max_count=int(counts.max()), n_positions=ntot, n_cells=ncell)
+                   max_count=int(counts.max()), n_positions=ntot, n_cells=ncell, pix_count_dev=pix_count)
         if indata is not None:
             d_in = indata if torch.is_tensor(indata) else h2d(np.ascontiguousarray(indata, dtype=np.float32))
             nfr = d_in.shape[0]
@@ -150,3 +150,86 @@ def to_host(res):
         else:
             out[k] = v
     return out
+
+
+class DeviceInStamp:
+    """Host view of one InStamp (coadd.py:656-749) whose pixels were binned on the device: positions and counts for the
+    host-side planning (make_selection, PSF-group bookkeeping); the layers stay in HBM (``data`` is None)."""
+
+    def __init__(self, j_st, i_st, pix_count, x_val, y_val, n2):
+        self.j_st, self.i_st = j_st, i_st
+        self.pix_count = np.asarray(pix_count, dtype=np.uint32)
+        self.pix_cumsum = np.cumsum([0] + list(self.pix_count), dtype=np.uint32)  # coadd.py:691
+        self.x_val, self.y_val, self.data = x_val, y_val, None
+        if j_st % 2 == 0 and i_st % 2 == 0:  # coadd.py:709-714
+            self.psf_compute_point_pix = [i_st * n2 - 0.5, j_st * n2 - 0.5]
+
+    def make_selection(self, pivot=(None, None), radius=None):
+        """coadd.py:716-749."""
+        if pivot == (None, None) or radius is None:
+            return None
+        dist_sq = np.zeros(self.x_val.shape[0])
+        if pivot[0] is not None:
+            dist_sq += np.square(self.x_val - pivot[0])
+        if pivot[1] is not None:
+            dist_sq += np.square(self.y_val - pivot[1])
+        sel = np.array(np.where(dist_sq < radius**2)[0], dtype=np.uint32)
+        return sel if sel.shape[0] < self.x_val.shape[0] else None
+
+
+class PartitionedBlock:
+    """Duck-typed coadd.Block for coadd.GpuBlock whose InStamps come straight from DevicePartition results.
+
+    InStamp.__init__ (coadd.py:682-707) concatenates, per postage stamp, the lists of all input images; here each
+    image's lists are copied on the device into the block's concatenated pixel arrays (``device_pixels``: exactly what
+    GpuBlock would otherwise build on the host and upload), and only the positions come back for the planning.
+    parts[k] is DevicePartition.partition(..., indata) of input image k (``is_relevant`` False: no pixels)."""
+
+    def __init__(self, cfg, inimages, parts, outwcs=None, this_sub=0):
+        self.cfg, self.inimages, self.n_inimage = cfg, list(inimages), len(inimages)
+        self.outwcs, self.this_sub = outwcs, this_sub
+        ns = cfg.n1P + 2
+        nst, nimg = ns * ns, self.n_inimage
+        counts = np.zeros((nimg, nst), dtype=np.int64)
+        for k, part in enumerate(parts):
+            if part.get("is_relevant", False):
+                counts[k] = np.asarray(part["pix_count"], dtype=np.int64).ravel()
+        per_stamp = counts.sum(axis=0)
+        inst_off = np.concatenate([[0], np.cumsum(per_stamp)[:-1]]).astype(np.int64)
+        within = np.cumsum(counts, axis=0) - counts  # exclusive over the images of one stamp
+        npix = int(per_stamp.sum())
+        dev, st = "cuda", stream_handle()
+        gx = torch.empty(max(npix, 1), dtype=torch.float64, device=dev)
+        gy = torch.empty(max(npix, 1), dtype=torch.float64, device=dev)
+        gimg = torch.empty(max(npix, 1), dtype=torch.int32, device=dev)
+        gdata = torch.empty((cfg.n_inframe, max(npix, 1)), dtype=torch.float32, device=dev)
+        for k, part in enumerate(parts):
+            if not part.get("is_relevant", False) or part["max_count"] == 0:
+                continue
+            data = part["data"]
+            assert data.shape[0] == cfg.n_inframe and data.shape[-1] == part["max_count"]
+            d_off = h2d(inst_off + within[k])
+            _lib.dev_assemble_instamps(ptr(part["x_val"]), ptr(part["y_val"]), ptr(data), cfg.n_inframe, nst,
+                                       part["x_val"].shape[-1], part["max_count"], ptr(part["pix_count_dev"]),
+                                       ptr(d_off), k, npix, ptr(gx), ptr(gy), ptr(gimg), ptr(gdata), st)
+        torch.cuda.current_stream().synchronize()
+        h_x, h_y = gx[:npix].cpu().numpy(), gy[:npix].cpu().numpy()
+        h_img = gimg[:npix].cpu().numpy()
+        self.device_pixels = dict(d_x=gx[:npix], d_y=gy[:npix], d_img=gimg[:npix], d_data=gdata[:, :npix], h_x=h_x,
+                                  h_y=h_y, h_img=h_img, inst_off=inst_off.reshape(ns, ns), npix_total=npix)
+        self.instamps = [[None] * ns for _ in range(ns)]
+        for j in range(ns):
+            for i in range(ns):
+                sid = j * ns + i
+                a, b = int(inst_off[sid]), int(inst_off[sid] + per_stamp[sid])
+                self.instamps[j][i] = DeviceInStamp(j, i, counts[:, sid], h_x[a:b], h_y[a:b], cfg.n2)
+
+    def stamp_order(self):
+        """OutStamp traversal of coadd_output_stamps: 2x2 groups (coadd.py:2056-2060)."""
+        n1P = self.cfg.n1P
+        for j in range(1, n1P + 1, 2):
+            for i in range(1, n1P + 1, 2):
+                for dj in range(2):
+                    for di in range(2):
+                        if j + dj <= n1P and i + di <= n1P:
+                            yield (j + dj, i + di)

@@ -597,3 +597,56 @@ def test_partition_large_cells_and_overflow():
     small = DevicePartition(cfg, use, relax_coef=0.5)
     with pytest.raises(IndexError):
         small.partition(outpix, mask)
+
+
+def test_device_partition_feeds_block():
+    """f2 -> (a): InStamps binned on the device go into GpuBlock without a host round trip of the layers
+    (partition.PartitionedBlock).  The block maps are bit-identical to those of the host path fed with the downloaded
+    copies of the same lists, and the per-stamp pixel sets are those of the synthetic block's own binning."""
+    import copy
+    import types
+
+    from pyimcom_b200.partition import DevicePartition, PartitionedBlock, to_host
+    from pyimcom_b200.synth import SynthInStamp
+
+    spec = cases.BLOCK_CASES["pad4"]
+    blk = cases.make_block(spec)
+    cfg = blk.cfg
+    ns = cfg.n1P + 2
+    sca, shift = 256, 100.0  # the synthetic detector coordinates are centred near 0: shift them into [0, sca)
+    rng = np.random.default_rng(3)
+    dp = DevicePartition(cfg, np.ones((ns, ns), dtype=bool), sca_nside=sca, sp_res=16)
+    parts, twins = [], []
+    for im in blk.inimages:
+        vv, uu = np.mgrid[0:sca, 0:sca]
+        indata = rng.standard_normal((cfg.n_inframe, sca, sca)).astype(np.float32)
+        sin = im.outpix2world2inpix(np.asarray(blk.star_xy, dtype=np.float64)[None, :])[0]
+        indata[0] = im.psf(uu - shift - sin[0], vv - shift - sin[1]).astype(np.float32)  # a star through this PSF
+        part = dp.partition(lambda xy, im=im: im.inpix2outpix(np.asarray(xy, dtype=np.float64) - shift),
+                            np.ones((sca, sca), dtype=bool), indata)
+        assert part["is_relevant"]
+        parts.append(part)
+        h = to_host(part)
+        tw = copy.copy(im)
+        tw.pix_count, tw.x_val, tw.y_val, tw.data, tw.max_count = h["pix_count"], h["x_val"], h["y_val"], h["data"], h["max_count"]
+        twins.append(tw)
+        for j in range(ns):  # same pixel sets as the synthetic block's own binning (list order differs: cell-major)
+            for i in range(ns):
+                n = int(im.pix_count[j, i])
+                assert n == int(h["pix_count"][j, i])
+                assert np.array_equal(np.sort(im.x_val[j, i, :n]), np.sort(h["x_val"][j, i, :n]))
+    pblk = PartitionedBlock(cfg, blk.inimages, parts, outwcs=blk.outwcs)
+    hblk = types.SimpleNamespace(cfg=cfg, inimages=twins, n_inimage=len(twins), outwcs=blk.outwcs, this_sub=0,
+                                 stamp_order=pblk.stamp_order)
+    hblk.instamps = [[SynthInStamp(hblk, j, i) for i in range(ns)] for j in range(ns)]
+    for j in range(ns):
+        for i in range(ns):
+            assert np.array_equal(pblk.instamps[j][i].x_val, hblk.instamps[j][i].x_val)
+            assert np.array_equal(pblk.instamps[j][i].pix_cumsum, hblk.instamps[j][i].pix_cumsum)
+    gd = GpuBlock(pblk, PSFTables(pblk, G.iD5512C, G.gridD5512C)).prepare().run()
+    gh = GpuBlock(hblk, PSFTables(hblk, G.iD5512C, G.gridD5512C)).prepare().run()
+    assert gd.h2d_bytes < gh.h2d_bytes
+    md, mh = gd.download(), gh.download()
+    for k in md:
+        assert np.array_equal(md[k], mh[k]), k
+    assert np.abs(md["out_map"][0, 0]).max() > 0.01  # the star is there
