@@ -55,6 +55,7 @@ def test_struct_layouts(lib):
     assert ctypes.sizeof(lib.PairDesc) == 40
     assert ctypes.sizeof(lib.EighProblem) == 40
     assert ctypes.sizeof(lib.AsmDesc) == 1056  # 648 + 324 + 40 + 36 + 4, rounded up to the 8-byte alignment
+    assert ctypes.sizeof(lib.PartCell) == 24 and lib.PART_MAXSLOT == 256
 
 
 def test_seams_expose_reference_names():
