@@ -156,7 +156,14 @@ __device__ __forceinline__ void gemm_tile_nt(const double* A, int lda, const dou
 // consecutive doubles per instruction) touch every 8-byte bank word exactly twice, the minimum for 256 B.
 // Used by the four update kernels (operands and output never overlap there); the in-place products with inv(L_kk)
 // keep the 128x128 tile, which stages the whole K = 128 operand before it writes.
-constexpr int KT2 = 16, ST2 = 4, TB = 64, GT2 = 128;
+#ifndef B200_T64_STAGES
+#define B200_T64_STAGES 4
+#endif
+#ifndef B200_T64_CTAS
+#define B200_T64_CTAS 3
+#endif
+constexpr int KT2 = 16, ST2 = B200_T64_STAGES, TB = 64, GT2 = 128;
+constexpr int CTAS2 = B200_T64_CTAS;  // resident CTAs per SM the 64x64-tile kernels are compiled for
 constexpr int STAGE2_DOUBLES = 2 * TB * KT2;
 constexpr size_t GEMM2_SMEM = (size_t)ST2 * STAGE2_DOUBLES * sizeof(double);  // 65536 B
 
@@ -299,7 +306,7 @@ __global__ void __launch_bounds__(GT, 1) k_gemm_nt(const double* __restrict__ A,
 }
 
 template <int MODE>
-__global__ void __launch_bounds__(GT2, 3) k_gemm64_nt(const double* __restrict__ A, int lda,
+__global__ void __launch_bounds__(GT2, CTAS2) k_gemm64_nt(const double* __restrict__ A, int lda,
                                                       const double* __restrict__ B, int ldb, double* C, int ldc, int K) {
     extern __shared__ __align__(16) double smem[];
     const int tn = blockIdx.x, tm = blockIdx.y;
@@ -319,7 +326,7 @@ __device__ __forceinline__ bool x_half_tile(const SolveSys& s, int r) {
 //
 // Super-panel update:  W[i][j] -= W[i][0:c0] W[j][0:c0]^T  (c0 <= j < c1, j <= i)  and the same for the X rows.
 template <bool T64>
-__global__ void __launch_bounds__(T64 ? GT2 : GT, T64 ? 3 : 1) k_chol_super_update(SolveBatch bt, int c0, int c1) {
+__global__ void __launch_bounds__(T64 ? GT2 : GT, T64 ? CTAS2 : 1) k_chol_super_update(SolveBatch bt, int c0, int c1) {
     extern __shared__ __align__(16) double smem[];
     const SolveSys& s = bt.s[blockIdx.z];
     const int nb = s.npad / NB, mb = s.mpad / NB;
@@ -344,7 +351,7 @@ __global__ void __launch_bounds__(T64 ? GT2 : GT, T64 ? 3 : 1) k_chol_super_upda
 // Panel step k: rows below the diagonal block (and all X rows) times inv(L_kk)^T; the W part is also
 // stored transposed into the upper block triangle.
 template <bool T64>
-__global__ void __launch_bounds__(T64 ? GT2 : GT, T64 ? 3 : 1) k_chol_panel(SolveBatch bt, int k) {
+__global__ void __launch_bounds__(T64 ? GT2 : GT, T64 ? CTAS2 : 1) k_chol_panel(SolveBatch bt, int k) {
     extern __shared__ __align__(16) double smem[];
     const SolveSys& s = bt.s[blockIdx.y];
     const int nb = s.npad / NB, mb = s.mpad / NB;
@@ -377,7 +384,7 @@ __global__ void __launch_bounds__(T64 ? GT2 : GT, T64 ? 3 : 1) k_chol_panel(Solv
 // Update inside the super-panel after panel k:  W[i][j] -= W[i][k] W[j][k]^T (k < j < c1, j <= i)  and
 // X[t][j] -= X[t][k] W[j][k]^T.
 template <bool T64>
-__global__ void __launch_bounds__(T64 ? GT2 : GT, T64 ? 3 : 1) k_chol_update(SolveBatch bt, int k, int c1) {
+__global__ void __launch_bounds__(T64 ? GT2 : GT, T64 ? CTAS2 : 1) k_chol_update(SolveBatch bt, int k, int c1) {
     extern __shared__ __align__(16) double smem[];
     const SolveSys& s = bt.s[blockIdx.z];
     const int nb = s.npad / NB, mb = s.mpad / NB;
@@ -403,7 +410,7 @@ __global__ void __launch_bounds__(T64 ? GT2 : GT, T64 ? 3 : 1) k_chol_update(Sol
 // [e0, e1) the super-panel of a system with nb blocks is lo = max(0, nb - e1) <= k < hi = nb - e0.
 // Super-panel update:  X[t][j] -= X[t][hi:nb] L[hi:nb][j]  (lo <= j < hi); L[k][j]^T lives at W[j][k] (upper triangle).
 template <bool T64>
-__global__ void __launch_bounds__(T64 ? GT2 : GT, T64 ? 3 : 1) k_back_super_update(SolveBatch bt, int e0, int e1) {
+__global__ void __launch_bounds__(T64 ? GT2 : GT, T64 ? CTAS2 : 1) k_back_super_update(SolveBatch bt, int e0, int e1) {
     extern __shared__ __align__(16) double smem[];
     const SolveSys& s = bt.s[blockIdx.z];
     const int nb = s.npad / NB, mb = s.mpad / NB;
@@ -418,7 +425,7 @@ __global__ void __launch_bounds__(T64 ? GT2 : GT, T64 ? 3 : 1) k_back_super_upda
 
 // Backward step k, part 1:  X[t][k] = X[t][k] inv(L_kk)   (B operand = inv(L_kk)^T)
 template <bool T64>
-__global__ void __launch_bounds__(T64 ? GT2 : GT, T64 ? 3 : 1) k_back_diag(SolveBatch bt, int kfromtop) {
+__global__ void __launch_bounds__(T64 ? GT2 : GT, T64 ? CTAS2 : 1) k_back_diag(SolveBatch bt, int kfromtop) {
     extern __shared__ __align__(16) double smem[];
     const SolveSys& s = bt.s[blockIdx.y];
     const int nb = s.npad / NB, mb = s.mpad / NB;
@@ -440,7 +447,7 @@ __global__ void __launch_bounds__(T64 ? GT2 : GT, T64 ? 3 : 1) k_back_diag(Solve
 
 // Backward step k, part 2, inside the super-panel:  X[t][j] -= X[t][k] L[k][j]  (lo <= j < k)
 template <bool T64>
-__global__ void __launch_bounds__(T64 ? GT2 : GT, T64 ? 3 : 1) k_back_update(SolveBatch bt, int kfromtop, int e1) {
+__global__ void __launch_bounds__(T64 ? GT2 : GT, T64 ? CTAS2 : 1) k_back_update(SolveBatch bt, int kfromtop, int e1) {
     extern __shared__ __align__(16) double smem[];
     const SolveSys& s = bt.s[blockIdx.z];
     const int nb = s.npad / NB, mb = s.mpad / NB;
