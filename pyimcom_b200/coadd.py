@@ -22,6 +22,7 @@ from __future__ import annotations
 
 import ctypes as C
 import os
+import types
 import weakref
 
 import numpy as np
@@ -470,8 +471,8 @@ class GpuBlock:
         def wanted():
             seen, out = set(), []
             for p in plans:
-                for a in range(9):
-                    for b in range(a, 9):
+                for a in range(len(p.insts)):
+                    for b in range(a, len(p.insts)):
                         key = (p.insts[a], p.insts[b])
                         if key in self._pairs or key in seen:
                             continue
@@ -525,6 +526,52 @@ class GpuBlock:
                              int(tiles[-1]), ptr(self.d_tables), ptr(self.d_pair_lut), self.blk.n_inimage,
                              self.arena.ngrid, float(cfg.dscale), float(cfg.nc_ovl), float(cfg.flat_penalty),
                              self.arena.poly, ptr(self._pool), float(points), stream_handle())
+
+    def pair_block(self, a, b) -> torch.Tensor:
+        """The full InStamp-pair block of A, (npix_a, npix_b) float64 on the device (a <= b in raster order):
+        what SysMatA.get_iisubmat returns (psfutil.py:2009-2092).  A view into the pair-block pool: copy it if it has to
+        outlive the next ensure_pairs call."""
+        assert a <= b, f"ji_st1={a} should precede ji_st2={b}"
+        nA, nB = self._inst_count(a), self._inst_count(b)
+        if nA == 0 or nB == 0:
+            return torch.zeros((nA, nB), dtype=torch.float64, device="cuda")
+
+        if (a, b) not in self._pairs:  # (ensure_pairs reads only .insts of a StampPlan)
+            self.ensure_pairs([types.SimpleNamespace(insts=[a] if a == b else [a, b])])
+        off, ld = self._pairs[(a, b)]
+        return self._pool[off:off + nA * ld].view(nA, ld)[:, :nB]
+
+    def io_block(self, ji_in, selection, x0out: float, y0out: float) -> torch.Tensor:
+        """One InStamp's columns of -B/2, (n_out, m, n_selected) float64 on the device, for the output stamp whose
+        first pixel sits at (x0out, y0out): what SysMatB.get_iosubmat returns (psfutil.py:2125-2185, 1497-1595).
+        selection: indices into the InStamp's pixels (None: all of them)."""
+        cfg, tab = self.cfg, self.tab
+        nimg = self.blk.n_inimage
+        base = int(self.inst_off[ji_in])
+        ntot = self._inst_count(ji_in)
+        loc = np.arange(ntot, dtype=np.int64) if selection is None else np.asarray(selection, dtype=np.int64)
+        n, m = int(loc.size), cfg.n2f**2
+        if n == 0:
+            return torch.zeros((cfg.n_out, m, 0), dtype=torch.float64, device="cuda")
+        G = anchor(ji_in)
+        tab.group(G)
+        io = tab.get_io(G)
+        lut_io = np.full((nimg, cfg.n_out), -1, dtype=np.int64)
+        for k in tab.grp_imgs[G]:
+            lut_io[k, :] = [self.arena.offset(io, (tab.grp_index(G, k), o)) for o in range(cfg.n_out)]
+        npad, mpad = rup(n), rup(m)
+        gidx = torch.from_numpy(base + loc).cuda()
+        px = torch.zeros(npad, dtype=torch.float64, device="cuda")
+        py = torch.zeros(npad, dtype=torch.float64, device="cuda")
+        px[:n], py[:n] = self.d_x[gidx], self.d_y[gidx]
+        pcode = torch.zeros(npad, dtype=torch.int32, device="cuda")
+        pcode[:n] = self.d_img[gidx]
+        d_lut = h2d(lut_io)
+        mB = torch.empty((cfg.n_out, mpad, npad), dtype=torch.float64, device="cuda")
+        _lib.dev_build_B(ptr(px), ptr(py), ptr(pcode), n, npad, ptr(self.d_tables), ptr(d_lut), cfg.n_out,
+                         self.arena.ngrid, float(cfg.dscale), float(cfg.nc_ovl), cfg.n2f, mpad, float(x0out), float(y0out),
+                         ptr(mB), mB.stride(1), mB.stride(0), stream_handle())
+        return mB[:, :m, :n]
 
     def _release_pool(self):
         """Park the pair-block pool for the next GpuBlock on this device (at most two are kept)."""

@@ -650,3 +650,66 @@ def test_device_partition_feeds_block():
     for k in md:
         assert np.array_equal(md[k], mh[k]), k
     assert np.abs(md["out_map"][0, 0]).max() > 0.01  # the star is there
+
+
+def test_sysmat_seam():
+    """System-matrix seam: pyimcom_b200.sysmat.SysMatA / SysMatB driven exactly as the reference's OutStamp
+    drives psfutil.SysMatA / SysMatB -- counting pass with sim_mode=True, caches cleared, then the assembly of
+    coadd.py:1028-1082 -- give the oracle's A and -B/2 (P-f64), and the reference counts drain to zero."""
+    from itertools import combinations
+
+    from pyimcom_b200.sysmat import SysMatA, SysMatB
+
+    spec = cases.BLOCK_CASES["pad4"]
+    blk = cases.make_block(spec)
+    cfg = blk.cfg
+    otab = PSFTables(blk, R.iD5512C, R.gridD5512C)
+    ns = cfg.n1P + 2
+    stamps = list(spec["stamps"])
+    blk.outstamps = [[None] * ns for _ in range(ns)]
+    for (j, i) in stamps:
+        blk.outstamps[j][i] = OracleOutStamp(blk, otab, j, i)
+    sa, sb = SysMatA(blk), SysMatB(blk)
+    for (j, i) in stamps:  # OutStamp.__init__ in sim mode (coadd.py:860-867)
+        o = blk.outstamps[j][i]
+        for ji in o.ji_st_in_s:
+            assert sa.get_iisubmat(ji, ji, sim_mode=True) is None
+            assert sb.get_iosubmat(ji, (j, i), sim_mode=True) is None
+        for pair in combinations(o.ji_st_in_s, 2):
+            sa.get_iisubmat(*pair, sim_mode=True)
+    assert sa.iisubmats and all(v is None for v in sa.iisubmats.values())
+    sa.iisubmats.clear()  # coadd.py:2062-2063
+    sb.iopsfovls.clear()
+    with pytest.raises(AssertionError):
+        sa.get_iisubmat((2, 2), (1, 1))
+    with pytest.raises(AssertionError):
+        sb.get_iosubmat((0, 0), (2, 2))
+    for (j, i) in stamps:  # OutStamp._build_system_matrices (coadd.py:1028-1082) through the seam
+        o = blk.outstamps[j][i]
+        cs = o.inpix_cumsum.astype(np.int64)
+        n = int(cs[-1])
+        sysmata = np.zeros((n, n))
+        for idx, ji, sel in zip(range(9), o.ji_st_in_s, o.selections):
+            sub = sa.get_iisubmat(ji, ji)
+            assert sub.dtype == np.float64 and sub.shape[0] == sub.shape[1] == int(blk.instamps[ji[0]][ji[1]].pix_cumsum[-1])
+            if sel is not None:
+                sub = sub[np.ix_(sel, sel)]
+            sysmata[cs[idx]:cs[idx + 1], cs[idx]:cs[idx + 1]] = sub
+        for idx_s, pair, sels in zip(combinations(range(9), 2), combinations(o.ji_st_in_s, 2),
+                                     combinations(o.selections, 2)):
+            sub = sa.get_iisubmat(*pair)
+            if sels[0] is not None:
+                sub = sub[np.ix_(sels[0], sels[1])] if sels[1] is not None else sub[sels[0], :]
+            elif sels[1] is not None:
+                sub = sub[:, sels[1]]
+            r0, r1, c0, c1 = cs[idx_s[0]], cs[idx_s[0] + 1], cs[idx_s[1]], cs[idx_s[1] + 1]
+            sysmata[r0:r1, c0:c1] = sub
+            sysmata[c0:c1, r0:r1] = sub.T
+        mhalfb = np.zeros((cfg.n_out, cfg.n2f**2, n))
+        for idx, ji in zip(range(9), o.ji_st_in_s):
+            mhalfb[:, :, cs[idx]:cs[idx + 1]] = sb.get_iosubmat(ji, (j, i))
+        o.build_system_matrices()
+        assert rel(sysmata, o.sysmata) < P64 and rel(mhalfb, o.mhalfb) < P64
+        assert np.abs(sysmata).max() > 0 and np.abs(mhalfb).max() > 0
+    assert not sa.iisubmats and not sb.iopsfovls
+    assert not sa.iisubmats_ref.any() and not sb.iopsfovls_ref.any()
