@@ -151,22 +151,31 @@ def cpu_stamps(blk, n_stamps, threads):
     from oracle.sysmat import OracleOutStamp
     from pyimcom_b200.psfovl_host import PSFTables
 
-    R.set_threads(threads)
+    import contextlib
+
+    R.set_threads(os.cpu_count() or 1)
     tab = PSFTables(blk, R.iD5512C, R.gridD5512C, dedup=True)
     order = list(blk.stamp_order())[:n_stamps]
     for (j, i) in order[:1]:  # builds the PSF-overlap tables outside the clock, as on the GPU arm
         OracleOutStamp(blk, tab, j, i).build_system_matrices()
+    R.set_threads(threads)
+    limit = contextlib.nullcontext()
+    if threads == 1:  # production layout of the reference: one core per block (docs/run_README.rst)
+        from threadpoolctl import threadpool_limits
+
+        limit = threadpool_limits(limits=1)
     ii_cache = {}  # the reference's SysMatA cache: InStamp-pair blocks are interpolated once per block
-    t0 = time.perf_counter()
-    for (j, i) in order:
-        o = OracleOutStamp(blk, tab, j, i, ii_cache=ii_cache)
-        o.build_system_matrices()
-        with warnings.catch_warnings():
-            warnings.simplefilter("ignore")
-            OL.CholKernel(o)()
-        o.post_kernel()
-        o.perform_coaddition()
-    return time.perf_counter() - t0
+    with limit:
+        t0 = time.perf_counter()
+        for (j, i) in order:
+            o = OracleOutStamp(blk, tab, j, i, ii_cache=ii_cache)
+            o.build_system_matrices()
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                OL.CholKernel(o)()
+            o.post_kernel()
+            o.perform_coaddition()
+        return time.perf_counter() - t0
 
 
 def run_reference(args):
@@ -398,6 +407,9 @@ def run_gpu(args):
             cpu = {"value": ncpu * cfg.n2**2 / tcpu, "unit": UNIT, "cores": cores, "kind": "port",
                    "sample": f"first {ncpu} OutStamps of the same block, oracle/ (C + OpenMP interpolation on all cores, "
                              "SciPy/OpenBLAS Cholesky)", "seconds_per_stamp": tcpu / ncpu}
+            t1 = cpu_stamps(blk, 1, 1)  # a second figure with one thread (the reference runs one core per block)
+            cpu["single_thread"] = {"value": cfg.n2**2 / t1, "unit": UNIT, "cores": 1, "sample": "first OutStamp of the block",
+                                    "seconds_per_stamp": t1}
         n_in = int(np.mean([gb.plans[ji].n for ji in gb.order]))
         line = {"metric": METRIC, "value": world * px_per_step * args.steps / t_res, "unit": UNIT, "n_gpus": world,
                 "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": 1e3 * t_res / args.steps,
