@@ -103,11 +103,12 @@ def load():
     return _loaded
 
 
-def run_block(blk, kernel: str, kappaC, stamps=None, exact=None):
+def run_block(blk, kernel: str, kappaC, stamps=None, exact=None, only=False):
     """Drive the reference's own InStamp -> OutStamp path on a SynthBlock.
 
     Returns {(j,i): dict of the reference's arrays} for the requested OutStamps.  ``blk`` is a
-    pyimcom_b200.synth.SynthBlock; its cfg is mutated to the requested kernel/kappa set.
+    pyimcom_b200.synth.SynthBlock; its cfg is mutated to the requested kernel/kappa set.  ``only=True`` constructs and
+    runs just the requested OutStamps (the reference counts of the two-pass protocol then cover that subset).
     """
     import numpy as np
 
@@ -130,6 +131,8 @@ def run_block(blk, kernel: str, kappaC, stamps=None, exact=None):
     rb.sysmata = psfutil.SysMatA(rb)
     rb.sysmatb = psfutil.SysMatB(rb)
     order = list(blk.stamp_order())
+    if only:
+        order = [ji for ji in order if ji in stamps]
     for (j, i) in order:
         rb.outstamps[j][i] = coadd.OutStamp(rb, j, i)
     rb.sysmata.iisubmats.clear()

@@ -389,6 +389,8 @@ class GpuBlock:
         self._pairs = {}  # (inst_a, inst_b) -> (pool offset in doubles, ld)
         self._pool = None
         self._pool_used = 0
+        self._pool_gen = 0  # bumped whenever cached blocks are dropped: older assemble closures refuse to run
+        self.pool_evictions = 0
         self.pair_points = 0  # entries interpolated so far (vs sum of n^2/2 without the cache)
         self.d_fade_w = h2d(trapezoid_weights(cfg.fade_kernel)) if cfg.fade_kernel > 0 else None
         crossed = (self.d_pair_lut,) if dp is not None else (self.d_x, self.d_y, self.d_data, self.d_img, self.d_pair_lut)
@@ -437,6 +439,7 @@ class GpuBlock:
         """Forget every cached InStamp-pair block (a new mosaic block starts with an empty SysMatA cache)."""
         self._pairs.clear()
         self._pool_used = 0
+        self._pool_gen += 1
         self.pair_points = 0
 
     def reset_maps(self):
@@ -462,12 +465,15 @@ class GpuBlock:
     def _inst_count(self, ji):
         return int(self.blk.instamps[ji[0]][ji[1]].pix_cumsum[-1])
 
-    def ensure_pairs(self, plans):
+    def ensure_pairs(self, plans, before_evict=None):
         """Interpolate, in one launch, every InStamp-pair block the given OutStamps need that is not cached yet.
 
         Blocks live in one pool (bump allocation).  When the pool is full the cache is dropped and the blocks of the
         current OutStamps are recomputed: the traversal order makes older blocks dead anyway, as the reference's
-        reference counts do (psfutil.py:1997-2004)."""
+        reference counts do (psfutil.py:1997-2004).  ``before_evict`` is called first in that case: a pipelined batch
+        whose systems are still unmaterialised views of the pool (DeviceSystem.assemble; the repair branch of the
+        Cholesky kernel re-assembles A from them) has to be finished before its blocks are overwritten.  Every
+        eviction bumps ``_pool_gen``; an assemble closure of an older generation refuses to run."""
         def wanted():
             seen, out = set(), []
             for p in plans:
@@ -489,6 +495,10 @@ class GpuBlock:
         total = sum(size(nA, nB) for _, nA, nB in need)
         cap = self._pool.numel() if self._pool is not None else 0
         if self._pool_used + total > cap:
+            if before_evict is not None:
+                before_evict()
+            self._pool_gen += 1
+            self.pool_evictions += 1
             cur = torch.cuda.current_stream()
             for st in side_streams_in_use():  # a pipelined batch may still be cutting its A out of the pool there
                 cur.wait_stream(st)
@@ -641,9 +651,12 @@ class GpuBlock:
         A, assemble = None, None
         if self.a_cache:
             self.ensure_pairs([p])  # no-op when coadd_batch has already requested the whole batch's blocks
-            desc, pool = self._asm_desc(p), self._pool
+            desc, pool, gen = self._asm_desc(p), self._pool, self._pool_gen
 
-            def assemble(diag_add, desc=desc, pool=pool, idx=idx, n=n, npad=npad):
+            def assemble(diag_add, desc=desc, pool=pool, idx=idx, n=n, npad=npad, gen=gen):
+                if gen != self._pool_gen:
+                    raise RuntimeError("pair-block pool was evicted after this system was planned: its blocks are gone "
+                                       "(finish the batch before the next ensure_pairs)")
                 W = torch.empty((npad, npad), dtype=torch.float64, device="cuda")
                 _lib.dev_assemble_A(C.byref(desc), ptr(idx), n, npad, ptr(pool), ptr(W), W.stride(0), float(diag_add),
                                     stream_handle())
@@ -811,9 +824,17 @@ class GpuBlock:
                 spec = self.apply_spec(k, indata, want_T32=False, want_Ti64=False)
                 self._overlap_add(p, 0, apply_T(ds, kos[u], 0, spec))
 
+        def finish_pending():
+            nonlocal pending
+            if pending is not None:
+                finish(pending)
+                pending = None
+
         for b, ks in enumerate(batches):
             plans = [self.plans[self.order[k]] for k in ks]
-            self.ensure_pairs([pl for pl in plans if pl.n > 0])
+            # (if the pool has to be evicted for this batch, the previous batch is completed first: its repair branch
+            # would otherwise re-assemble A from overwritten blocks)
+            self.ensure_pairs([pl for pl in plans if pl.n > 0], before_evict=finish_pending)
             live = []
             for k, p in zip(ks, plans):
                 if p.n == 0:
@@ -825,11 +846,9 @@ class GpuBlock:
             if b + 1 < len(batches):  # host planning of the next batch hides behind the work just enqueued
                 for k in (batches[b + 1][0], batches[b + 1][-1]):
                     self._ensure_planned(k)
-            if pending is not None:
-                finish(pending)
+            finish_pending()
             pending = (live, handle)
-        if pending is not None:
-            finish(pending)
+        finish_pending()
         return self
 
     def build_output(self, is_final: bool = True, pad_sides: str = "", download: bool = True):

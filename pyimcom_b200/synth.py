@@ -98,6 +98,61 @@ class GaussMixPSF:
         return self(g[None, :], g[:, None]) / oversamp**2
 
 
+Q_FILTER_NATIVE = (1.155, 1.456, 1.250, 1.021, 0.834, 0.689, 0.491, 1.009, 0.000, 1.159, 1.685)  # config.py:91
+OBSC = 0.31  # config.py:94
+
+
+class AiryPSF:
+    """Roman-like synthetic PSF: obscured Airy disc (x) Gaussian jitter (x) square pixel tophat, circularly truncated.
+
+    The oversampled image is the spot ``OutPSF.psf_simple_airy`` draws (psfutil.py:149-224): amplitude
+    ``J0 + J2`` of the full aperture minus ``obsc^2`` times that of the obscuration, squared, ``pi / (4 ldp^2
+    (1 - obsc^2))`` normalisation, smoothing applied as a transfer function on the padded FFT grid; here the spot may
+    also be decentred by a sub-pixel offset and is cut to zero outside ``rcut`` native pixels (the short-range PSF
+    G^(S) that PSF splitting hands to PSFGrp, coadd.py:565-569).  ``__call__`` evaluates the same function off the
+    grid (cubic spline through a finer rendering), for the point-source layer.
+    """
+
+    def __init__(self, ldp=1.25, obsc=OBSC, sigma=0.3, tophat=1.0, x0=0.0, y0=0.0, rcut=None):
+        self.ldp, self.obsc, self.sigma, self.tophat = float(ldp), float(obsc), float(sigma), float(tophat)
+        self.x0, self.y0, self.rcut = float(x0), float(y0), rcut
+        self._fine = None
+
+    def _render(self, n, ov):
+        """n x n samples at 1/ov native pixels, centred at ((n-1)/2, (n-1)/2) + (x0, y0) * ov, flux per sample."""
+        from scipy.special import jv
+
+        ldp, sig, th, ob = self.ldp * ov, self.sigma * ov, self.tophat * ov, self.obsc
+        kp = 1 + int(np.ceil(th + 6 * sig))
+        npad = n + 2 * kp
+        g = np.arange(npad) - (npad - 1) / 2.0
+        r = np.hypot(g[None, :] - self.x0 * ov, g[:, None] - self.y0 * ov) / ldp
+        amp = jv(0, np.pi * r) + jv(2, np.pi * r) - ob**2 * (jv(0, np.pi * r * ob) + jv(2, np.pi * r * ob))
+        img = np.square(amp) * (np.pi / (4.0 * ldp**2 * (1.0 - ob**2)))
+        u = np.fft.fftfreq(npad)
+        ux, uy = u[None, :npad // 2 + 1], u[:, None]
+        mtf = np.exp(-2.0 * np.pi**2 * sig**2 * (ux**2 + uy**2)) * np.sinc(ux * th) * np.sinc(uy * th)
+        img = np.fft.irfft2(np.fft.rfft2(img) * mtf, s=(npad, npad))[kp:-kp, kp:-kp]
+        if self.rcut is not None:
+            c = np.arange(n) - (n - 1) / 2.0
+            img = img * (np.hypot(c[None, :] - self.x0 * ov, c[:, None] - self.y0 * ov) < self.rcut * ov)
+        return img
+
+    def oversampled(self, npix, oversamp):
+        return self._render(npix * oversamp, oversamp)
+
+    def __call__(self, x, y):
+        from scipy.ndimage import map_coordinates
+
+        ov, half = 8, 24
+        if self._fine is None:
+            self._fine = self._render(2 * half * ov + 1, ov) * ov**2  # flux per native pixel, centre on a sample
+        x, y = np.broadcast_arrays(np.asarray(x, dtype=np.float64), np.asarray(y, dtype=np.float64))
+        c = half * ov
+        return map_coordinates(self._fine, [y.ravel() * ov + c, x.ravel() * ov + c], order=3, mode="constant",
+                               cval=0.0).reshape(x.shape)
+
+
 class SynthImage:
     """Duck-typed stand-in for coadd.InImage (the attributes InStamp/PSFGrp touch)."""
 
@@ -206,7 +261,7 @@ class SynthBlock:
     """Duck-typed coadd.Block: cfg, inimages, instamps (+ tables added by psfovl_host)."""
 
     def __init__(self, cfg: StampConfig, n_image=3, seed=12345, psf_sigmas=(0.85, 0.95, 1.05),
-                 rot_deg=3.0, star=True, asym=0.08):
+                 rot_deg=3.0, star=True, asym=0.08, psf_kind="gauss"):
         self.cfg = cfg
         self.this_sub = 0
         self.outwcs = _IdentityWCS()
@@ -223,11 +278,18 @@ class SynthBlock:
             t = rng.uniform(0.0, 1.0, size=2) * s
             sig = psf_sigmas[k % len(psf_sigmas)]
             ang = rng.uniform(0, math.pi)
-            comps = [(1.0 - asym, 0.0, 0.0, sig, sig * 1.06, ang)]
-            if asym:
-                comps.append((asym, 0.6 * math.cos(2.1 * k + 0.3), 0.6 * math.sin(2.1 * k + 0.3), sig * 1.3,
-                              sig * 1.3, 0.0))
-            im = SynthImage((100 + k, 1 + k), s * R, t, GaussMixPSF(comps), cfg)
+            if psf_kind == "airy":
+                # Roman-like: lambda/D of the configured filter (a few per cent of defocus-like spread between the
+                # exposures), jitter sigma = psf_sigmas[k] native px, decentred by up to 0.05 px, cut at 0.45 npixpsf
+                psf = AiryPSF(ldp=Q_FILTER_NATIVE[cfg.use_filter] * (1.0 + 0.02 * math.cos(1.7 * k)), sigma=sig,
+                              x0=0.05 * math.cos(ang), y0=0.05 * math.sin(ang), rcut=0.45 * cfg.npixpsf)
+            else:
+                comps = [(1.0 - asym, 0.0, 0.0, sig, sig * 1.06, ang)]
+                if asym:
+                    comps.append((asym, 0.6 * math.cos(2.1 * k + 0.3), 0.6 * math.sin(2.1 * k + 0.3), sig * 1.3,
+                                  sig * 1.3, 0.0))
+                psf = GaussMixPSF(comps)
+            im = SynthImage((100 + k, 1 + k), s * R, t, psf, cfg)
             im.partition(rng, self.star_xy)
             self.inimages.append(im)
         self.n_inimage = len(self.inimages)

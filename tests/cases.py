@@ -247,3 +247,79 @@ def partition_case(name):
     mask_b = rng.random((sca, sca)) < 0.97
     indata = rng.standard_normal((cfg.n_inframe, sca, sca)).astype(np.float32)
     return cfg, outpix, mask_a, mask_b, use, indata, sca, sp_res
+
+
+# ---------------------------------------------------------------------------------------------------
+# BASELINE.json configurations at their stated sizes (tests/golden/full_*.npz are made by the reference itself:
+# tests/golden/make_golden_full.py; the GPU tests compare the CUDA path with them directly)
+# ---------------------------------------------------------------------------------------------------
+T_SHAPE = dict(n1=4, n2=25, dtheta_arcsec=0.04, fade_kernel=1, postage_pad=0, npixpsf=42, oversamp=6,
+               instamp_pad_arcsec=0.8, n_inframe=5, uctarget=1e-6, sigmamax=0.5)
+P4_SHAPE = dict(n1=2, n2=32, dtheta_arcsec=0.0390625, postage_pad=1, npixpsf=48, oversamp=8, n_inframe=6,
+                uctarget=1e-6, sigmamax=0.5)
+SIG3 = (0.85, 0.95, 1.05)
+SIG6 = (0.85, 0.9, 0.95, 1.0, 1.05, 1.1)
+FULL_CASES = {
+    # configs[0]: tests-shaped block, CholKernel (n ~ 1.5 k, m = 729)
+    "cfg1": dict(cfg=dict(T_SHAPE, linear_algebra="Cholesky", kappaC_arr=[5e-4]), n_image=3, seed=12345, sig=SIG3,
+                 stamp=(2, 2)),
+    # configs[1]: the same block, EigenKernel with the per-pixel kappa bisection (nbis = 13)
+    "cfg2": dict(cfg=dict(T_SHAPE, linear_algebra="Eigen", kappaC_arr=[1e-5, 1e-4, 1e-3]), n_image=3, seed=12345,
+                 sig=SIG3, stamp=(2, 2)),
+    # configs[2]: paper-4 Iter stamp (FADE = 0, m = 1024, INPAD 0.6", kappa = 0, rtol 1.5e-3, 30 iterations, n ~ 2.8 k)
+    "cfg3": dict(cfg=dict(P4_SHAPE, fade_kernel=0, instamp_pad_arcsec=0.6, linear_algebra="Iterative", kappaC_arr=[0.0],
+                          iter_rtol=1.5e-3, iter_max=30), n_image=6, seed=2024, sig=SIG6, stamp=(2, 2)),
+    # the same stamp with kappa/C = 1: the well-posed variant (10-13 iterations), where CG iteration counts must be
+    # identical (at kappa/C <= 0.1 the recurrence runs 20-30 iterations and a 1e-15 relative perturbation of A already
+    # changes the reference's own iteration counts: tests/test_oracle_golden.py::test_cg_sensitivity)
+    "cfg3k": dict(cfg=dict(P4_SHAPE, fade_kernel=0, instamp_pad_arcsec=0.6, linear_algebra="Iterative",
+                           kappaC_arr=[1.0], iter_rtol=1.5e-3, iter_max=30), n_image=6, seed=2024, sig=SIG6,
+                  stamp=(2, 2)),
+    # configs[3]: the paper-4 stamp of bench.py (FADE = 3, m = 1444, INPAD 1.24", kappa/C = 6e-4, n ~ 6.2 k)
+    "p4": dict(cfg=dict(P4_SHAPE, fade_kernel=3, instamp_pad_arcsec=1.24, linear_algebra="Cholesky", kappaC_arr=[6e-4]),
+               n_image=6, seed=1000, sig=SIG6, stamp=(2, 2)),
+    # configs[4]: n_out = 3 with PSF splitting on Roman-like PSFs (obscured Airy (x) jitter Gaussian (x) pixel tophat,
+    # circularly truncated short-range PSF), three Gaussian targets
+    "cfg5": dict(cfg=dict(T_SHAPE, linear_algebra="Cholesky", kappaC_arr=[5e-4], n_out=3, psfsplit=True, sigmatarget=0.85,
+                          sigmatarget_extra=(0.93, 1.02), outpsf_extra=("GAUSSIAN", "GAUSSIAN")), n_image=3, seed=777,
+                 sig=(0.30, 0.34, 0.38), psf_kind="airy", stamp=(2, 2)),
+}
+# strides of the stored sub-samples (coprime with the tile sizes of the kernels)
+FULL_SUB = dict(a=(37, 41), b=(29, 31), t_rows=61)
+
+
+def make_full_block(name):
+    spec = FULL_CASES[name]
+    cfg = StampConfig(**spec["cfg"])
+    return SynthBlock(cfg, n_image=spec["n_image"], seed=spec["seed"], psf_sigmas=spec["sig"], star=True,
+                      psf_kind=spec.get("psf_kind", "gauss"))
+
+
+def full_errors(s, g):
+    """Deviations of one coadded OutStamp `s` (reference attribute names; a GpuOutStamp or an OracleOutStamp after
+    post_kernel / perform_coaddition) from the reference-made golden `g` = np.load(full_<case>.npz):
+    max|d| / max|ref| per array, UC absolute.  Index work (inpix_cumsum) must be identical and is asserted here."""
+    sa, sb, tr = FULL_SUB["a"], FULL_SUB["b"], FULL_SUB["t_rows"]
+
+    def rel(a, b):
+        b = np.asarray(b, dtype=np.float64)
+        return float(np.abs(np.asarray(a, dtype=np.float64) - b).max() / max(np.abs(b).max(), 1e-300))
+
+    assert np.array_equal(np.asarray(s.inpix_cumsum), g["inpix_cumsum"])
+    T = np.asarray(s.T)
+    T64 = T.astype(np.float64)
+    e = {
+        "outovlc": rel(s.outovlc, g["outovlc"]),
+        "sysmata": max(rel(s.sysmata[::sa[0], ::sa[1]], g["sysmata_sub"]), rel(np.diag(s.sysmata), g["sysmata_diag"])),
+        "mhalfb": rel(s.mhalfb[:, ::sb[0], ::sb[1]], g["mhalfb_sub"]),
+        "T": max(rel(T[:, ::tr, :], g["T_rows"]), rel(T[:, ::sb[0], ::sb[1]], g["T_sub"])),
+        # every element of T enters these two: float64 sums of the float32 matrix, normalised by the sum of |T|
+        "T_rowsum": float(np.abs(T64.sum(axis=-1) - g["T_rowsum"]).max() / np.abs(T64).sum(axis=-1).max()),
+        "T_colabs": rel(np.abs(T64).sum(axis=-2), g["T_colabs"]),
+        "UC_abs": float(np.abs(np.asarray(s.UC, dtype=np.float64) - g["UC"]).max()),
+    }
+    for nm in ("Sigma", "kappa", "outimage", "Tsum_stamp", "Tsum_inpix", "Neff"):
+        e[nm] = rel(getattr(s, nm), g[nm])
+    if "Ti64_sub" in g.files and getattr(s, "Ti64", None) is not None:
+        e["Ti64"] = rel(np.asarray(s.Ti64)[:, ::sb[0], ::sb[1]], g["Ti64_sub"])
+    return e
