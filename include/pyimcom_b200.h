@@ -174,16 +174,29 @@ typedef struct b200_solve_sys {
     int mrows;    /* number of real rows of X (rows mrows..mpad-1 are zero padding and stay zero); 0 = treat all as real.
                      A last row-tile with at most 64 real rows is solved at half cost. */
     int pad_;
+    void* work;        /* optional device scratch of b200_chol_work_bytes(npad, mpad) bytes, 1024-byte aligned: digit planes
+                          and row scales of the finished panels.  With it (for every system of the call) the long-K panel
+                          updates run on the INT8 tcgen05 tensor cores (see b200_dev_ozaki_gemm_nt); NULL: all-DMMA path. */
+    size_t work_bytes;
 } b200_solve_sys;
 
 /* scipy.linalg.cholesky + cho_solve (lakernel.py:263, 276, 304, 358) for up to B200_MAXB systems at once. */
 int b200_dev_chol_solve(const b200_solve_sys* sys, int nsys, int do_factor, int do_solve, void* stream);
+size_t b200_chol_work_bytes(int npad, int mpad);
 /* W <- A (n x n) + sum(incs) on the diagonal, identity in rows/cols n..npad-1 (lakernel.py:295-299, 356). */
 int b200_dev_pad_system(double* W, int ldw, int n, int npad, const double* A, int lda, const double* incs, int ninc,
                         void* stream);
 /* C (M x N) = [C +/-] A (M x K) * B (N x K)^T; M,N multiples of 128, K even; accumulate 0/+1/-1. */
 int b200_dev_gemm_nt(const double* A, int lda, const double* B, int ldb, double* C, int ldc, int M, int N, int K,
                      int accumulate, void* stream);
+/* C (M x N) -= A (M x K) * B (N x K)^T evaluated on the INT8 tcgen05 tensor cores from error-free integer slices of
+ * the float64 operands (Ozaki scheme: 8 radix-128 digit planes per row-scaled operand, exact INT32 accumulation in TMEM,
+ * float64 recombination; agrees with the float64 product to ~2^-50 of |A_i||B_j| per entry).  M % 128 == 0, N % 64 == 0,
+ * K % 64 == 0; work: device scratch of at least b200_ozaki_gemm_work_bytes(M, N, K) bytes.  The same kernels carry the
+ * long-K panel updates inside b200_dev_chol_solve (there the operands are sliced once per finished panel). */
+int b200_dev_ozaki_gemm_nt(const double* A, int lda, const double* B, int ldb, double* C, int ldc, int M, int N, int K,
+                           void* work, size_t work_bytes, void* stream);
+size_t b200_ozaki_gemm_work_bytes(int M, int N, int K);
 int b200_dev_transpose(const double* A, int lda, double* At, int ldat, int rows, int cols, void* stream);
 /* np.linalg.eigh (lakernel.py:162, 201, 266): block Jacobi (pairs of 16-row blocks, 32x32 sub-problems in shared
  * memory).  A (n x n, lda) is destroyed and must be padded with the identity up to ntot = 16 * (ceil(n/16) rounded up

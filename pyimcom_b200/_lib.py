@@ -45,7 +45,7 @@ class SolveSys(C.Structure):
     """b200_solve_sys"""
 
     _fields_ = [("W", vp), ("X", vp), ("Dinv", vp), ("info", vp), ("npad", i32), ("mpad", i32), ("ldw", i32),
-                ("ldx", i32), ("mrows", i32), ("pad_", i32)]
+                ("ldx", i32), ("mrows", i32), ("pad_", i32), ("work", vp), ("work_bytes", szt)]
 
 
 class PairDesc(C.Structure):
@@ -110,6 +110,7 @@ PROTOTYPES = {
     "b200_dev_chol_solve": [C.POINTER(SolveSys), i32, i32, i32, vp],
     "b200_dev_pad_system": [vp, i32, i32, i32, vp, i32, C.POINTER(f64), i32, vp],
     "b200_dev_gemm_nt": [vp, i32, vp, i32, vp, i32, i32, i32, i32, i32, vp],
+    "b200_dev_ozaki_gemm_nt": [vp, i32, vp, i32, vp, i32, i32, i32, i32, vp, szt, vp],
     "b200_dev_transpose": [vp, i32, vp, i32, i32, i32, vp],
     "b200_dev_eigh_batch": [C.POINTER(EighProblem), i32, i32, C.POINTER(i32), vp],
     "b200_dev_eigh": [vp, i32, i32, vp, i32, vp, i32, C.POINTER(i32), vp],
@@ -138,6 +139,10 @@ lib.b200_last_error.restype = C.c_char_p
 lib.b200_last_error.argtypes = []
 lib.b200_version.restype = C.c_int
 lib.b200_version.argtypes = []
+lib.b200_ozaki_gemm_work_bytes.restype = C.c_size_t
+lib.b200_ozaki_gemm_work_bytes.argtypes = [i32, i32, i32]
+lib.b200_chol_work_bytes.restype = C.c_size_t
+lib.b200_chol_work_bytes.argtypes = [i32, i32]
 lib.b200_launch_count.restype = C.c_longlong
 lib.b200_launch_count.argtypes = []
 
@@ -163,7 +168,7 @@ profile_read_raw = globals()["profile_read"]
 
 PROF_KINDS = ("chol_super_update", "potrf_diag", "chol_panel", "chol_inner_update", "back_super_update", "back_diag",
               "back_inner_update", "build_A", "build_B", "finalize", "gemm_nt", "iter_cg", "lakernel1", "eigh",
-              "assemble_A")
+              "assemble_A", "oz_slice")
 
 
 def profile_read():

@@ -7,6 +7,7 @@
 
 #include "common.cuh"
 #include "kernels.h"
+#include "ozaki.cuh"
 
 namespace b200 {
 
@@ -346,6 +347,12 @@ int b200_dev_gemm_nt(const double* A, int lda, const double* B, int ldb, double*
                      int accumulate, void* s) {
     return launch_gemm_nt(A, lda, B, ldb, C, ldc, M, N, K, accumulate, ST(s));
 }
+int b200_dev_ozaki_gemm_nt(const double* A, int lda, const double* B, int ldb, double* C, int ldc, int M, int N, int K,
+                           void* work, size_t work_bytes, void* s) {
+    return launch_ozaki_gemm_nt(A, lda, B, ldb, C, ldc, M, N, K, work, work_bytes, ST(s));
+}
+size_t b200_ozaki_gemm_work_bytes(int M, int N, int K) { return oz_gemm_work_bytes(M, N, K); }
+size_t b200_chol_work_bytes(int npad, int mpad) { return chol_work_bytes(npad, mpad); }
 int b200_dev_transpose(const double* A, int lda, double* At, int ldat, int rows, int cols, void* s) {
     return launch_transpose(A, lda, At, ldat, rows, cols, ST(s));
 }

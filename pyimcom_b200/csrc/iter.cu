@@ -12,7 +12,8 @@
 //      one warp per row, lanes over the selected columns.
 //   3. Ti[a, sel] = float32(x) (the reference's Ti is float32 from the start, lakernel.py:577), zeros elsewhere;
 //      written as f64 holding the float32-rounded value so the downstream D/N/T kernels are shared with Cholesky.
-// All reductions use a fixed thread->element mapping and fixed trees: iteration counts are reproducible.
+// All reductions use a fixed thread->element mapping and fixed trees: iteration counts are reproducible.  The
+// element-wise updates round the product before the sum, as NumPy / Numba do (no FMA contraction).
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -88,7 +89,7 @@ __global__ void __launch_bounds__(CT) k_iter_cg(const double* __restrict__ AA, i
         if (sqrt(rho) < atol) break;
         if (it > 0) {
             const double beta = rho / rho_prev;
-            for (int j = tid; j < na; j += CT) p[j] = p[j] * beta + r[j];
+            for (int j = tid; j < na; j += CT) p[j] = __dadd_rn(__dmul_rn(p[j], beta), r[j]);  // p *= beta; p += r (two roundings)
         }
         __syncthreads();
         // q = A_sel p : warp per row
@@ -113,8 +114,8 @@ __global__ void __launch_bounds__(CT) k_iter_cg(const double* __restrict__ AA, i
         nprod++;
         const double alpha = rho / pq;
         for (int j = tid; j < na; j += CT) {
-            x[j] += alpha * p[j];
-            r[j] -= alpha * q[j];
+            x[j] = __dadd_rn(x[j], __dmul_rn(alpha, p[j]));  // x += alpha * p, r -= alpha * q: NumPy rounds the
+            r[j] = __dsub_rn(r[j], __dmul_rn(alpha, q[j]));  // product before the sum (no FMA contraction)
         }
         rho_prev = rho;
         __syncthreads();
@@ -273,7 +274,7 @@ __global__ void __launch_bounds__(CT) k_iter_cg_tile(const double* __restrict__ 
             for (int j = tid; j < na; j += CT) {
 #pragma unroll
                 for (int c = 0; c < TP; c++)
-                    if (!done[c]) p[j * TP + c] = p[j * TP + c] * beta[c] + r[j * TP + c];
+                    if (!done[c]) p[j * TP + c] = __dadd_rn(__dmul_rn(p[j * TP + c], beta[c]), r[j * TP + c]);
             }
         }
         __syncthreads();
@@ -324,8 +325,8 @@ __global__ void __launch_bounds__(CT) k_iter_cg_tile(const double* __restrict__ 
 #pragma unroll
             for (int c = 0; c < TP; c++)
                 if (!done[c]) {
-                    x[j * TP + c] += alpha[c] * p[j * TP + c];
-                    r[j * TP + c] -= alpha[c] * q[j * TP + c];
+                    x[j * TP + c] = __dadd_rn(x[j * TP + c], __dmul_rn(alpha[c], p[j * TP + c]));
+                    r[j * TP + c] = __dsub_rn(r[j * TP + c], __dmul_rn(alpha[c], q[j * TP + c]));
                 }
         }
         __syncthreads();

@@ -58,6 +58,7 @@ int launch_build_B(const double* px, const double* py, const int* pcode, int n, 
 
 // linalg.cu
 int launch_chol_solve(const SolveSys* h_sys, int nsys, int do_factor, int do_solve, cudaStream_t s);
+size_t chol_work_bytes(int npad, int mpad);
 int launch_gemm_nt(const double* A, int lda, const double* B, int ldb, double* C, int ldc, int M, int N, int K,
                    int accumulate, cudaStream_t s);
 int launch_pad_system(double* W, int ldw, int n, int npad, const double* A, int lda, const double* incs, int ninc,

@@ -21,6 +21,7 @@
 
 #include "common.cuh"
 #include "kernels.h"
+#include "ozaki.cuh"
 
 namespace b200 {
 
@@ -650,6 +651,7 @@ __global__ void k_transpose(const double* __restrict__ A, int lda, double* __res
 
 bool g_attr_done = false;
 bool g_tile64 = true;
+bool g_ozaki = true;  // B200_OZAKI=0: never use the sliced INT8 path, even when the systems carry a workspace
 int g_sp = SP_DEFAULT;
 int gemm_attrs() {
     if (g_attr_done) return 0;
@@ -672,6 +674,8 @@ int gemm_attrs() {
     {
         const char* e = getenv("B200_TILE64");  // 0: the 128x128 one-CTA-per-SM tile everywhere (A/B comparisons)
         g_tile64 = !(e && e[0] == '0');
+        const char* oz = getenv("B200_OZAKI");
+        g_ozaki = !(oz && oz[0] == '0');
         const char* sp = getenv("B200_SP");
         if (sp && atoi(sp) >= 1 && atoi(sp) <= 64) g_sp = atoi(sp);
     }
@@ -681,6 +685,30 @@ int gemm_attrs() {
 }
 
 }  // namespace
+
+// ---- sliced INT8 path: workspace of one system ---------------------------------------------------
+// [scaleL npad][scaleU npad][scaleX nsp x mpad] doubles, then (1024-aligned) the digit planes of W and of X.
+struct OzWork {
+    double *scaleL, *scaleU, *scaleX;
+    int8_t *SLW, *SLX;
+};
+static size_t oz_scale_bytes(int npad, int mpad) {
+    const int nsp = npad / NB;  // (one chunk per block column covers every super-panel width)
+    return (((size_t)(2 * npad + (size_t)nsp * mpad) * sizeof(double)) + 1023) & ~(size_t)1023;
+}
+size_t chol_work_bytes(int npad, int mpad) {
+    return oz_scale_bytes(npad, mpad) + (size_t)OZ_NS * npad * ((size_t)npad + mpad) + 1024;
+}
+static OzWork oz_carve(const SolveSys& s) {
+    OzWork w;
+    uint8_t* b = reinterpret_cast<uint8_t*>(((uintptr_t)s.work + 1023) & ~(uintptr_t)1023);
+    w.scaleL = reinterpret_cast<double*>(b);
+    w.scaleU = w.scaleL + s.npad;
+    w.scaleX = w.scaleU + s.npad;
+    w.SLW = reinterpret_cast<int8_t*>(b + oz_scale_bytes(s.npad, s.mpad));
+    w.SLX = w.SLW + (size_t)OZ_NS * s.npad * s.npad;
+    return w;
+}
 
 // ---- launchers ---------------------------------------------------------------------------------
 int launch_chol_solve(const SolveSys* h_sys, int nsys, int do_factor, int do_solve, cudaStream_t st) {
@@ -700,6 +728,85 @@ int launch_chol_solve(const SolveSys* h_sys, int nsys, int do_factor, int do_sol
         mbmax = s.mpad / NB > mbmax ? s.mpad / NB : mbmax;
     }
     for (int i = nsys; i < MAXB; i++) bt.s[i] = bt.s[0];
+    // Sliced INT8 path (ozaki.cu): every system brings a workspace and the batch has more than one super-panel.
+    // Long-K products then run on tcgen05 from digit planes of the finished panels:
+    //   W part  left-looking as before (rows of L share one a-priori scale sqrt(W_ii), so the INT32 accumulators run
+    //           over the whole K range);
+    //   X parts RIGHT-looking per super-panel chunk (the rows of Z and of Ti have no a-priori bound: each finished
+    //           chunk is scaled by its exact row maxima and applied to all remaining columns at once).
+    bool oz = g_ozaki && g_tile64 && do_factor && nbmax > g_sp;
+    for (int i = 0; i < nsys && oz; i++)
+        oz = bt.s[i].work != nullptr && bt.s[i].work_bytes >= chol_work_bytes(bt.s[i].npad, bt.s[i].mpad) &&
+             bt.s[i].npad <= 60000;
+    OzWork ow[MAXB];
+    CUtensorMap mapWA[MAXB], mapWB[MAXB], mapXA[MAXB];
+    if (oz) {
+        for (int i = 0; i < nsys; i++) {
+            const SolveSys& s = bt.s[i];
+            ow[i] = oz_carve(s);
+            if (int rc = oz_make_map(&mapWA[i], ow[i].SLW, s.npad, s.npad / OZ_BK, OZ_BM)) return rc;
+            if (int rc = oz_make_map(&mapWB[i], ow[i].SLW, s.npad, s.npad / OZ_BK, OZ_BN)) return rc;
+            if (s.mpad > 0)
+                if (int rc = oz_make_map(&mapXA[i], ow[i].SLX, s.mpad, s.npad / OZ_BK, OZ_BM)) return rc;
+        }
+    }
+    const int KB = NB / OZ_BK;  // K chunks of the digit planes per block column
+    // slice rows [r0, r1) x block columns [b0, b1) of W (which: 0 = L part with the a-priori scales, 1 = L^T part with
+    // exact row maxima) and / or all rows of X (chunk index xc >= 0) for every system; one launch each for scales / digits
+    auto oz_slice = [&](int which, int wr0_blk, int wr1_blk, int wb0, int wb1, bool from_end, int xc, int xb0, int xb1) -> int {
+        OzSliceBatch sb;
+        int nj = 0, rows_max = 0, nkb_max = 0;
+        OzSliceBatch mx;  // jobs that need an exact-maximum scale pass first
+        int nmx = 0, mx_rows = 0;
+        for (int q = 0; q < nsys; q++) {
+            const SolveSys& s = bt.s[q];
+            const int nb = s.npad / NB;
+            if (which >= 0) {
+                int r0 = wr0_blk, r1 = wr1_blk, b0 = wb0, b1 = wb1;
+                r1 = r1 < nb ? r1 : nb;
+                b1 = b1 < nb ? b1 : nb;
+                if (r1 > r0 && b1 > b0) {
+                    OzSliceSys j{s.W, s.ldw, r0 * NB, (r1 - r0) * NB, b0 * KB, (b1 - b0) * KB,
+                                 which == 0 ? ow[q].scaleL : ow[q].scaleU, ow[q].SLW, s.npad, which == 1};
+                    sb.s[nj++] = j;
+                    rows_max = j.nrows > rows_max ? j.nrows : rows_max;
+                    nkb_max = j.nkb > nkb_max ? j.nkb : nkb_max;
+                    if (which == 1) {
+                        mx.s[nmx++] = j;
+                        mx_rows = j.nrows > mx_rows ? j.nrows : mx_rows;
+                    }
+                }
+            }
+            if (xc >= 0 && s.mpad > 0) {
+                int b0 = xb0, b1 = xb1;
+                if (from_end) {  // block columns counted from the end of this system
+                    const int hi = nb - xb0, lo = nb - xb1 > 0 ? nb - xb1 : 0;
+                    b0 = lo;
+                    b1 = hi;
+                }
+                b1 = b1 < nb ? b1 : nb;
+                if (b1 > b0) {
+                    OzSliceSys j{s.X, s.ldx, 0, s.mpad, b0 * KB, (b1 - b0) * KB, ow[q].scaleX + (size_t)xc * s.mpad,
+                                 ow[q].SLX, s.mpad, 0};
+                    // (the scale array is indexed by absolute row; chunk xc has its own array)
+                    sb.s[nj++] = j;
+                    mx.s[nmx++] = j;
+                    rows_max = j.nrows > rows_max ? j.nrows : rows_max;
+                    mx_rows = j.nrows > mx_rows ? j.nrows : mx_rows;
+                    nkb_max = j.nkb > nkb_max ? j.nkb : nkb_max;
+                }
+            }
+        }
+        if (nj == 0) return 0;
+        prof_begin(PROF_OZ_SLICE, st);
+        if (nmx > 0)
+            if (int rc = oz_launch_scale_max(mx, nmx, mx_rows, st)) return rc;
+        const int rc = oz_launch_slice(sb, nj, rows_max, nkb_max, st);
+        double bytes = 0;
+        for (int j = 0; j < nj; j++) bytes += 16.0 * sb.s[j].nrows * (double)sb.s[j].nkb * OZ_BK;
+        prof_end(bytes, st);
+        return rc;
+    };
     // algorithmic flop counts of the launches (profiling only): tiles actually computed x 2*128^2*K
     // right-hand-side row tiles of system q, a half tile (x_half_tile) counting as half the work
     auto mb_eff = [&](int q) {
@@ -724,9 +831,47 @@ int launch_chol_solve(const SolveSys* h_sys, int nsys, int do_factor, int do_sol
     const double tri = g_tile64 ? 0.75 : 1.0;  // the strip kernels skip the zero quarter of the triangular inverse
     if (do_factor) {
         const int SP = g_sp;
+        if (oz) {  // a-priori row scales of L from the diagonal of W, before it is overwritten
+            OzSliceBatch sb;
+            int rows_max = 0;
+            for (int q = 0; q < nsys; q++) {
+                sb.s[q] = OzSliceSys{bt.s[q].W, bt.s[q].ldw, 0, bt.s[q].npad, 0, 0, ow[q].scaleL, ow[q].SLW, bt.s[q].npad, 0};
+                rows_max = bt.s[q].npad > rows_max ? bt.s[q].npad : rows_max;
+            }
+            if (int rc = oz_launch_scale_diag(sb, nsys, rows_max, st)) return rc;
+        }
         for (int c0 = 0; c0 < nbmax; c0 += SP) {
             const int c1 = c0 + SP < nbmax ? c0 + SP : nbmax;
-            if (c0 > 0) {
+            if (c0 > 0 && oz) {
+                // W[i][j] -= L[i][0:c0] L[j][0:c0]^T  (c0 <= j < c1, j <= i) on the INT8 tensor cores
+                OzBatch gb;
+                int mt = 0, nt = 0;
+                double tiles = 0;
+                for (int q = 0; q < nsys; q++) {
+                    const SolveSys& s = bt.s[q];
+                    const int nb = s.npad / NB;
+                    OzSys& g = gb.s[q];
+                    g.mapA = mapWA[q];
+                    g.mapB = mapWB[q];
+                    g.scaleA = g.scaleB = ow[q].scaleL;
+                    g.C = s.W + (size_t)c0 * NB * s.ldw + (size_t)c0 * NB;
+                    g.ldc = s.ldw;
+                    const int cc1 = c1 < nb ? c1 : nb;
+                    g.m_tiles = nb > c0 ? nb - c0 : 0;
+                    g.n_tiles = cc1 > c0 ? (cc1 - c0) * (NB / OZ_BN) : 0;
+                    g.rowA0 = g.rowB0 = g.rowC0 = g.colC0 = c0 * NB;
+                    g.kb0 = 0;
+                    g.kb1 = c0 * KB;
+                    g.tri = 1;
+                    mt = g.m_tiles > mt ? g.m_tiles : mt;
+                    nt = g.n_tiles > nt ? g.n_tiles : nt;
+                    for (int j = c0; j < cc1; j++) tiles += (nb - j) - 0.25;
+                }
+                for (int q = nsys; q < MAXB; q++) gb.s[q] = gb.s[0];
+                prof_begin(PROF_CHOL_SUPER, st);
+                if (int rc = oz_launch_gemm(gb, nsys, mt, nt, st)) return rc;
+                prof_end(tiles * tile_flops * c0 * NB, st);
+            } else if (c0 > 0) {
                 prof_begin(PROF_CHOL_SUPER, st);
                 if (g_tile64)
                     k_chol_super_update<true><<<dim3(2 * (c1 - c0), 2 * (nbmax - c0 + mbmax), nsys), GT2, GEMM2_SMEM, st>>>(bt, c0, c1);
@@ -760,6 +905,45 @@ int launch_chol_solve(const SolveSys* h_sys, int nsys, int do_factor, int do_sol
                     B200_LAUNCHED(1);
                 }
             }
+            if (oz && c1 < nbmax) {
+                // the finished super-panel becomes digit planes: L rows below it (a-priori scales), its own rows of
+                // L^T to the right of it (exact row maxima; read by the backward solve), and the chunk of Z
+                const int xc = c0 / SP;
+                if (int rc = oz_slice(0, c1, nbmax, c0, c1, false, mbmax > 0 ? xc : -1, c0, c1)) return rc;
+                if (mbmax > 0) {
+                    if (int rc = oz_slice(1, c0, c1, c0 + 1, nbmax, false, -1, 0, 0)) return rc;
+                    // X[t][j] -= Z[t][c0:c1] L[j][c0:c1]^T for every block column j >= c1 (right-looking)
+                    OzBatch gb;
+                    int mt = 0, nt = 0;
+                    double tiles = 0;
+                    for (int q = 0; q < nsys; q++) {
+                        const SolveSys& s = bt.s[q];
+                        const int nb = s.npad / NB;
+                        OzSys& g = gb.s[q];
+                        g.mapA = mapXA[q];
+                        g.mapB = mapWB[q];
+                        g.scaleA = ow[q].scaleX + (size_t)xc * s.mpad;
+                        g.scaleB = ow[q].scaleL;
+                        g.C = s.X + (size_t)c1 * NB;
+                        g.ldc = s.ldx;
+                        g.m_tiles = nb > c1 ? s.mpad / NB : 0;
+                        g.n_tiles = nb > c1 ? (nb - c1) * (NB / OZ_BN) : 0;
+                        g.rowA0 = 0;
+                        g.rowB0 = c1 * NB;
+                        g.rowC0 = g.colC0 = 0;
+                        g.kb0 = c0 * KB;
+                        g.kb1 = c1 * KB;
+                        g.tri = 0;
+                        mt = g.m_tiles > mt ? g.m_tiles : mt;
+                        nt = g.n_tiles > nt ? g.n_tiles : nt;
+                        if (nb > c1) tiles += (double)(s.mpad / NB) * (nb - c1);
+                    }
+                    for (int q = nsys; q < MAXB; q++) gb.s[q] = gb.s[0];
+                    prof_begin(PROF_CHOL_SUPER, st);
+                    if (int rc = oz_launch_gemm(gb, nsys, mt, nt, st)) return rc;
+                    prof_end(tiles * tile_flops * (c1 - c0) * NB, st);
+                }
+            }
         }
         B200_CUDA(cudaGetLastError());
     }
@@ -769,7 +953,7 @@ int launch_chol_solve(const SolveSys* h_sys, int nsys, int do_factor, int do_sol
         const int SP = g_sp;
         for (int e0 = 0; e0 < nbmax; e0 += SP) {
             const int e1 = e0 + SP < nbmax ? e0 + SP : nbmax;
-            if (e0 > 0) {
+            if (e0 > 0 && !oz) {
                 prof_begin(PROF_BACK_SUPER, st);
                 if (g_tile64)
                     k_back_super_update<true><<<dim3(2 * (e1 - e0), 2 * mbmax, nsys), GT2, GEMM2_SMEM, st>>>(bt, e0, e1);
@@ -801,6 +985,42 @@ int launch_chol_solve(const SolveSys* h_sys, int nsys, int do_factor, int do_sol
                     prof_end(mbsum * (e1 - 1 - kk) * tile_flops * NB, st);
                     B200_LAUNCHED(1);
                 }
+            }
+            if (oz && e1 < nbmax) {
+                // the finished chunk of Ti (block columns [nb - e1, nb - e0) of each system) is sliced and applied to all
+                // columns to its left:  X[t][j] -= Ti[t][lo:hi] L[lo:hi][j]  (j < lo; L^T rows live in W's upper triangle)
+                const int xc = e0 / SP;
+                if (int rc = oz_slice(-1, 0, 0, 0, 0, true, xc, e0, e1)) return rc;
+                OzBatch gb;
+                int mt = 0, nt = 0;
+                double tiles = 0;
+                for (int q = 0; q < nsys; q++) {
+                    const SolveSys& s = bt.s[q];
+                    const int nb = s.npad / NB;
+                    const int hi = nb - e0, lo = nb - e1 > 0 ? nb - e1 : 0;
+                    OzSys& g = gb.s[q];
+                    g.mapA = mapXA[q];
+                    g.mapB = mapWB[q];
+                    g.scaleA = ow[q].scaleX + (size_t)xc * s.mpad;
+                    g.scaleB = ow[q].scaleU;
+                    g.C = s.X;
+                    g.ldc = s.ldx;
+                    g.m_tiles = (hi > lo && lo > 0) ? s.mpad / NB : 0;
+                    g.n_tiles = (hi > lo && lo > 0) ? lo * (NB / OZ_BN) : 0;
+                    g.rowA0 = 0;
+                    g.rowB0 = 0;
+                    g.rowC0 = g.colC0 = 0;
+                    g.kb0 = lo * KB;
+                    g.kb1 = hi > lo ? hi * KB : lo * KB;
+                    g.tri = 0;
+                    mt = g.m_tiles > mt ? g.m_tiles : mt;
+                    nt = g.n_tiles > nt ? g.n_tiles : nt;
+                    if (hi > lo && lo > 0) tiles += (double)(s.mpad / NB) * lo * (hi - lo);
+                }
+                for (int q = nsys; q < MAXB; q++) gb.s[q] = gb.s[0];
+                prof_begin(PROF_BACK_SUPER, st);
+                if (int rc = oz_launch_gemm(gb, nsys, mt, nt, st)) return rc;
+                prof_end(tiles * tile_flops * NB, st);
             }
         }
         B200_CUDA(cudaGetLastError());

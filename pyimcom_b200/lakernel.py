@@ -138,6 +138,9 @@ def chol_solve_batch(Ws, Xs, factor=True, solve=True, mrows=None):
     nsys = len(Ws)
     assert 0 < nsys <= _lib.MAXB
     info = torch.zeros(nsys, dtype=torch.int32, device="cuda")
+    # sliced INT8 (tcgen05) path for the long-K panel updates: needs a per-system scratch for the digit planes; only
+    # worth it when the batch has more than one super-panel of block columns
+    use_oz = OZAKI and factor and max(W.shape[0] for W in Ws) > OZAKI_MIN_N
     sysarr = (_lib.SolveSys * nsys)()
     keep = []
     for k in range(nsys):
@@ -153,6 +156,11 @@ def chol_solve_batch(Ws, Xs, factor=True, solve=True, mrows=None):
         s.mpad = X.shape[0] if X is not None else 0
         s.ldx = X.stride(0) if X is not None else npad
         s.mrows = int(mrows[k]) if (mrows is not None and X is not None) else 0
+        if use_oz:
+            nbytes = int(_lib.lib.b200_chol_work_bytes(npad, s.mpad))
+            work = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
+            keep.append(work)
+            s.work, s.work_bytes = work.data_ptr(), nbytes
     _lib.dev_chol_solve(sysarr, nsys, int(factor), int(solve and Xs is not None), stream_handle())
     return info, keep
 
@@ -195,6 +203,8 @@ def _padded_system(ds: DeviceSystem, incs):
     return W
 
 
+OZAKI = os.environ.get("B200_OZAKI", "1") != "0"  # long-K panel updates on the INT8 tcgen05 tensor cores (csrc/ozaki.cu)
+OZAKI_MIN_N = 512  # (the library itself only switches over when there is more than one super-panel)
 SOLVE_STREAMS = int(os.environ.get("B200_SOLVE_STREAMS", "3"))  # concurrent groups of systems in the batched factorisation (1 = everything on the caller's stream)
 STREAM_PRIORITIES = os.environ.get("B200_STREAM_PRIORITIES", "1") != "0"
 _SIDE = {}

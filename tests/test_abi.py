@@ -50,7 +50,7 @@ def test_ctypes_prototypes_match_header(lib):
 def test_struct_layouts(lib):
     # sizes a C compiler gives the three structs that cross the boundary (LP64)
     assert ctypes.sizeof(lib.TableRef) == 24
-    assert ctypes.sizeof(lib.SolveSys) == 56
+    assert ctypes.sizeof(lib.SolveSys) == 72
     assert ctypes.sizeof(lib.FinalizeArgs) == 184
     assert ctypes.sizeof(lib.PairDesc) == 40
     assert ctypes.sizeof(lib.EighProblem) == 40

@@ -216,22 +216,34 @@ def test_config3_inside_the_cg_spread():
     o0, k0 = oracle_full_stamp("cfg3")
     T0, n0 = k0.f64[0]["Ti"].astype(np.float64), k0.f64[0]["niter"].ravel()
     scale = np.abs(T0).max()
-    spread_all, spread_eq, flips = 0.0, 0.0, 0
+    spread_all, flips, dmax = 0.0, 0, 0
+    q_eq = np.zeros(3)  # median / 90 % / 99 % quantiles of the per-pixel deviation where the counts agree
+
+    def quant(d):
+        return np.array([np.median(d), np.quantile(d, 0.9), np.quantile(d, 0.99)])
+
     for _ in range(2):
         _, k1 = oracle_full_stamp("cfg3", sysmata=perturb)
         d = np.abs(k1.f64[0]["Ti"] - T0).max(axis=1) / scale
         n1 = k1.f64[0]["niter"].ravel()
         spread_all, flips = max(spread_all, d.max()), max(flips, int((n1 != n0).sum()))
-        spread_eq = max(spread_eq, d[n1 == n0].max())
+        dmax = max(dmax, int(np.abs(n1.astype(int) - n0).max()))
+        q_eq = np.maximum(q_eq, quant(d[n1 == n0]))
     Tg = s.Ti64[0] if s.Ti64 is not None else s.T[0]
     ng = s.extras[0]["niter"].ravel()
     dg = np.abs(Tg - T0).max(axis=1) / scale
-    print(f"config 3: oracle spread {spread_all:.2e} (equal counts {spread_eq:.2e}, {flips} flips); GPU vs oracle "
-          f"{dg.max():.2e} (equal counts {dg[ng == n0].max():.2e}, {(ng != n0).sum()} flips)")
+    qg = quant(dg[ng == n0])
+    print(f"config 3: oracle under a 1e-15 perturbation: max {spread_all:.2e}, {flips} of {n0.size} counts change (by <= "
+          f"{dmax}), equal-count quantiles {q_eq}; GPU vs oracle: max {dg.max():.2e}, {(ng != n0).sum()} counts differ (by <= "
+          f"{np.abs(ng.astype(int) - n0).max()}), equal-count quantiles {qg}, equal-count max {dg[ng == n0].max():.2e}")
     assert rel(s.sysmata, o0.sysmata) < P64 and rel(s.mhalfb, o0.mhalfb) < P64
-    assert dg.max() < 3 * spread_all and (ng != n0).sum() < 3 * flips  # (i)
-    assert dg[ng == n0].max() < 3 * spread_eq  # (ii)
-    assert np.abs(ng.astype(int) - n0).max() <= 2
+    # (i) same worst case (a pixel whose count changed moves by ~1e-2), comparable number of changed counts
+    assert dg.max() < 2 * spread_all and (ng != n0).sum() < 3 * flips
+    assert np.abs(ng.astype(int) - n0).max() <= dmax + 1
+    # (ii) where the counts agree the deviations follow the same heavy-tailed distribution (the maximum of ~900
+    # samples of it is not a stable statistic: bounded by the changed-count level instead)
+    assert np.all(qg < 2.5 * q_eq), (qg, q_eq)
+    assert dg[ng == n0].max() < spread_all
     # (iii) stopping rule on the true residual, every 5th output pixel
     relv = k0.f64[0]["relevant"]
     A, mB = s.sysmata, s.mhalfb[0]
