@@ -42,13 +42,17 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 from pyimcom_b200.synth import StampConfig, SynthBlock  # noqa: E402
 
-# DRAM traffic of the dominant kernel from the committed ncu capture (profiles/ncu_r01.txt: k_chol_super_update,
-# grid (8,74,6) = super-panel c0=24 of 49 block columns for the 6 systems of one solve stream, 2.48 ms under ncu):
-# dram__bytes_read.sum + dram__bytes_write.sum of that launch
-NCU_TRAFFIC_BYTES = 844.72192e6 + 102.279936e6
-NCU_TRAFFIC_NOTE = ("ncu --set full, one launch of k_chol_super_update (super-panel c0=24 of 49 block columns, 6 systems of one "
-                    "solve stream): 0.845 GB read + 0.102 GB written vs 8.8e10 flop => 93 flop/B, far above the FP64 ridge "
-                    "(~5.5 flop/B); tensor pipe 93.1 % busy")
+# DRAM traffic of the dominant kernel: NOT measured by this run (ncu cannot run inside it).  It is read from the summary
+# of the committed `ncu --set full` capture of the same kernel on the same workload (profiles/ncu_r02_top.json, written
+# by tools/ncu_summary.py from the .ncu-rep; fields: kernel, grid, dram_bytes_read, dram_bytes_write, flops, source).
+def ncu_traffic():
+    try:
+        d = json.load(open(os.path.join(ROOT, "profiles", "ncu_r02_top.json")))
+        return float(d["dram_bytes_read"]) + float(d["dram_bytes_write"]), d
+    except (OSError, KeyError, ValueError):
+        return None, {"note": "profiles/ncu_r02_top.json missing"}
+
+
 METRIC = "coadd_output_pixels_per_sec"
 UNIT = "output px/s"
 SEED0 = 1000
@@ -185,9 +189,12 @@ def run_reference(args):
     cores = os.cpu_count() or 1
     blk = make_block(0)
     cfg = blk.cfg
-    sample = 4  # OutStamps per step: a bounded sample of the block (~5 s of CPU work per step on 16 cores)
+    # OutStamps per step: 16 (a 4x4 corner of the block, so that the reference's SysMatA reuse of InStamp-pair blocks is
+    # as on the GPU arm), fewer only if K steps would not finish within ~7 minutes on this host
     for _ in range(args.warmup if args.warmup < 2 else 1):
         cpu_stamps(blk, 1, cores)
+    t1 = cpu_stamps(blk, 2, cores) / 2
+    sample = int(max(4, min(16, 420.0 / max(args.steps, 1) / max(t1, 1e-3))))
     times = [cpu_stamps(blk, sample, cores) for _ in range(args.steps)]
     t = float(np.mean(times))
     val = sample * cfg.n2**2 / t
@@ -212,7 +219,7 @@ def run_gpu(args):
     from pyimcom_b200 import pyimcom_croutines as G
     from pyimcom_b200.coadd import GpuBlock
     from pyimcom_b200.psfovl_host import PSFTables
-    from pyimcom_b200.shard import gather_cube
+    from pyimcom_b200.shard import assign_stamp_groups, gather_cube, reduce_cube
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -226,6 +233,8 @@ def run_gpu(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    if args.strong:
+        return run_strong(args, world, rank, barrier)
     blk = make_block(rank)
     cfg = blk.cfg
     tab = PSFTables(blk, G.iD5512C, G.gridD5512C, dedup=True)  # PSF-overlap tables (row f1): built once, outside the clock
@@ -250,6 +259,21 @@ def run_gpu(args):
             best = min(best, e0.elapsed_time(e1) * 1e-3)
     fp64_peak = 2 * N**3 / best / 1e12
     del a, b, c
+    # INT8 tensor peak of this GPU (the pipe the long-K updates run on): cuBLASLt IGEMM through torch._int_mm
+    NI = 8192
+    ai = torch.randint(-64, 64, (NI, NI), dtype=torch.int8, device="cuda")
+    bi = torch.randint(-64, 64, (NI, NI), dtype=torch.int8, device="cuda")
+    best = 1e9
+    for it in range(6):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        ci = torch._int_mm(ai, bi)
+        e1.record()
+        torch.cuda.synchronize()
+        if it:
+            best = min(best, e0.elapsed_time(e1) * 1e-3)
+    int8_peak = 2 * NI**3 / best / 1e12
+    del ai, bi, ci
 
     def step_resident():
         gb.reset_maps()
@@ -337,10 +361,27 @@ def run_gpu(args):
     t_e2e = e0.elapsed_time(e1) * 1e-3
     h2d = int(g2.h2d_bytes)
     d2h = int(sum(v.nbytes for v in maps.values()))
+    gather_verified = None
     if world > 1:
         tt = torch.tensor([t_res, t_e2e], dtype=torch.float64, device="cuda")
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         t_res, t_e2e = float(tt[0]), float(tt[1])
+        # the gathered cube is checked, outside the clock: every rank coadded a DIFFERENT block (seed 1000 + rank); its
+        # checksums (sum, sum of squares, max |.| in float64) travel by all_gather and rank 0 recomputes them from the slice
+        # of the gathered cube that should hold that rank's block
+        def checks(t):
+            t = t.double()
+            return torch.stack([t.sum(), t.square().sum(), t.abs().max()])
+
+        cube = gather_cube(gb.out_map, world, rank)
+        mine = checks(gb.out_map)
+        allc = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(allc, mine)
+        if rank == 0:
+            allc = torch.stack(allc)
+            got = torch.stack([checks(cube[r]) for r in range(world)])
+            distinct = len({tuple(row.tolist()) for row in allc}) == world
+            gather_verified = bool(torch.equal(got, allc) and distinct and bool(torch.isfinite(allc).all()))
     if rank == 0:
         peaks = {}
         try:
@@ -350,7 +391,9 @@ def run_gpu(args):
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
         hbm_src = "MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
         TENSOR = ("chol_super_update", "chol_panel", "chol_inner_update", "back_super_update", "back_diag",
-                  "back_inner_update", "gemm_nt", "potrf_diag")
+                  "back_inner_update", "gemm_nt", "potrf_diag", "oz_gemm")
+        ns = int(_lib.lib.b200_ozaki_slices())
+        i8_per_f64 = ns * (ns + 1) // 2  # INT8 products evaluated per float64 product (digit pairs t + u < NS)
 
         def stage_table(pr, t_total):
             out = {}
@@ -360,49 +403,69 @@ def run_gpu(args):
                 out[name] = {"launches": cnt, "ms_total": round(ms, 3), "share_of_step": round(ms * 1e-3 / t_total, 4),
                              "achieved": round(rate, 3), "unit": "TFLOP/s" if tensor else "GB/s",
                              "frac": round(rate / (fp64_peak if tensor else hbm_peak), 4)}
+                if name == "oz_gemm":  # work is counted in float64-equivalent flops; the pipe executes 36x that in INT8
+                    out[name].update(unit="TFLOP/s float64-equivalent", frac_of_dgemm_peak=out[name].pop("frac"),
+                                     int8_tops=round(rate * i8_per_f64, 1),
+                                     frac_of_int8_peak=round(rate * i8_per_f64 / int8_peak, 4))
             return out
 
-        def dmma_total(pr):
-            ms = sum(pr[k][0] for k in pr if k.startswith(("chol_", "back_")))
-            fl = sum(pr[k][1] for k in pr if k.startswith(("chol_", "back_")))
-            return ms, fl
+        def tensor_total(pr):
+            ks = [k for k in pr if k.startswith(("chol_", "back_", "oz_gemm"))]
+            return sum(pr[k][0] for k in ks), sum(pr[k][1] for k in ks)
 
         stages = stage_table(prof, t_prof)
-        dom = "chol_super_update"
+        dom = "oz_gemm" if "oz_gemm" in prof else "chol_super_update"
         ms, work, cnt = prof.get(dom, (0.0, 0.0, 0))
-        ach = work / (ms * 1e-3) / 1e12 if ms > 0 else 0.0
-        tensor_ms, tensor_fl = dmma_total(prof)
-        roofline = {"bound": "tensor", "kernel": "k_chol_super_update (FP64 DMMA m8n8k4 tile GEMM, long-K)",
-                    "achieved": round(ach, 3), "peak": round(fp64_peak, 3), "unit": "TFLOP/s",
-                    "frac": round(ach / fp64_peak, 4),
-                    "traffic": NCU_TRAFFIC_BYTES,
-                    "traffic_note": NCU_TRAFFIC_NOTE,
-                    "peak_source": f"cuBLAS DGEMM {N}^3 through torch.matmul, best of 5, measured in this run "
-                                   "(MEASURED_PEAKS.json has no FP64 entry)",
-                    "launches": cnt, "avg_launch_ms": round(ms / max(cnt, 1), 4),
-                    "flops_per_launch": work / max(cnt, 1),
+        eq = work / (ms * 1e-3) / 1e12 if ms > 0 else 0.0  # float64-equivalent TFLOP/s of the dominant kernel
+        tensor_ms, tensor_fl = tensor_total(prof)
+        traffic, traffic_src = ncu_traffic()
+        if dom == "oz_gemm":
+            ach, peak, kname = eq * i8_per_f64, int8_peak, (
+                "k_oz_gemm: long-K panel updates of the Cholesky / triangular solves as error-free sliced INT8 products on "
+                f"tcgen05 (TMA-fed, TMEM accumulators; {ns} digit planes per operand = {i8_per_f64} INT8 products per "
+                "float64 product)")
+            peak_src = (f"cuBLASLt INT8 GEMM {NI}^3 through torch._int_mm, best of 5, measured in this run (nominal dense "
+                        "INT8 4500 TOP/s; MEASURED_PEAKS.json bf16 burst x 2 = "
+                        f"{2 * float(peaks.get('bf16_tflops', 0)):.0f})")
+            unit = "TFLOP/s"
+        else:
+            ach, peak, kname = eq, fp64_peak, "k_chol_super_update (FP64 DMMA m8n8k4 tile GEMM, long-K)"
+            peak_src = f"cuBLAS DGEMM {N}^3 through torch.matmul, best of 5, measured in this run"
+            unit = "TFLOP/s"
+        roofline = {"bound": "tensor", "kernel": kname, "achieved": round(ach, 3), "peak": round(peak, 3), "unit": unit,
+                    "frac": round(ach / peak, 4), "traffic": traffic, "traffic_source": traffic_src,
+                    "ops": ("INT8 multiply-adds x 2 executed by tcgen05.mma.kind::i8 = float64-equivalent flops x "
+                            f"{i8_per_f64}") if dom == "oz_gemm" else "float64 flops",
+                    "fp64_equivalent": {"achieved": round(eq, 3), "unit": "TFLOP/s", "dgemm_peak": round(fp64_peak, 3),
+                                        "ratio_to_dgemm_peak": round(eq / fp64_peak, 4),
+                                        "dgemm_peak_source": f"cuBLAS DGEMM {N}^3 through torch.matmul, best of 5, this run"},
+                    "peak_source": peak_src, "launches": cnt, "avg_launch_ms": round(ms / max(cnt, 1), 4),
+                    "flops_per_launch": work / max(cnt, 1) * (i8_per_f64 if dom == "oz_gemm" else 1),
                     "note": (f"per-launch events are recorded on a repeat of the K timed steps (same work, same {n_streams} "
                              "concurrent solve streams, batches pipelined): a launch's event interval includes the time it "
                              "shares the SMs with the other streams' kernels; 'serialized' repeats one step on one stream"),
-                    "all_dmma_kernels": {"achieved": round(tensor_fl / (tensor_ms * 1e-3) / 1e12, 3) if tensor_ms else 0,
-                                         "share_of_step": round(tensor_ms * 1e-3 / t_prof, 4),
-                                         "flops_per_step": tensor_fl / max(args.steps, 1),
-                                         "achieved_wall": round(tensor_fl / t_res / 1e12, 3)},
+                    "all_tensor_kernels": {"fp64_equivalent_achieved": round(tensor_fl / (tensor_ms * 1e-3) / 1e12, 3) if tensor_ms else 0,
+                                           "share_of_step": round(tensor_ms * 1e-3 / t_prof, 4),
+                                           "fp64_equivalent_flops_per_step": tensor_fl / max(args.steps, 1),
+                                           "fp64_equivalent_achieved_wall": round(tensor_fl / t_res / 1e12, 3),
+                                           "ratio_to_dgemm_peak_wall": round(tensor_fl / t_res / 1e12 / fp64_peak, 4)},
                     "ms_per_step_with_events": round(1e3 * t_prof / args.steps, 3),
                     "hbm_peak_gbs": hbm_peak, "hbm_peak_source": hbm_src, "stages": stages}
         if prof_serial:
             t_ser = sum(v[0] for v in prof_serial.values()) * 1e-3
             ms_s, work_s, cnt_s = prof_serial.get(dom, (0.0, 0.0, 0))
-            ach_s = work_s / (ms_s * 1e-3) / 1e12 if ms_s > 0 else 0.0
-            sm, sf = dmma_total(prof_serial)
-            roofline["serialized"] = {"achieved": round(ach_s, 3), "frac": round(ach_s / fp64_peak, 4), "launches": cnt_s,
+            eq_s = work_s / (ms_s * 1e-3) / 1e12 if ms_s > 0 else 0.0
+            ach_s = eq_s * (i8_per_f64 if dom == "oz_gemm" else 1)
+            sm, sf = tensor_total(prof_serial)
+            roofline["serialized"] = {"achieved": round(ach_s, 3), "frac": round(ach_s / peak, 4), "launches": cnt_s,
                                       "avg_launch_ms": round(ms_s / max(cnt_s, 1), 4),
-                                      "all_dmma_kernels": {"achieved": round(sf / (sm * 1e-3) / 1e12, 3) if sm else 0},
+                                      "fp64_equivalent_achieved": round(eq_s, 3),
+                                      "all_tensor_kernels": {"fp64_equivalent_achieved": round(sf / (sm * 1e-3) / 1e12, 3) if sm else 0},
                                       "stages": stage_table(prof_serial, max(t_ser, 1e-9))}
         cores = os.cpu_count() or 1
         cpu = None
         if world == 1 and not args.no_cpu:
-            ncpu = 8  # ~10 s of CPU work on 16 cores
+            ncpu = 16  # ~16 s of CPU work on 16 cores (a 4x4 corner of the block: InStamp-pair blocks are reused as on the GPU)
             tcpu = cpu_stamps(blk, ncpu, cores)
             cpu = {"value": ncpu * cfg.n2**2 / tcpu, "unit": UNIT, "cores": cores, "kind": "port",
                    "sample": f"first {ncpu} OutStamps of the same block, oracle/ (C + OpenMP interpolation on all cores, "
@@ -420,6 +483,81 @@ def run_gpu(args):
                         "host_ms_prepare_run_download": e2e_host[-args.steps:]},
                 "gpu_launches": int(launches), "stamps_per_sec": world * n_stamps * args.steps / t_res,
                 "clocks": clk.summary(), "roofline": roofline, "cpu_baseline": cpu}
+        if world > 1:
+            line["gather_verified"] = gather_verified
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_strong(args, world, rank, barrier):
+    """Strong scaling of ONE block: contiguous strips of whole 2x2 stamp-group rows per rank, every rank holds
+    the block's pixels and tables (the one-stamp halo of InStamps comes for free), seam InStamp-pair blocks are
+    recomputed on both sides, zero-initialised full cubes are sum-reduced on rank 0.  Rank 0 also coadds the unsharded
+    block (outside the clock) and checks the reduced cube against it: identical away from the strip seams, and equal to
+    float32 rounding of the seam overlap-adds on them."""
+    import torch
+    import torch.distributed as dist
+
+    from pyimcom_b200 import _lib
+    from pyimcom_b200 import pyimcom_croutines as G
+    from pyimcom_b200.coadd import GpuBlock
+    from pyimcom_b200.psfovl_host import PSFTables
+    from pyimcom_b200.shard import assign_stamp_groups, reduce_cube
+
+    blk = make_block(0, n1=args.strong_n1)
+    cfg = blk.cfg
+    tab = PSFTables(blk, G.iD5512C, G.gridD5512C, dedup=True)
+    mine = assign_stamp_groups(cfg.n1P, world, rank)
+    gb = GpuBlock(blk, tab).prepare(stamps=mine)
+
+    def step():
+        gb.reset_maps()
+        gb.reset_cache()
+        gb.run()
+        cube = gb.out_map.clone()
+        return reduce_cube(cube, world)
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    n0 = _lib.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        cube = step()
+    e1.record()
+    barrier()
+    t = torch.tensor([e0.elapsed_time(e1) * 1e-3], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    t = float(t[0])
+    if rank == 0:
+        full = GpuBlock(blk, tab).prepare()
+        full.run()
+        ref = full.out_map
+        same = (cube == ref)
+        scale = float(ref.abs().max())
+        # rows of the map that belong to a strip seam: the fade borders of the stamps on either side overlap there
+        fk, n2 = cfg.fade_kernel, cfg.n2
+        per = (len(range(1, cfg.n1P + 1, 2)) + world - 1) // world
+        seam = torch.zeros(ref.shape[-2], dtype=torch.bool, device=ref.device)
+        for r in range(1, world):
+            y = 2 * per * r * n2
+            seam[max(0, y - 0):y + 2 * fk] = True
+        off_seam_equal = bool(same[..., ~seam, :].all())
+        max_dev = float((cube - ref).abs().max()) / scale
+        n_total = cfg.n1P * cfg.n1P
+        line = {"metric": METRIC, "value": n_total * cfg.n2**2 * args.steps / t, "unit": UNIT, "n_gpus": world,
+                "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": 1e3 * t / args.steps,
+                "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": config_dict(cfg, n_total, {"parallelism": f"one block, {world} strips of 2x2 stamp-group rows",
+                                                     "stamps_per_rank": [len(assign_stamp_groups(cfg.n1P, world, r))
+                                                                         for r in range(world)]}),
+                "gpu_launches": int(_lib.launch_count() - n0),
+                "strong_verified": {"identical_off_seams": off_seam_equal, "max_rel_deviation": max_dev,
+                                    "seam_rows": int(seam.sum()),
+                                    "ok": bool(off_seam_equal and max_dev < 1e-6)}}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -432,6 +570,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=("b200", "reference"))
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
+    ap.add_argument("--strong", action="store_true", help="strong scaling: ONE block split into strips of stamp groups")
+    ap.add_argument("--strong-n1", type=int, default=14, help="n1 of the block of the --strong run (n1P = n1 + 2)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

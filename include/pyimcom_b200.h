@@ -197,6 +197,8 @@ int b200_dev_gemm_nt(const double* A, int lda, const double* B, int ldb, double*
 int b200_dev_ozaki_gemm_nt(const double* A, int lda, const double* B, int ldb, double* C, int ldc, int M, int N, int K,
                            void* work, size_t work_bytes, void* stream);
 size_t b200_ozaki_gemm_work_bytes(int M, int N, int K);
+/* digit planes per operand, NS: a float64 product costs NS (NS + 1) / 2 INT8 products */
+int b200_ozaki_slices(void);
 int b200_dev_transpose(const double* A, int lda, double* At, int ldat, int rows, int cols, void* stream);
 /* np.linalg.eigh (lakernel.py:162, 201, 266): block Jacobi (pairs of 16-row blocks, 32x32 sub-problems in shared
  * memory).  A (n x n, lda) is destroyed and must be padded with the identity up to ntot = 16 * (ceil(n/16) rounded up

@@ -141,6 +141,8 @@ lib.b200_version.restype = C.c_int
 lib.b200_version.argtypes = []
 lib.b200_ozaki_gemm_work_bytes.restype = C.c_size_t
 lib.b200_ozaki_gemm_work_bytes.argtypes = [i32, i32, i32]
+lib.b200_ozaki_slices.restype = C.c_int
+lib.b200_ozaki_slices.argtypes = []
 lib.b200_chol_work_bytes.restype = C.c_size_t
 lib.b200_chol_work_bytes.argtypes = [i32, i32]
 lib.b200_launch_count.restype = C.c_longlong
@@ -168,7 +170,7 @@ profile_read_raw = globals()["profile_read"]
 
 PROF_KINDS = ("chol_super_update", "potrf_diag", "chol_panel", "chol_inner_update", "back_super_update", "back_diag",
               "back_inner_update", "build_A", "build_B", "finalize", "gemm_nt", "iter_cg", "lakernel1", "eigh",
-              "assemble_A", "oz_slice")
+              "assemble_A", "oz_slice", "oz_gemm")
 
 
 def profile_read():

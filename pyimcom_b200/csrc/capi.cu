@@ -353,6 +353,7 @@ int b200_dev_ozaki_gemm_nt(const double* A, int lda, const double* B, int ldb, d
 }
 size_t b200_ozaki_gemm_work_bytes(int M, int N, int K) { return oz_gemm_work_bytes(M, N, K); }
 size_t b200_chol_work_bytes(int npad, int mpad) { return chol_work_bytes(npad, mpad); }
+int b200_ozaki_slices(void) { return OZ_NS; }
 int b200_dev_transpose(const double* A, int lda, double* At, int ldat, int rows, int cols, void* s) {
     return launch_transpose(A, lda, At, ldat, rows, cols, ST(s));
 }

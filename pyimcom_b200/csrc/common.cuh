@@ -37,7 +37,7 @@ extern long long g_launches;
 enum ProfKind {
     PROF_CHOL_SUPER = 0, PROF_POTRF_DIAG, PROF_CHOL_PANEL, PROF_CHOL_INNER, PROF_BACK_SUPER, PROF_BACK_DIAG,
     PROF_BACK_INNER, PROF_BUILD_A, PROF_BUILD_B, PROF_FINALIZE, PROF_GEMM, PROF_ITER_CG, PROF_LAKERNEL1,
-    PROF_EIGH, PROF_ASSEMBLE_A, PROF_OZ_SLICE, PROF_NKINDS
+    PROF_EIGH, PROF_ASSEMBLE_A, PROF_OZ_SLICE, PROF_OZ_GEMM, PROF_NKINDS
 };
 void prof_begin(int kind, cudaStream_t st);
 void prof_end(double work, cudaStream_t st);  // work: flops (tensor kinds) or bytes (HBM kinds) of the launch

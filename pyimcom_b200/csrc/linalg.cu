@@ -868,7 +868,7 @@ int launch_chol_solve(const SolveSys* h_sys, int nsys, int do_factor, int do_sol
                     for (int j = c0; j < cc1; j++) tiles += (nb - j) - 0.25;
                 }
                 for (int q = nsys; q < MAXB; q++) gb.s[q] = gb.s[0];
-                prof_begin(PROF_CHOL_SUPER, st);
+                prof_begin(PROF_OZ_GEMM, st);
                 if (int rc = oz_launch_gemm(gb, nsys, mt, nt, st)) return rc;
                 prof_end(tiles * tile_flops * c0 * NB, st);
             } else if (c0 > 0) {
@@ -939,7 +939,7 @@ int launch_chol_solve(const SolveSys* h_sys, int nsys, int do_factor, int do_sol
                         if (nb > c1) tiles += (double)(s.mpad / NB) * (nb - c1);
                     }
                     for (int q = nsys; q < MAXB; q++) gb.s[q] = gb.s[0];
-                    prof_begin(PROF_CHOL_SUPER, st);
+                    prof_begin(PROF_OZ_GEMM, st);
                     if (int rc = oz_launch_gemm(gb, nsys, mt, nt, st)) return rc;
                     prof_end(tiles * tile_flops * (c1 - c0) * NB, st);
                 }
@@ -1018,7 +1018,7 @@ int launch_chol_solve(const SolveSys* h_sys, int nsys, int do_factor, int do_sol
                     if (hi > lo && lo > 0) tiles += (double)(s.mpad / NB) * lo * (hi - lo);
                 }
                 for (int q = nsys; q < MAXB; q++) gb.s[q] = gb.s[0];
-                prof_begin(PROF_BACK_SUPER, st);
+                prof_begin(PROF_OZ_GEMM, st);
                 if (int rc = oz_launch_gemm(gb, nsys, mt, nt, st)) return rc;
                 prof_end(tiles * tile_flops * NB, st);
             }

@@ -27,6 +27,10 @@
 #include "kernels.h"
 #include "ozaki.cuh"
 
+#ifndef B200_OZ_PREFETCH_REG
+#define B200_OZ_PREFETCH_REG 1
+#endif
+
 namespace b200 {
 
 namespace {
@@ -204,9 +208,16 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) k_oz_gemm(const __grid_constant
         // the tile of C the warp will update is fetched while the tensor core works: row r of the warp's 32 rows is 512
         // contiguous bytes, one 16-byte piece per lane (32 independent loads in flight per lane)
         double* Cw = s.C + (size_t)(tm * OZ_BM + quad * 32) * s.ldc + (size_t)tn * OZ_BN + 2 * lane;
+#if B200_OZ_PREFETCH_REG
         double2 cin[32];
 #pragma unroll
         for (int r = 0; r < 32; r++) cin[r] = *reinterpret_cast<const double2*>(Cw + (size_t)r * s.ldc);
+#else
+        // (L2 prefetch instead of 128 registers per thread: leaves room for a second kernel's CTAs on the SM)
+#pragma unroll 8
+        for (int r = lane & 3; r < 32; r += 4)
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(Cw - 2 * lane + 16 * (lane >> 2) + (size_t)r * s.ldc));
+#endif
         mbar_wait(accum_done, 0);
         tc_fence_after();
         if (p.dbgbuf) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_main));
@@ -238,7 +249,11 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) k_oz_gemm(const __grid_constant
         // phase 2: the warp walks its 32 rows
 #pragma unroll
         for (int r = 0; r < 32; r++) {
+#if B200_OZ_PREFETCH_REG
             double2 c = cin[r];
+#else
+            double2 c = *reinterpret_cast<const double2*>(Cw + (size_t)r * s.ldc);
+#endif
             c.x -= stg[r * OZ_EPI_LD + 2 * lane];
             c.y -= stg[r * OZ_EPI_LD + 2 * lane + 1];
             *reinterpret_cast<double2*>(Cw + (size_t)r * s.ldc) = c;
