@@ -50,7 +50,7 @@ def compress_map(map_: np.ndarray, coef: int, dtype) -> np.ndarray:
     return np.clip(np.floor(coef * np.log10(np.clip(map_, 1e-32, None)) + 0.5), a_min, a_max).astype(dtype)
 
 
-def build_output(maps: dict, cfg, n_inimage: int, is_final: bool = True, pad_sides: str = "") -> dict:
+def build_output(maps: dict, cfg, n_inimage: int, is_final: bool = True, pad_sides: str = "", keep_inputs=None) -> dict:
     """The arrays Block.build_output_file puts into its HDUs, keyed by EXTNAME (coadd.py:2156-2303).
 
     maps: out_map (n_out, n_inframe, side, side), T_weightmap (n_out, n_inimage, n1P, n1P) and the quality maps
@@ -74,4 +74,6 @@ def build_output(maps: dict, cfg, n_inimage: int, is_final: bool = True, pad_sid
         if letter in cfg.outmaps:
             ext, coef, dt = ENCODING[letter]
             out[ext] = compress_map(m[names[letter]][:, sl, sl], coef, dt)
+            if keep_inputs is not None:  # the float32 maps that were encoded (tests: tie analysis of differing codes)
+                keep_inputs[ext] = (m[names[letter]][:, sl, sl].copy(), coef)
     return out

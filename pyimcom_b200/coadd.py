@@ -29,6 +29,7 @@ import numpy as np
 import torch
 
 from . import _lib
+from .adapter import adapt_block
 from .lakernel import SOLVERS, ApplySpec, DeviceSystem, apply_T, eigen_decompose_batch, ptr, rup, solve_chol_batch, solve_eigen
 from .lakernel import solve_chol_finish, solve_chol_launch, side_streams_in_use
 from .lakernel import stream_handle
@@ -157,6 +158,7 @@ class GpuBlock:
     def __init__(self, blk, tables, kernel: str | None = None, a_cache: bool = True):
         if not torch.cuda.is_available():
             raise RuntimeError("pyimcom_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+        blk = adapt_block(blk)  # a reference Block / Config gets the derived attributes (dscale, nc_ovl, rpix_search, ...)
         self.blk, self.tab = blk, tables
         self.cfg = blk.cfg
         self.kernel = kernel or self.cfg.linear_algebra
@@ -625,8 +627,11 @@ class GpuBlock:
             d.seg_start[a] = int(p.inpix_cumsum[a])
         return d
 
-    def build_system(self, k: int, need_A: bool = True):
+    def build_system(self, k: int, need_A: bool = True, skip_AB: bool = False):
         """Stage (a): gather + A + mBhalf for stamp number k of self.order.  Returns (DeviceSystem, indata).
+
+        skip_AB: the no-quality-control mode of the empirical kernel (coadd.py:1020-1025): neither system matrix is
+        interpolated (mBhalf is left as zeros of the right shape).
 
         need_A=False (pair-block cache on): A is not materialised; the solver cuts A + kappa I straight out of the
         cached blocks through DeviceSystem.assemble."""
@@ -649,6 +654,14 @@ class GpuBlock:
                               indata.stride(0), st)
         ncode = 4 * nimg
         A, assemble = None, None
+        if skip_AB:
+            mB = torch.zeros((cfg.n_out, mpad, npad), dtype=torch.float64, device="cuda")
+            ds = DeviceSystem(n=n, m=m, n2f=cfg.n2f, A=None, mB=mB, C=np.asarray(self.tab.outovlc, dtype=np.float64),
+                              px=px, py=py, assemble=None)
+            g = torch.arange(cfg.n2f, dtype=torch.float64, device="cuda")
+            ds.outy = (p.y0out + g).repeat_interleave(cfg.n2f).contiguous()
+            ds.outx = (p.x0out + g).repeat(cfg.n2f).contiguous()
+            return ds, indata
         if self.a_cache:
             self.ensure_pairs([p])  # no-op when coadd_batch has already requested the whole batch's blocks
             desc, pool, gen = self._asm_desc(p), self._pool, self._pool_gen
@@ -705,14 +718,16 @@ class GpuBlock:
         live = []
         # single-kappa Cholesky needs A only as A + kappa I: skip materialising it unless the caller keeps the stamp
         need_A = keep or self.kernel != "Cholesky" or len(np.atleast_1d(cfg.kappaC_arr)) > 1
-        if self.a_cache:
+        # EmpirKernel without quality control (coadd.py:856-858, 1020-1025): no system matrices, U/C = Sigma = kappa = 0
+        no_qlt = self.kernel == "Empirical" and bool(getattr(cfg, "no_qlt_ctrl", False))
+        if self.a_cache and not no_qlt:
             self.ensure_pairs([pl for pl in (self.plans[self.order[k]] for k in ks) if pl.n > 0])
         for q, k in enumerate(ks):
             p = self.plans[self.order[k]]
             if p.n == 0:  # lakernel.py:110-119 and coadd.py:1094-1100: nothing to add except UC = kappa = 1
                 self._empty_stamp(p, keep)
                 continue
-            ds, indata = self.build_system(k, need_A=need_A)
+            ds, indata = self.build_system(k, need_A=need_A, skip_AB=no_qlt)
             live.append((q, k, p, ds, indata))
         if self.kernel == "Eigen" and live:  # one decomposition per stamp serves every output PSF; all stamps together
             for (q, k, p, ds, indata), eig in zip(live, eigen_decompose_batch([t[3] for t in live])):
@@ -731,6 +746,8 @@ class GpuBlock:
                     ko = kos[u]
                 elif self.kernel == "Eigen":
                     ko = solve_eigen(ds, cfg, j_out, eig=kept[q]["_eig"])
+                elif no_qlt:
+                    ko = SOLVERS[self.kernel](ds, cfg, j_out, no_qlt_ctrl=True)
                 else:
                     ko = SOLVERS[self.kernel](ds, cfg, j_out)
                 spec = self.apply_spec(k, indata, want_T32=keep, want_Ti64=keep)
@@ -762,6 +779,9 @@ class GpuBlock:
         self.T_weightmap[j_out, :, p.j_st - 1, p.i_st - 1] = res["Tsum_stamp"][: self.blk.n_inimage].float()
 
     def _empty_stamp(self, p, keep):
+        """An OutStamp without input pixels (lakernel.py:110-119, coadd.py:1094-1100): UC = kappa = 1 (faded), nothing
+        else.  Deliberate difference: the reference's _perform_coaddition then forms Neff = 1 / sum((Tsum / sum|Tsum|)^2)
+        from empty sums, i.e. 0/0 = NaN, and adds that NaN into Neff_map; here an empty stamp adds nothing to Neff_map."""
         cfg = self.cfg
         y0, x0 = (p.j_st - 1) * cfg.n2, (p.i_st - 1) * cfg.n2
         sl = (slice(None), slice(y0, y0 + cfg.n2f), slice(x0, x0 + cfg.n2f))

@@ -20,6 +20,7 @@ namespace b200 {
 namespace {
 
 constexpr int JT = 256;
+constexpr int EIGH_INNER_DEFAULT = 1;
 
 // V^T = I on the whole padded range (ntot rows/columns); per-row squared norms of the real n x n part of A
 __global__ void k_jacobi_init(double* __restrict__ Vt, int ldv, int n, int ntot, const double* __restrict__ G, int lda,
@@ -71,6 +72,7 @@ struct EighSys {
     int ldg, ldv, nblk;  // nblk even (>= 2): number of 16-row blocks, padding blocks carry the identity
     double floor1;       // 2 sqrt(n) eps |A|_F
     int* nrot;
+    int inner;           // cyclic sweeps of the 32 x 32 sub-problem per visit (stops early once nothing rotates)
 };
 struct EighBatch {
     EighSys s[MAXB];
@@ -198,6 +200,8 @@ __global__ void __launch_bounds__(256, 2) k_jacobi_block_round(EighBatch bt, int
     // 16 disjoint pairs per inner round, 16 threads per pair.
     const int pr = tid >> 4, sub = tid & 15;
     int napplied = 0;
+    for (int isw = 0; isw < sy.inner; isw++) {
+    int applied_now = 0;
     for (int rnd = 0; rnd < B2 - 1; rnd++) {
         int p, q;
         circle_pair(B2, rnd, pr, p, q);
@@ -217,6 +221,7 @@ __global__ void __launch_bounds__(256, 2) k_jacobi_block_round(EighBatch bt, int
         const double c = cs[2 * pr], s = cs[2 * pr + 1];
         if (s != 0.0) {  // rows p, q:  S <- R^T S
             napplied = 1;
+            applied_now = 1;
 #pragma unroll
             for (int h = 0; h < 2; h++) {
                 const int col = sub + 16 * h;
@@ -239,6 +244,8 @@ __global__ void __launch_bounds__(256, 2) k_jacobi_block_round(EighBatch bt, int
             }
         }
         __syncthreads();
+    }
+    if (!__syncthreads_or(applied_now)) break;  // the sub-problem is diagonal to the rounding floor
     }
     if (!__syncthreads_or(napplied)) return;
     if (tid == 0) atomicAdd(sy.nrot, 1);
@@ -374,6 +381,9 @@ int launch_jacobi_eigh_batch(const EighProblem* pr, int nsys, int max_sweeps, in
     B200_CUDA(cudaStreamSynchronize(st));
     double floor_mult = 1.0;
     if (const char* e = getenv("B200_EIGH_FLOOR_MULT")) floor_mult = atof(e);  // experiment knob
+    int inner = EIGH_INNER_DEFAULT;
+    if (const char* e = getenv("B200_EIGH_INNER")) inner = atoi(e) > 0 ? atoi(e) : 1;  // experiment knob
+    for (int q = 0; q < MAXB; q++) bt.s[q].inner = inner;
     for (int q = 0; q < nsys; q++)
         bt.s[q].floor1 = floor_mult * 2.0 * 2.220446049250313e-16 * sqrt((double)pr[q].n * fro2_h[q]);
     int sweep = 0;

@@ -27,10 +27,6 @@
 #include "kernels.h"
 #include "ozaki.cuh"
 
-#ifndef B200_OZ_PREFETCH_REG
-#define B200_OZ_PREFETCH_REG 1
-#endif
-
 namespace b200 {
 
 namespace {
@@ -106,7 +102,7 @@ __device__ __forceinline__ constexpr uint32_t oz_idesc(int n) {
     return (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(OZ_BM >> 4) << 24);
 }
 
-constexpr int OZ_THREADS = 192;
+constexpr int OZ_THREADS = 320;  // TMA warp, MMA warp, eight epilogue warps
 constexpr int OZ_A_STAGE = OZ_NS * OZ_BM * OZ_BK;  // 65536
 constexpr int OZ_B_STAGE = OZ_NS * OZ_BN * OZ_BK;  // 32768
 constexpr int OZ_STAGE = OZ_A_STAGE + OZ_B_STAGE;
@@ -202,35 +198,32 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) k_oz_gemm(const __grid_constant
             tc_commit(accum_done);
         }
     } else {
-        // ---- epilogue: warps 2..5 own TMEM lanes 32 * (warp % 4) .. + 31 = rows of the tile ----
-        const int quad = warp & 3;
+        // ---- epilogue: warps 2..9.  A warp can only read the TMEM lanes 32 (warp % 4) .. + 31 (= rows of the tile);
+        // two warps share each lane quadrant and split the 64 columns, so that the drain of the 8 accumulators (the
+        // only part of a tile's life the tensor core waits for) runs on eight warps.
+        const int quad = warp & 3, half = (warp - 2) >> 2;
         const int row = quad * 32 + lane;
-        // the tile of C the warp will update is fetched while the tensor core works: row r of the warp's 32 rows is 512
-        // contiguous bytes, one 16-byte piece per lane (32 independent loads in flight per lane)
-        double* Cw = s.C + (size_t)(tm * OZ_BM + quad * 32) * s.ldc + (size_t)tn * OZ_BN + 2 * lane;
-#if B200_OZ_PREFETCH_REG
-        double2 cin[32];
+        constexpr int HC = OZ_BN / 2;  // columns per warp
+        // the piece of C the warp will update is fetched while the tensor core works: two rows of 32 doubles per step,
+        // one 16-byte piece per lane (16 independent loads in flight per lane)
+        double* Cw = s.C + (size_t)(tm * OZ_BM + quad * 32 + (lane >> 4)) * s.ldc + (size_t)tn * OZ_BN + half * HC +
+                     2 * (lane & 15);
+        double2 cin[16];
 #pragma unroll
-        for (int r = 0; r < 32; r++) cin[r] = *reinterpret_cast<const double2*>(Cw + (size_t)r * s.ldc);
-#else
-        // (L2 prefetch instead of 128 registers per thread: leaves room for a second kernel's CTAs on the SM)
-#pragma unroll 8
-        for (int r = lane & 3; r < 32; r += 4)
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(Cw - 2 * lane + 16 * (lane >> 2) + (size_t)r * s.ldc));
-#endif
+        for (int r = 0; r < 16; r++) cin[r] = *reinterpret_cast<const double2*>(Cw + (size_t)(2 * r) * s.ldc);
         mbar_wait(accum_done, 0);
         tc_fence_after();
         if (p.dbgbuf) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_main));
         const double sa = s.scaleA[s.rowA0 + tm * OZ_BM + row];
         // phase 1: own row -> float64 values (Horner over the levels, scaled) parked in shared memory.  The stage ring is
         // free: accum_done says that every MMA has finished reading it.  Row stride 65 doubles: lane l starts in bank 2 l.
-        double* stg = reinterpret_cast<double*>(base) + (size_t)(quad * 32) * OZ_EPI_LD;
+        double* stg = reinterpret_cast<double*>(base) + (size_t)(quad * 32) * OZ_EPI_LD + half * HC;
         double* mine = stg + (size_t)lane * OZ_EPI_LD;
 #pragma unroll 1
-        for (int c0 = 0; c0 < OZ_BN; c0 += 16) {
+        for (int c0 = 0; c0 < HC; c0 += 16) {
             double acc[16];
             uint32_t v[16];
-            const uint32_t taddr = tmem + ((uint32_t)(quad * 32) << 16) + c0;
+            const uint32_t taddr = tmem + ((uint32_t)(quad * 32) << 16) + half * HC + c0;
             tmem_ld16(taddr + (OZ_NS - 1) * OZ_BN, v);
             tmem_ld_wait();
 #pragma unroll
@@ -243,20 +236,17 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) k_oz_gemm(const __grid_constant
                 for (int j = 0; j < 16; j++) acc[j] = fma(acc[j], 0.0078125, (double)(int)v[j]);
             }
 #pragma unroll
-            for (int j = 0; j < 16; j++) mine[c0 + j] = acc[j] * (sa * sB[c0 + j]);  // powers of two: exact
+            for (int j = 0; j < 16; j++) mine[c0 + j] = acc[j] * (sa * sB[half * HC + c0 + j]);  // powers of two: exact
         }
         __syncwarp();
-        // phase 2: the warp walks its 32 rows
+        // phase 2: the warp walks its 32 rows, two at a time
+        const double* sp = stg + (size_t)(lane >> 4) * OZ_EPI_LD + 2 * (lane & 15);
 #pragma unroll
-        for (int r = 0; r < 32; r++) {
-#if B200_OZ_PREFETCH_REG
+        for (int r = 0; r < 16; r++) {
             double2 c = cin[r];
-#else
-            double2 c = *reinterpret_cast<const double2*>(Cw + (size_t)r * s.ldc);
-#endif
-            c.x -= stg[r * OZ_EPI_LD + 2 * lane];
-            c.y -= stg[r * OZ_EPI_LD + 2 * lane + 1];
-            *reinterpret_cast<double2*>(Cw + (size_t)r * s.ldc) = c;
+            c.x -= sp[(2 * r) * OZ_EPI_LD];
+            c.y -= sp[(2 * r) * OZ_EPI_LD + 1];
+            *reinterpret_cast<double2*>(Cw + (size_t)(2 * r) * s.ldc) = c;
         }
     }
     tc_fence_before();

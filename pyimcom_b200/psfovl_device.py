@@ -26,6 +26,7 @@ import torch
 
 from . import _lib
 from .lakernel import ptr, rup, stream_handle
+from .adapter import adapt_block
 from .psfovl_host import PSFTables
 
 
@@ -62,6 +63,7 @@ class DeviceTables(PSFTables):
     def __init__(self, blk, iC, gridC, dedup=False):
         if not torch.cuda.is_available():
             raise RuntimeError("pyimcom_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+        blk = adapt_block(blk)
         cfg = blk.cfg
         ns, nfft, nc = cfg.nsamp, cfg.nfft, cfg.nc_ovl
         nl = cfg.nsamp_ovl      # lags kept per axis: ns, or 2 ns + 1 with PSF splitting (psfutil.py:1075-1083)

@@ -19,6 +19,7 @@ from __future__ import annotations
 
 import numpy as np
 
+from .adapter import adapt_block
 from .synth import StampConfig
 
 
@@ -36,6 +37,7 @@ def tri_index(n_psf, j, i):
 
 class PSFTables:
     def __init__(self, blk, iC, gridC, dedup=False):
+        blk = adapt_block(blk)  # (a reference Block: derived PSFGrp / PSFOvl quantities come from the adapter)
         self.blk = blk
         self.cfg: StampConfig = blk.cfg
         self.iC, self.gridC = iC, gridC

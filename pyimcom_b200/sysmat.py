@@ -43,7 +43,7 @@ class SysMatA:
 
     def __init__(self, blk, tables=None):
         self.blk = blk
-        self._ctx = _context(blk, tables)
+        self._ctx = _context(blk, tables)  # (reference Blocks are wrapped by pyimcom_b200.adapter inside GpuBlock)
         self.iisubmats = {}  # psfutil.py:1797
         ns = blk.cfg.n1P + 2
         self.iisubmats_ref = np.zeros((ns, ns, 13), dtype=np.uint8)  # psfutil.py:1800

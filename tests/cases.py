@@ -209,6 +209,31 @@ def codes_match(got, want, max_frac=0.005):
     return d.max() <= 1 and (d > 0).mean() <= max_frac
 
 
+def code_mismatches_are_ties(got, want, x, coef):
+    """Integer output must be identical unless the reference's own float32 formula is ambiguous at that pixel.
+
+    Block.compress_map evaluates floor(coef * log10(x) + 0.5) in float32 (coadd.py:2128).  NumPy's float32 log10 is the
+    host libm's log10f (glibc: up to 2 ulp, not correctly rounded), the device takes the correctly rounded float32
+    logarithm; the product and the sum round once more each.  A code may therefore differ -- by one count -- only where
+    the exact value y = coef * log10(x) + 0.5 lies within that float32 evaluation error of an integer:
+        |y - rint(y)| <= 2.5 ulp32(log10 x) * |coef| + ulp32(coef * log10 x).
+    Asserts exactly that for EVERY mismatching pixel (and that nothing differs by more than one count); returns
+    (number of mismatches, number of pixels inside the ambiguity band)."""
+    got, want = np.asarray(got), np.asarray(want)
+    assert got.dtype == want.dtype and got.shape == want.shape == np.shape(x)
+    d = got.astype(np.int64) - want.astype(np.int64)
+    x64 = np.clip(np.asarray(x, dtype=np.float32), np.float32(1e-32), None).astype(np.float64)
+    lg = np.log10(x64)
+    y = coef * lg + 0.5
+    band = 2.5 * np.spacing(np.abs(lg).astype(np.float32)).astype(np.float64) * abs(coef) \
+        + np.spacing(np.abs(coef * lg).astype(np.float32)).astype(np.float64)
+    tie = np.abs(y - np.rint(y)) <= band
+    mism = d != 0
+    assert np.abs(d).max(initial=0) <= 1, "a 16-bit code differs by more than one count"
+    assert np.all(tie[mism]), f"{int((mism & ~tie).sum())} codes differ where the float32 formula is not ambiguous"
+    return int(mism.sum()), int(tie.sum())
+
+
 # ---------------------------------------------------------------------------------------------------
 # input-pixel partitioning (SURVEY 8f row f2)
 # ---------------------------------------------------------------------------------------------------

@@ -93,3 +93,55 @@ def test_cell_descriptor_layout():
     assert CELL_DTYPE.itemsize == ctypes.sizeof(_lib.PartCell) == 24
     for name, fld in zip(CELL_DTYPE.names, _lib.PartCell._fields_):
         assert name == fld[0] and CELL_DTYPE.fields[name][1] == getattr(_lib.PartCell, name).offset
+
+
+def test_adapter_derives_the_reference_quantities():
+    """pyimcom_b200.adapter: a reference-shaped Config (only the reference's own attribute names) gets the derived
+    quantities the device path reads, equal to what StampConfig carries and -- in the build container -- to the
+    reference's own PSFGrp.setup / PSFOvl.setup class state for configs/paper4_configs/H158_Chol_benchmark.json."""
+    import types
+
+    from pyimcom_b200.adapter import adapt_block, adapt_config, default_stamp_order
+    from pyimcom_b200.synth import StampConfig
+
+    sc = StampConfig(n1=6, n2=32, dtheta_arcsec=0.0390625, fade_kernel=3, postage_pad=1, npixpsf=48, oversamp=8,
+                     instamp_pad_arcsec=1.24, psfsplit=True)
+    ref_like = types.SimpleNamespace(n1P=sc.n1P, n2f=sc.n2f, dtheta=sc.dtheta, instamp_pad=sc.instamp_pad,
+                                     npixpsf=sc.npixpsf, inpsf_oversamp=sc.oversamp, psfsplit=True, fade_kernel=3,
+                                     postage_pad=1, NsideP=sc.NsideP, n_out=1, kappaC_arr=sc.kappaC_arr)
+    v = adapt_config(ref_like)
+    for k in ("oversamp", "nsamp", "nfft", "nsamp_ovl", "nc_ovl", "n2", "n1"):
+        assert getattr(v, k) == getattr(sc, k), k
+    for k in ("dscale", "rpix_search"):
+        assert abs(getattr(v, k) - getattr(sc, k)) < 1e-12 * abs(getattr(sc, k)), k
+    assert v.kappaC_arr is ref_like.kappaC_arr and adapt_config(sc) is sc  # pass-through, idempotent
+    with pytest.raises(AttributeError):
+        v.not_a_config_key
+    blk = types.SimpleNamespace(cfg=ref_like, n_inimage=2)
+    b = adapt_block(blk)
+    assert list(b.stamp_order()) == list(default_stamp_order(sc.n1P)) and b.n_inimage == 2
+    assert list(default_stamp_order(2)) == [(1, 1), (1, 2), (2, 1), (2, 2)]
+
+    from oracle import refhost
+
+    if not refhost.available():
+        return
+    import contextlib
+    import io
+
+    ref = refhost.load()
+    with contextlib.redirect_stdout(io.StringIO()):
+        c = ref.config.Config("/root/reference/configs/paper4_configs/H158_Chol_benchmark.json")
+    v = adapt_config(c)
+    G, O = ref.psfutil.PSFGrp, ref.psfutil.PSFOvl
+    saved = {k: getattr(G, k, None) for k in ("oversamp", "nsamp", "nfft", "dscale", "psfsplit", "nc", "yxo")}
+    try:
+        G.setup(npixpsf=c.npixpsf, oversamp=c.inpsf_oversamp, dtheta=c.dtheta, psfsplit=bool(c.psfsplit))
+        O.setup(flat_penalty=c.flat_penalty)
+        assert (v.oversamp, v.nsamp, v.nfft, v.nsamp_ovl, v.nc_ovl) == (G.oversamp, G.nsamp, G.nfft, O.nsamp, O.nc)
+        assert v.dscale == G.dscale and (v.n1, v.n2, v.n1P, v.n2f) == (80, 32, 84, 38)
+        assert abs(v.rpix_search - 1.24 / 0.0390625) < 1e-9
+    finally:
+        for k, val in saved.items():
+            if val is not None:
+                setattr(G, k, val)
