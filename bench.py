@@ -528,11 +528,24 @@ def run_strong(args, world, rank, barrier):
         cube = step()
     e1.record()
     barrier()
+    launches = int(_lib.launch_count() - n0)
     t = torch.tensor([e0.elapsed_time(e1) * 1e-3], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     t = float(t[0])
+    # every rank's own cube also travels to rank 0, which recomputes each strip itself: are the ranks' GPUs bit-consistent?
+    from pyimcom_b200.shard import gather_cube
+
+    gb.reset_maps()
+    gb.reset_cache()
+    gb.run()
+    parts = gather_cube(gb.out_map, world, rank)
     if rank == 0:
+        strips_same = []
+        for r in range(world):
+            g_r = GpuBlock(blk, tab).prepare(stamps=assign_stamp_groups(cfg.n1P, world, r)).run()
+            strips_same.append(bool(torch.equal(g_r.out_map, parts[r])))
+            del g_r
         full = GpuBlock(blk, tab).prepare()
         full.run()
         ref = full.out_map
@@ -547,6 +560,7 @@ def run_strong(args, world, rank, barrier):
             seam[max(0, y - 0):y + 2 * fk] = True
         off_seam_equal = bool(same[..., ~seam, :].all())
         max_dev = float((cube - ref).abs().max()) / scale
+        rows_diff = torch.nonzero((cube != ref).any(dim=-1).any(dim=0).any(dim=0)).flatten().tolist()
         n_total = cfg.n1P * cfg.n1P
         line = {"metric": METRIC, "value": n_total * cfg.n2**2 * args.steps / t, "unit": UNIT, "n_gpus": world,
                 "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": 1e3 * t / args.steps,
@@ -554,9 +568,10 @@ def run_strong(args, world, rank, barrier):
                 "config": config_dict(cfg, n_total, {"parallelism": f"one block, {world} strips of 2x2 stamp-group rows",
                                                      "stamps_per_rank": [len(assign_stamp_groups(cfg.n1P, world, r))
                                                                          for r in range(world)]}),
-                "gpu_launches": int(_lib.launch_count() - n0),
+                "gpu_launches": launches,
                 "strong_verified": {"identical_off_seams": off_seam_equal, "max_rel_deviation": max_dev,
-                                    "seam_rows": int(seam.sum()),
+                                    "seam_rows": int(seam.sum()), "rows_that_differ": rows_diff[:24],
+                                    "strips_recomputed_on_rank0_identical": strips_same,
                                     "ok": bool(off_seam_equal and max_dev < 1e-6)}}
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -252,6 +252,8 @@ class DeviceTables(PSFTables):
             self.grp_rft[G] = self._cache[key]
             return
         arr = torch.zeros((len(imgs), self.cfg.nsamp, self.cfg.nsamp), dtype=torch.float64, device="cuda")
+        if self.dedup:  # (shared tables are sampled at the first group's point whoever asks first: see psfovl_host)
+            inst = blk.instamps[0][0]
         for q, k in enumerate(imgs):
             arr[q] = self._sample_in(inst, blk.inimages[k])
         self.grp_rft[G] = self._finish(arr)

@@ -134,6 +134,10 @@ class PSFTables:
             self.grp_rft[G] = self._cache[key]
             return
         arr = np.zeros((len(imgs), self.cfg.nsamp, self.cfg.nsamp))
+        if self.dedup:
+            # shared tables must not depend on which group happened to ask first (ranks that coadd different strips of one
+            # block would otherwise hold tables that differ in the last bit): always sample at the first group's point
+            inst = blk.instamps[0][0]
         for q, k in enumerate(imgs):
             arr[q] = self._sample_in(inst, blk.inimages[k])
         self.grp_rft[G] = self._finish(arr)

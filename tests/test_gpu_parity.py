@@ -456,6 +456,31 @@ def test_block_run_maps():
     assert rel(maps["UC_map"], UC) < 5e-6
 
 
+def test_strip_sharded_block_equals_unsharded():
+    """SURVEY 8e, single-block sharding: the block coadded as two strips of 2x2 stamp-group rows (shard.
+    assign_stamp_groups; each strip adds into its own zero-initialised cube, the cubes are summed as shard.reduce_cube
+    does) equals the unsharded block bit for bit except on the rows where the fade borders of the two strips overlap,
+    and there to float32 rounding of the seam adds.  (bench.py --strong runs the same check across real ranks.)"""
+    from pyimcom_b200.shard import assign_stamp_groups
+
+    spec = cases.BLOCK_CASES["pad4"]
+    blk = cases.make_block(spec)
+    cfg = blk.cfg
+    tab = PSFTables(blk, G.iD5512C, G.gridD5512C)
+    ref = GpuBlock(blk, tab).prepare().run().download()
+    world = 2
+    parts = [GpuBlock(blk, tab).prepare(stamps=assign_stamp_groups(cfg.n1P, world, r)).run().download() for r in range(world)]
+    assert sorted(sum((assign_stamp_groups(cfg.n1P, world, r) for r in range(world)), [])) == sorted(blk.stamp_order())
+    y = 2 * ((len(range(1, cfg.n1P + 1, 2)) + world - 1) // world) * cfg.n2
+    seam = np.zeros(ref["out_map"].shape[-2], dtype=bool)
+    seam[y:y + 2 * cfg.fade_kernel] = True
+    for k in ("out_map", "UC_map", "Sigma_map", "kappa_map", "Tsum_map", "Neff_map"):
+        tot = parts[0][k] + parts[1][k]
+        assert np.array_equal(tot[..., ~seam, :], ref[k][..., ~seam, :]), k
+        assert rel(tot, ref[k]) < 5e-7, k
+    assert np.array_equal(parts[0]["T_weightmap"] + parts[1]["T_weightmap"], ref["T_weightmap"])
+
+
 def test_empirical_without_quality_control():
     """cfg.no_qlt_ctrl with the empirical kernel (coadd.py:856-858, 1020-1025; lakernel.py:770-774): no system matrix is
     interpolated (no pair-block / mBhalf launch), T and therefore the coadded image are those of the regular empirical
