@@ -205,7 +205,7 @@ def _padded_system(ds: DeviceSystem, incs):
 
 OZAKI = os.environ.get("B200_OZAKI", "1") != "0"  # long-K panel updates on the INT8 tcgen05 tensor cores (csrc/ozaki.cu)
 OZAKI_MIN_N = 512  # (the library itself only switches over when there is more than one super-panel)
-SOLVE_STREAMS = int(os.environ.get("B200_SOLVE_STREAMS", "3"))  # concurrent groups of systems in the batched factorisation (1 = everything on the caller's stream)
+SOLVE_STREAMS = int(os.environ.get("B200_SOLVE_STREAMS", "2"))  # concurrent groups of systems in the batched factorisation (1 = everything on the caller's stream)
 STREAM_PRIORITIES = os.environ.get("B200_STREAM_PRIORITIES", "1") != "0"
 _SIDE = {}
 
