@@ -289,6 +289,14 @@ int b200_dev_stamp_maps(const double* kappa, const double* Sigma, const double* 
 /* dst[l, y0+iy, x0+ix] += src[l, iy, ix] for an (nlayer, n2f, n2f) stamp into an (nlayer, side, side) f32 canvas. */
 int b200_dev_accumulate(const void* src, int src_is_f64, int nlayer, int n2f, float* dst, int side, int y0, int x0,
                         void* stream);
+/* Block._output_stamp_wrapper (coadd.py:1976-1994) for one output PSF of one stamp in ONE launch: the n_inframe coadded
+ * layers into out_map (n_inframe, side, side), the float32 U/C, Sigma, kappa maps and the float64 Tsum_inpix, Neff maps
+ * (n2f, n2f) into their (side, side) canvases, and T_weight[k * tw_stride] = Tsum_stamp[k] for the n_img input images. */
+int b200_dev_accumulate_stamp(const float* outimage, int n_inframe, const float* UC, const float* Sigma,
+                              const float* kappa, const double* Tsum_inpix, const double* Neff, const double* Tsum_stamp,
+                              int n_img, int n2f, float* out_map, float* UC_map, float* Sigma_map, float* kappa_map,
+                              float* Tsum_map, float* Neff_map, int side, int y0, int x0, float* T_weight,
+                              int tw_stride, void* stream);
 
 /* ---- 6. device: block output assembly (Block.build_output_file, coadd.py:2139-2176) ---------- */
 /* out (nlayer, side-2fk, side-2fk) = in (nlayer, side, side) without its fade margin.  recover != 0 first divides the

@@ -127,6 +127,8 @@ PROTOTYPES = {
     "b200_dev_finalize": [C.POINTER(FinalizeArgs), vp],
     "b200_dev_stamp_maps": [vp, vp, vp, i32, i32, i32, i32, vp, vp, vp, vp, vp, i32, i32, vp, vp, vp, vp],
     "b200_dev_accumulate": [vp, i32, i32, i32, vp, i32, i32, i32, vp],
+    "b200_dev_accumulate_stamp": [vp, i32, vp, vp, vp, vp, vp, vp, i32, i32, vp, vp, vp, vp, vp, vp, i32, i32, i32, vp, i32,
+                                  vp],
     "b200_dev_unfade_crop": [vp, i32, i32, i32, i32, i32, i32, i32, i32, vp, vp, vp],
     "b200_dev_compress_map": [vp, C.c_long, i32, i32, vp, vp],
     "b200_dev_partition": [vp, i32, vp, vp, vp, i32, vp, i32, i32, f64, f64, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp,

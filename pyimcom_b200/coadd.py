@@ -766,17 +766,13 @@ class GpuBlock:
     def _overlap_add(self, p, j_out, res):
         """coadd.py:1976-1994: add one stamp's faded results into the block maps."""
         cfg = self.cfg
-        st = stream_handle()
         y0, x0 = (p.j_st - 1) * cfg.n2, (p.i_st - 1) * cfg.n2
-        acc = lambda src, f64, nl, dst: _lib.dev_accumulate(ptr(src), int(f64), nl, cfg.n2f, ptr(dst), self.side, y0,  # noqa: E731
-                                                            x0, st)
-        acc(res["outimage"], False, cfg.n_inframe, self.out_map[j_out])
-        acc(res["UC"], False, 1, self.UC_map[j_out])
-        acc(res["Sigma"], False, 1, self.Sigma_map[j_out])
-        acc(res["kappa"], False, 1, self.kappa_map[j_out])
-        acc(res["Tsum_inpix"], True, 1, self.Tsum_map[j_out])
-        acc(res["Neff"], True, 1, self.Neff_map[j_out])
-        self.T_weightmap[j_out, :, p.j_st - 1, p.i_st - 1] = res["Tsum_stamp"][: self.blk.n_inimage].float()
+        tw = self.T_weightmap[j_out, :, p.j_st - 1, p.i_st - 1]  # (n_inimage,) strided view
+        _lib.dev_accumulate_stamp(ptr(res["outimage"]), cfg.n_inframe, ptr(res["UC"]), ptr(res["Sigma"]),
+                                  ptr(res["kappa"]), ptr(res["Tsum_inpix"]), ptr(res["Neff"]), ptr(res["Tsum_stamp"]),
+                                  self.blk.n_inimage, cfg.n2f, ptr(self.out_map[j_out]), ptr(self.UC_map[j_out]),
+                                  ptr(self.Sigma_map[j_out]), ptr(self.kappa_map[j_out]), ptr(self.Tsum_map[j_out]),
+                                  ptr(self.Neff_map[j_out]), self.side, y0, x0, ptr(tw), tw.stride(0), stream_handle())
 
     def _empty_stamp(self, p, keep):
         """An OutStamp without input pixels (lakernel.py:110-119, coadd.py:1094-1100): UC = kappa = 1 (faded), nothing

@@ -430,6 +430,15 @@ int b200_dev_accumulate(const void* src, int src_is_f64, int nlayer, int n2f, fl
                         void* s) {
     return launch_accumulate(src, src_is_f64, nlayer, n2f, dst, side, y0, x0, ST(s));
 }
+int b200_dev_accumulate_stamp(const float* outimage, int n_inframe, const float* UC, const float* Sigma,
+                              const float* kappa, const double* Tsum_inpix, const double* Neff, const double* Tsum_stamp,
+                              int n_img, int n2f, float* out_map, float* UC_map, float* Sigma_map, float* kappa_map,
+                              float* Tsum_map, float* Neff_map, int side, int y0, int x0, float* T_weight,
+                              int tw_stride, void* s) {
+    return launch_accumulate_stamp(outimage, n_inframe, UC, Sigma, kappa, Tsum_inpix, Neff, Tsum_stamp, n_img, n2f, out_map,
+                                   UC_map, Sigma_map, kappa_map, Tsum_map, Neff_map, side, y0, x0, T_weight, tw_stride,
+                                   ST(s));
+}
 int b200_dev_unfade_crop(const float* in, int nlayer, int side, int fk, int recover, int pb, int pt, int pl, int pr,
                          const double* fade_w, float* out, void* s) {
     return launch_unfade_crop(in, nlayer, side, fk, recover, pb, pt, pl, pr, fade_w, out, ST(s));

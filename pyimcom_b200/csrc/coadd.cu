@@ -248,6 +248,36 @@ __global__ void __launch_bounds__(256) k_accumulate64(const double* __restrict__
         *d = *d + (float)src[t];
     }
 }
+// All maps of one stamp in one launch (Block._output_stamp_wrapper, coadd.py:1976-1994): the n_inframe coadded layers,
+// the U/C, Sigma, kappa maps (float32), the Tsum_inpix and Neff maps (float64 -> float32 as the reference's float32 maps
+// take them) and the per-image weight sums of T_weightmap.  Layer index: 0..nfr-1 image, then U, S, K, Tsum, Neff.
+struct AccumStamp {
+    const float *outimage, *UC, *Sigma, *kappa;
+    const double *Tsum_inpix, *Neff, *Tsum_stamp;
+    float *out_map, *UC_map, *Sigma_map, *kappa_map, *Tsum_map, *Neff_map, *T_weight;
+    int nfr, n2f, side, y0, x0, n_img, tw_stride;
+};
+__global__ void __launch_bounds__(256) k_accumulate_stamp(AccumStamp a) {
+    const int m = a.n2f * a.n2f;
+    const long tot = (long)(a.nfr + 5) * m;
+    for (long t = (long)blockIdx.x * blockDim.x + threadIdx.x; t < tot; t += (long)gridDim.x * blockDim.x) {
+        const int l = (int)(t / m), px = (int)(t - (long)l * m);
+        const int iy = px / a.n2f, ix = px - iy * a.n2f;
+        const size_t off = (size_t)(a.y0 + iy) * a.side + a.x0 + ix;
+        if (l < a.nfr) {
+            float* d = a.out_map + (size_t)l * a.side * a.side + off;
+            *d = *d + a.outimage[(size_t)l * m + px];
+        } else {
+            const int q = l - a.nfr;
+            float* d = (q == 0 ? a.UC_map : q == 1 ? a.Sigma_map : q == 2 ? a.kappa_map : q == 3 ? a.Tsum_map : a.Neff_map) + off;
+            const float v = q == 0 ? a.UC[px] : q == 1 ? a.Sigma[px] : q == 2 ? a.kappa[px]
+                          : q == 3 ? (float)a.Tsum_inpix[px] : (float)a.Neff[px];
+            *d = *d + v;
+        }
+    }
+    if (blockIdx.x == 0 && (int)threadIdx.x < a.n_img)
+        a.T_weight[(size_t)threadIdx.x * a.tw_stride] = (float)a.Tsum_stamp[threadIdx.x];
+}
 
 
 // ---- block output assembly (coadd.py:2086-2328) -----------------------------------
@@ -345,6 +375,20 @@ int launch_accumulate(const void* src, int src_is_f64, int nlayer, int n2f, floa
         k_accumulate64<<<grid, 256, 0, s>>>((const double*)src, nlayer, n2f, dst, side, y0, x0);
     else
         k_accumulate<<<grid, 256, 0, s>>>((const float*)src, nlayer, n2f, dst, side, y0, x0);
+    B200_LAUNCH_CHECK();
+    return 0;
+}
+
+int launch_accumulate_stamp(const float* outimage, int nfr, const float* UC, const float* Sigma, const float* kappa,
+                            const double* Tsum_inpix, const double* Neff, const double* Tsum_stamp, int n_img, int n2f,
+                            float* out_map, float* UC_map, float* Sigma_map, float* kappa_map, float* Tsum_map,
+                            float* Neff_map, int side, int y0, int x0, float* T_weight, int tw_stride, cudaStream_t s) {
+    B200_REQUIRE(y0 >= 0 && x0 >= 0 && y0 + n2f <= side && x0 + n2f <= side, "stamp outside the block canvas");
+    B200_REQUIRE(n_img <= 256 && nfr >= 0, "accumulate_stamp: at most 256 input images");
+    AccumStamp a{outimage, UC, Sigma, kappa, Tsum_inpix, Neff, Tsum_stamp, out_map, UC_map, Sigma_map, kappa_map,
+                 Tsum_map, Neff_map, T_weight, nfr, n2f, side, y0, x0, n_img, tw_stride};
+    const long tot = (long)(nfr + 5) * n2f * n2f;
+    k_accumulate_stamp<<<(int)((tot + 255) / 256), 256, 0, s>>>(a);
     B200_LAUNCH_CHECK();
     return 0;
 }

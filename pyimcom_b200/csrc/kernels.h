@@ -105,6 +105,10 @@ int launch_stamp_maps(const double* kappa, const double* Sigma, const double* UC
                       cudaStream_t s);
 int launch_accumulate(const void* src, int src_is_f64, int nlayer, int n2f, float* dst, int side, int y0, int x0,
                       cudaStream_t s);
+int launch_accumulate_stamp(const float* outimage, int nfr, const float* UC, const float* Sigma, const float* kappa,
+                            const double* Tsum_inpix, const double* Neff, const double* Tsum_stamp, int n_img, int n2f,
+                            float* out_map, float* UC_map, float* Sigma_map, float* kappa_map, float* Tsum_map,
+                            float* Neff_map, int side, int y0, int x0, float* T_weight, int tw_stride, cudaStream_t s);
 int launch_unfade_crop(const float* in, int nlayer, int side, int fk, int recover, int pb, int pt, int pl, int pr,
                        const double* fade_w, float* out, cudaStream_t s);
 int launch_compress_map(const float* in, long n, int coef, int is_unsigned, void* out, cudaStream_t s);

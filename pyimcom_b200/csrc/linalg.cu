@@ -829,6 +829,52 @@ int launch_chol_solve(const SolveSys* h_sys, int nsys, int do_factor, int do_sol
     };
     const double tile_flops = 2.0 * NB * NB;
     const double tri = g_tile64 ? 0.75 : 1.0;  // the strip kernels skip the zero quarter of the triangular inverse
+    // Right-looking update of the right-hand sides with one finished K range of Z (forward) or Ti (backward):
+    //   forward : X[:, j] -= Z[:, ka:kb] L[j, ka:kb]^T      for block columns ja <= j < jb   (B operand: rows of L)
+    //   backward: X[:, j] -= Ti[:, ka:kb] L[ka:kb, j]        for block columns ja <= j < jb   (B operand: rows of L^T)
+    // Ranges are absolute block columns (forward) or counted from the END of each system (backward: [nb - kb, nb - ka),
+    // [nb - jb, nb - ja)); xc selects the scale array the K range was sliced with.
+    auto oz_x_update = [&](bool backward, int ka, int kb, int ja, int jb, int xc) -> int {
+        OzBatch gb;
+        int mt = 0, nt = 0;
+        double work = 0;
+        for (int q = 0; q < nsys; q++) {
+            const SolveSys& s = bt.s[q];
+            const int nb = s.npad / NB;
+            int k0 = ka, k1 = kb < nb ? kb : nb, j0 = ja, j1 = jb < nb ? jb : nb;
+            if (backward) {
+                k0 = nb - kb > 0 ? nb - kb : 0;
+                k1 = nb - ka;
+                j0 = nb - jb > 0 ? nb - jb : 0;
+                j1 = nb - ja;
+            }
+            const bool any = s.mpad > 0 && k1 > k0 && j1 > j0;
+            OzSys& g = gb.s[q];
+            g.mapA = mapXA[q];
+            g.mapB = mapWB[q];
+            g.scaleA = ow[q].scaleX + (size_t)xc * s.mpad;
+            g.scaleB = backward ? ow[q].scaleU : ow[q].scaleL;
+            g.C = s.X + (size_t)(any ? j0 : 0) * NB;
+            g.ldc = s.ldx;
+            g.m_tiles = any ? s.mpad / NB : 0;
+            g.n_tiles = any ? (j1 - j0) * (NB / OZ_BN) : 0;
+            g.rowA0 = 0;
+            g.rowB0 = (any ? j0 : 0) * NB;
+            g.rowC0 = g.colC0 = 0;
+            g.kb0 = (any ? k0 : 0) * KB;
+            g.kb1 = (any ? k1 : 0) * KB;
+            g.tri = 0;
+            mt = g.m_tiles > mt ? g.m_tiles : mt;
+            nt = g.n_tiles > nt ? g.n_tiles : nt;
+            if (any) work += (double)(s.mpad / NB) * (j1 - j0) * (k1 - k0);
+        }
+        for (int q = nsys; q < MAXB; q++) gb.s[q] = gb.s[0];
+        if (mt == 0 || nt == 0) return 0;
+        prof_begin(PROF_OZ_GEMM, st);
+        const int rc = oz_launch_gemm(gb, nsys, mt, nt, st);
+        prof_end(work * tile_flops * NB, st);
+        return rc;
+    };
     if (do_factor) {
         const int SP = g_sp;
         if (oz) {  // a-priori row scales of L from the diagonal of W, before it is overwritten
@@ -909,39 +955,20 @@ int launch_chol_solve(const SolveSys* h_sys, int nsys, int do_factor, int do_sol
                 // the finished super-panel becomes digit planes: L rows below it (a-priori scales), its own rows of
                 // L^T to the right of it (exact row maxima; read by the backward solve), and the chunk of Z
                 const int xc = c0 / SP;
-                if (int rc = oz_slice(0, c1, nbmax, c0, c1, false, mbmax > 0 ? xc : -1, c0, c1)) return rc;
+                if (int rc = oz_slice(0, c1, nbmax, c0, c1, false, -1, 0, 0)) return rc;
                 if (mbmax > 0) {
                     if (int rc = oz_slice(1, c0, c1, c0 + 1, nbmax, false, -1, 0, 0)) return rc;
-                    // X[t][j] -= Z[t][c0:c1] L[j][c0:c1]^T for every block column j >= c1 (right-looking)
-                    OzBatch gb;
-                    int mt = 0, nt = 0;
-                    double tiles = 0;
-                    for (int q = 0; q < nsys; q++) {
-                        const SolveSys& s = bt.s[q];
-                        const int nb = s.npad / NB;
-                        OzSys& g = gb.s[q];
-                        g.mapA = mapXA[q];
-                        g.mapB = mapWB[q];
-                        g.scaleA = ow[q].scaleX + (size_t)xc * s.mpad;
-                        g.scaleB = ow[q].scaleL;
-                        g.C = s.X + (size_t)c1 * NB;
-                        g.ldc = s.ldx;
-                        g.m_tiles = nb > c1 ? s.mpad / NB : 0;
-                        g.n_tiles = nb > c1 ? (nb - c1) * (NB / OZ_BN) : 0;
-                        g.rowA0 = 0;
-                        g.rowB0 = c1 * NB;
-                        g.rowC0 = g.colC0 = 0;
-                        g.kb0 = c0 * KB;
-                        g.kb1 = c1 * KB;
-                        g.tri = 0;
-                        mt = g.m_tiles > mt ? g.m_tiles : mt;
-                        nt = g.n_tiles > nt ? g.n_tiles : nt;
-                        if (nb > c1) tiles += (double)(s.mpad / NB) * (nb - c1);
+                    // Chunks of Z are applied in PAIRS where possible (K = 2 SP blocks per launch amortises the drain of
+                    // the accumulators): the first chunk of a pair only brings the NEXT super-panel up to date; when the
+                    // second is finished both are sliced again with their joint row maxima and applied to everything
+                    // to the right of it in one launch.
+                    if (xc % 2 == 0) {
+                        if (int rc = oz_slice(-1, 0, 0, 0, 0, false, xc, c0, c1)) return rc;
+                        if (int rc = oz_x_update(false, c0, c1, c1, c1 + SP, xc)) return rc;
+                    } else {
+                        if (int rc = oz_slice(-1, 0, 0, 0, 0, false, xc, c0 - SP, c1)) return rc;
+                        if (int rc = oz_x_update(false, c0 - SP, c1, c1, nbmax, xc)) return rc;
                     }
-                    for (int q = nsys; q < MAXB; q++) gb.s[q] = gb.s[0];
-                    prof_begin(PROF_OZ_GEMM, st);
-                    if (int rc = oz_launch_gemm(gb, nsys, mt, nt, st)) return rc;
-                    prof_end(tiles * tile_flops * (c1 - c0) * NB, st);
                 }
             }
         }
@@ -990,37 +1017,13 @@ int launch_chol_solve(const SolveSys* h_sys, int nsys, int do_factor, int do_sol
                 // the finished chunk of Ti (block columns [nb - e1, nb - e0) of each system) is sliced and applied to all
                 // columns to its left:  X[t][j] -= Ti[t][lo:hi] L[lo:hi][j]  (j < lo; L^T rows live in W's upper triangle)
                 const int xc = e0 / SP;
-                if (int rc = oz_slice(-1, 0, 0, 0, 0, true, xc, e0, e1)) return rc;
-                OzBatch gb;
-                int mt = 0, nt = 0;
-                double tiles = 0;
-                for (int q = 0; q < nsys; q++) {
-                    const SolveSys& s = bt.s[q];
-                    const int nb = s.npad / NB;
-                    const int hi = nb - e0, lo = nb - e1 > 0 ? nb - e1 : 0;
-                    OzSys& g = gb.s[q];
-                    g.mapA = mapXA[q];
-                    g.mapB = mapWB[q];
-                    g.scaleA = ow[q].scaleX + (size_t)xc * s.mpad;
-                    g.scaleB = ow[q].scaleU;
-                    g.C = s.X;
-                    g.ldc = s.ldx;
-                    g.m_tiles = (hi > lo && lo > 0) ? s.mpad / NB : 0;
-                    g.n_tiles = (hi > lo && lo > 0) ? lo * (NB / OZ_BN) : 0;
-                    g.rowA0 = 0;
-                    g.rowB0 = 0;
-                    g.rowC0 = g.colC0 = 0;
-                    g.kb0 = lo * KB;
-                    g.kb1 = hi > lo ? hi * KB : lo * KB;
-                    g.tri = 0;
-                    mt = g.m_tiles > mt ? g.m_tiles : mt;
-                    nt = g.n_tiles > nt ? g.n_tiles : nt;
-                    if (hi > lo && lo > 0) tiles += (double)(s.mpad / NB) * lo * (hi - lo);
+                if (xc % 2 == 0) {  // (pairs of chunks, as in the forward solve)
+                    if (int rc = oz_slice(-1, 0, 0, 0, 0, true, xc, e0, e1)) return rc;
+                    if (int rc = oz_x_update(true, e0, e1, e1, e1 + SP, xc)) return rc;
+                } else {
+                    if (int rc = oz_slice(-1, 0, 0, 0, 0, true, xc, e0 - SP, e1)) return rc;
+                    if (int rc = oz_x_update(true, e0 - SP, e1, e1, nbmax, xc)) return rc;
                 }
-                for (int q = nsys; q < MAXB; q++) gb.s[q] = gb.s[0];
-                prof_begin(PROF_OZ_GEMM, st);
-                if (int rc = oz_launch_gemm(gb, nsys, mt, nt, st)) return rc;
-                prof_end(tiles * tile_flops * NB, st);
             }
         }
         B200_CUDA(cudaGetLastError());

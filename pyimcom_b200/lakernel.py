@@ -246,8 +246,20 @@ def _chol_launch(items):
         chunks = [(c0, min(c0 + per, n_items), pool[q % nstream]) for q, c0 in enumerate(range(0, n_items, per))]
     # right-hand sides are cloned on the caller's stream (whose allocator pool they return to after the T-apply stage);
     # the solve streams only own what they allocate and free themselves (W, the inverted diagonal blocks)
-    for k, (ds, _, j) in enumerate(items):
-        Xs[k] = ds.mB[j].clone()
+    # (consecutive items of one stamp and output PSF -- its kappa nodes -- share one (nv, mpad, npad) buffer, which is
+    # later handed to the node reduction as it is: no torch.stack copy of nv x 72 MB)
+    bufs = {}
+    k = 0
+    while k < n_items:
+        ds, _, j = items[k]
+        k1 = k + 1
+        while k1 < n_items and items[k1][0] is ds and items[k1][2] == j:
+            k1 += 1
+        buf = ds.mB[j].unsqueeze(0).repeat(k1 - k, 1, 1)
+        bufs[k] = buf
+        for p in range(k, k1):
+            Xs[p] = buf[p - k]
+        k = k1
     for st in pool:
         st.wait_stream(cur)
     for c0, c1, st in chunks:
@@ -262,7 +274,7 @@ def _chol_launch(items):
         ev = torch.cuda.Event()
         ev.record(st)
         events.append(ev)
-    return dict(items=items, Xs=Xs, infos=infos, events=events)
+    return dict(items=items, Xs=Xs, infos=infos, events=events, bufs=bufs)
 
 
 def _chol_finish(h):
@@ -283,7 +295,7 @@ def _chol_finish(h):
             w0 = shifts[id(ds)]
             warnings.warn(f"CholKernel: repaired negative eigenvalue {w0:19.12e}", stacklevel=3)
             W = _padded_system(ds, list(incs) + [abs(w0) + 1e-16])
-            Xs[k] = ds.mB[j].clone()
+            Xs[k].copy_(ds.mB[j])  # (in place: Xs[k] may be a slice of the stamp's node buffer)
             info2, _keep2 = chol_solve_batch([W], [Xs[k]], mrows=[ds.m])
             if int(info2.item()) != 0:
                 raise np.linalg.LinAlgError("Cholesky failed after the eigenvalue repair")
@@ -348,13 +360,15 @@ def solve_chol_finish(handle):
     kappaC = np.asarray(cfg.kappaC_arr, dtype=np.float64)
     nv = kappaC.size
     Xs = _chol_finish(handle["h"])
+    bufs = handle["h"]["bufs"]
     outs = []
     for q, ds in enumerate(dss):
         kappa_arr = kappaC * float(ds.C[j_out])
         if nv == 1:
             outs.append(KernelOutput(Tpi=Xs[q].unsqueeze(0), w=None, kappa_scalar=float(kappa_arr[0])))
         else:
-            Tpi = torch.stack(Xs[q * nv:(q + 1) * nv])
+            Tpi = bufs[q * nv]  # the nv node solutions of this stamp, already contiguous
+            assert Tpi.shape[0] == nv
             outs.append(_node_reduce(ds, j_out, Tpi, kappa_arr, kappaC, cfg.uctarget, cfg.sigmamax))
     return outs
 

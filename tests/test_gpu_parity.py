@@ -549,6 +549,9 @@ def test_repair_branch_survives_pool_eviction():
     assert n_rep > 0  # the case is built to fire the branch
     with warnings.catch_warnings(record=True) as w1:
         warnings.simplefilter("always")
+        from pyimcom_b200.coadd import release_parked_pools
+
+        release_parked_pools()  # (a pool parked by an earlier, larger block would be big enough never to evict)
         gb = GpuBlock(blk, tab)
         gb.pool_bytes = 8  # every batch evicts
         gb.prepare()
