@@ -331,15 +331,23 @@ __global__ void __launch_bounds__(256) k_oz_slice(OzSliceBatch p) {
         x[j + 1] = v.y * inv;
     }
     int8_t* dst = s.S + (((size_t)kb * OZ_NS) * s.rows_total + row) * OZ_BK + c8;
+    // Round-to-nearest-integer by the magic-number addition (|x| < 2^51): the low word of x + 1.5 * 2^52 IS the integer
+    // in two's complement, so no float -> int conversion is needed and a digit costs four FP64 additions / products.
+    // |x| <= 64 for the first digit (the scale bounds the row; garbage input of a failed factorisation is clamped),
+    // |x| <= 64 for every later one by construction (the remainder of a rounding is at most 1/2, times 128).
+    const double MAGIC = 6755399441055744.0;  // 1.5 * 2^52
+#pragma unroll
+    for (int j = 0; j < 8; j++) x[j] = fmin(fmax(x[j], -64.0), 64.0);
 #pragma unroll
     for (int t = 0; t < OZ_NS; t++) {
         uint32_t w[2] = {0u, 0u};
 #pragma unroll
         for (int j = 0; j < 8; j++) {
-            double d = rint(x[j]);
-            d = fmin(fmax(d, -127.0), 127.0);  // (only garbage input -- a failed factorisation -- ever clamps)
+            const double r = x[j] + MAGIC;
+            const int di = __double2loint(r);
+            const double d = r - MAGIC;
             x[j] = (x[j] - d) * 128.0;
-            w[j >> 2] |= ((uint32_t)(int)d & 0xffu) << (8 * (j & 3));
+            w[j >> 2] |= ((uint32_t)di & 0xffu) << (8 * (j & 3));
         }
         *reinterpret_cast<uint2*>(dst + (size_t)t * s.rows_total * OZ_BK) = make_uint2(w[0], w[1]);
     }

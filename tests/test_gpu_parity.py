@@ -215,6 +215,64 @@ def test_chol_solve_random(n, m):
     assert rel(L @ L.T, A) < 1e-13
 
 
+@pytest.mark.parametrize("M,N,K", [(128, 64, 64), (256, 192, 448), (1024, 512, 2048)])
+def test_ozaki_gemm(M, N, K):
+    """b200_dev_ozaki_gemm_nt: C -= A B^T from error-free INT8 digit planes on tcgen05 (csrc/ozaki.cu) against the float64
+    product (cuBLAS) on operands whose rows and entries span twelve decades: the error stays below 4e-15 of
+    sum_k |a_ik| |b_jk| + |c_ij| entry by entry -- the class of a float64 dot product itself (the DMMA tile of this library
+    measures 6e-15 to 2e-14 on the same inputs)."""
+    g = torch.Generator(device="cuda").manual_seed(M + N + K)
+    rnd = lambda *sh: torch.randn(sh, dtype=torch.float64, device="cuda", generator=g)  # noqa: E731
+    uni = lambda *sh: torch.rand(sh, dtype=torch.float64, device="cuda", generator=g)  # noqa: E731
+    A = rnd(M, K) * 10.0 ** (-6 * uni(M, 1)) * 10.0 ** (-6 * uni(M, K))
+    B = rnd(N, K) * 10.0 ** (-6 * uni(N, 1))
+    A[M // 2] = 0.0  # an all-zero row has scale 0
+    C0 = rnd(M, N) * 1e-3
+    nbytes = int(_lib.lib.b200_ozaki_gemm_work_bytes(M, N, K))
+    work = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
+    Cm = C0.clone()
+    _lib.dev_ozaki_gemm_nt(GL.ptr(A), K, GL.ptr(B), K, GL.ptr(Cm), N, M, N, K, GL.ptr(work), nbytes, GL.stream_handle())
+    torch.cuda.synchronize()
+    ref = C0 - A @ B.T
+    bound = A.abs() @ B.abs().T + C0.abs()
+    assert float(((Cm - ref).abs() / bound).max()) < 4e-15
+    assert torch.equal(Cm[M // 2], C0[M // 2])
+
+
+def test_sliced_int8_path_matches_dmma_path():
+    """The batched Cholesky + solves with the long-K updates on the INT8 tensor cores (default) and on the DMMA pipe
+    (B200_OZAKI=0 / no workspace) solve the same ill-conditioned system (cond 1e6, n = 1500: three super-panels, a
+    partial last one, right-hand sides with a half tile) to the same answer: both within P-f64 of LAPACK and of each
+    other, and L L^T = A to 1e-13 either way."""
+    from scipy.linalg import cho_solve, cholesky
+
+    rng = np.random.default_rng(11)
+    n, m = 1500, 200
+    Q, _ = np.linalg.qr(rng.standard_normal((n, n)))
+    A = (Q * np.logspace(-6, 0, n)) @ Q.T
+    A = 0.5 * (A + A.T)
+    B = rng.standard_normal((m, n))
+    ref = cho_solve((cholesky(A, lower=True), True), B.T).T
+    got = {}
+    old = GL.OZAKI
+    try:
+        for oz in (True, False):
+            GL.OZAKI = oz
+            ds = GL.upload_system(A, B[None], [1.0], 1)
+            W = GL._padded_system(ds, [])
+            X = ds.mB[0].clone()
+            info, _k = GL.chol_solve_batch([W], [X], mrows=[m])
+            assert int(info.item()) == 0
+            got[oz] = X[:m, :n].cpu().numpy()
+            L = np.tril(W[:n, :n].cpu().numpy())
+            assert rel(L @ L.T, A) < 1e-13
+            assert rel(got[oz], ref) < P64
+    finally:
+        GL.OZAKI = old
+    assert rel(got[True], got[False]) < 1e-10
+    assert not np.array_equal(got[True], got[False])  # (two different arithmetic paths really ran)
+
+
 def test_legacy_tile_path():
     """B200_TILE64=0 (the 128x128 one-CTA-per-SM tile, kept for A/B comparisons) is read once per process: run the dense
     linear-algebra tests again in a child process with it."""
