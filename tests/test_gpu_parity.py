@@ -269,7 +269,7 @@ def test_sliced_int8_path_matches_dmma_path():
             assert rel(got[oz], ref) < P64
     finally:
         GL.OZAKI = old
-    assert rel(got[True], got[False]) < 1e-10
+    assert rel(got[True], got[False]) < 2 * P64  # (cond 1e6: two float64-class solvers differ by ~cond * eps)
     assert not np.array_equal(got[True], got[False])  # (two different arithmetic paths really ran)
 
 
