@@ -135,3 +135,20 @@ print("bound")
 """
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and "bound" in r.stdout, r.stdout[-1500:] + r.stderr[-1500:]
+
+
+def test_workspace_sizes_of_the_sliced_path(lib):
+    """Host-side contract of the INT8 path (no compute call): 8 digit planes per operand; the per-system scratch of
+    b200_dev_chol_solve holds the digit planes of W and X (8 bytes per matrix element -- exactly the size of the float64
+    matrices they describe) plus the row scales, and the GEMM scratch the planes of both operands."""
+    assert lib.lib.b200_ozaki_slices() == 8
+    npad, mpad = 6272, 1536
+    wb = lib.lib.b200_chol_work_bytes(npad, mpad)
+    planes = 8 * npad * (npad + mpad)
+    scales = 8 * (2 * npad + (npad // 128) * mpad)
+    assert planes + scales <= wb <= planes + scales + 4096
+    assert lib.lib.b200_chol_work_bytes(128, 0) < lib.lib.b200_chol_work_bytes(256, 0)
+    M, N, K = 256, 128, 320
+    gb = lib.lib.b200_ozaki_gemm_work_bytes(M, N, K)
+    assert 8 * (M + N) * K + 8 * (M + N) <= gb <= 8 * (M + N) * K + 8 * (M + N) + 8192
+    assert ctypes.sizeof(lib.SolveSys) == 72 and lib.SolveSys.work.offset == 56
