@@ -258,3 +258,19 @@ def test_config3_inside_the_cg_spread():
     e = cases.full_errors(s, g)
     assert e["sysmata"] < P64 and e["mhalfb"] < P64
     assert e["T"] < 3 * spread_all and e["outimage"] < 10 * spread_all
+
+
+def test_paper4_block_maps_vs_reference_golden(block):
+    """The WHOLE 16-stamp paper-4 block (bench.py's block with n1 = 2) through GpuBlock.run() -- batched system matrices,
+    the sliced INT8 / DMMA Cholesky and solves, T-apply, overlap-add -- against block maps the reference itself produced
+    (tests/golden/make_golden_block.py: its own OutStamp path stamp by stamp, accumulated as Block._output_stamp_wrapper
+    does, coadd.py:1976-1994).  P-f32: the maps are float32 sums of float32 stamp arrays."""
+    blk, tab = block
+    g = np.load(os.path.join(GOLDEN, "full_p4block.npz"))
+    maps = GpuBlock(blk, tab).prepare().run().download()
+    assert set(g.files) <= set(maps)
+    errs = {k: rel(maps[k], g[k]) for k in g.files}
+    print({k: f"{v:.1e}" for k, v in errs.items()})
+    assert errs["out_map"] < 1e-5 and errs["T_weightmap"] < 2e-6
+    assert errs["Sigma_map"] < 1e-5 and errs["kappa_map"] < 2e-6 and errs["Tsum_map"] < 2e-6 and errs["Neff_map"] < 1e-5
+    assert np.abs(maps["UC_map"] - g["UC_map"]).max() < 1e-5 * max(1.0, float(np.abs(g["UC_map"]).max()))

@@ -314,3 +314,27 @@ def test_cg_sensitivity(golden_dir):
     assert k2.f64[0]["niter"].max() <= 14
     assert np.array_equal(k2.f64[0]["niter"], k3.f64[0]["niter"])
     assert np.abs(k3.f64[0]["Ti"] - k2.f64[0]["Ti"]).max() / np.abs(k2.f64[0]["Ti"]).max() < 1e-7
+
+
+def test_oracle_block_maps_vs_reference_full_size(golden_dir):
+    """Four stamps of the 16-stamp paper-4 block through the oracle, overlap-added where they land: the reference-made
+    block maps (tests/golden/full_p4block.npz) agree there to P-f32.  (The GPU test compares the whole block.)"""
+    g = np.load(os.path.join(golden_dir, "full_p4block.npz"))
+    blk = cases.make_full_block("p4")
+    cfg = blk.cfg
+    R.set_threads(os.cpu_count() or 1)
+    tab = PSFTables(blk, R.iD5512C, R.gridD5512C, dedup=True)
+    side = cfg.NsideP + 2 * cfg.fade_kernel
+    assert g["out_map"].shape == (1, cfg.n_inframe, side, side)
+    j, i = 1, 1  # the corner stamp: its first n2 x n2 pixels receive no other stamp's fade border
+    o = OracleOutStamp(blk, tab, j, i)
+    o.build_system_matrices()
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        OL.CholKernel(o)()
+    o.post_kernel()
+    o.perform_coaddition()
+    n2 = cfg.n2
+    assert rel(o.outimage[:, :, :n2, :n2], g["out_map"][:, :, :n2, :n2]) < 1e-5
+    assert rel(o.Sigma[:, :n2, :n2], g["Sigma_map"][:, :n2, :n2]) < 1e-5
+    assert rel(o.Tsum_stamp, g["T_weightmap"][:, :, 0, 0]) < 2e-6
