@@ -180,7 +180,8 @@ typedef struct b200_solve_sys {
     size_t work_bytes;
 } b200_solve_sys;
 
-/* scipy.linalg.cholesky + cho_solve (lakernel.py:263, 276, 304, 358) for up to B200_MAXB systems at once. */
+/* scipy.linalg.cholesky + cho_solve (lakernel.py:263, 276, 304, 358) for up to B200_MAXB systems at once.
+ * do_solve: 0 factor only, 1 X <- X (L L^T)^-1, 2 forward substitution only (X <- X L^-T). */
 int b200_dev_chol_solve(const b200_solve_sys* sys, int nsys, int do_factor, int do_solve, void* stream);
 size_t b200_chol_work_bytes(int npad, int mpad);
 /* W <- A (n x n) + sum(incs) on the diagonal, identity in rows/cols n..npad-1 (lakernel.py:295-299, 356). */
@@ -217,6 +218,10 @@ typedef struct b200_eigh_problem {
     int lda, ldv, n, pad_;
 } b200_eigh_problem;
 int b200_dev_eigh_batch(const b200_eigh_problem* problems, int nsys, int max_sweeps, int* sweeps, void* stream);
+/* Householder tridiagonalisation A = Q T Q^T of one symmetric matrix (the first stage of the eigensolver; exposed for the
+ * tests): A (n x n, lda) is overwritten -- row k holds reflector k at columns k+1.. (leading 1 stored) -- and the device
+ * arrays d, e, tau (n doubles each) receive T's diagonal, its sub-diagonal (e[n-1] = 0) and the reflector scales. */
+int b200_dev_tridiag(double* A, int lda, int n, double* d, double* e, double* tau, void* stream);
 
 /* ---- 4. device: per-output-pixel Lagrange multiplier (stage b) --------------------------------- */
 int b200_dev_lakernel1(const double* lam, const double* mPhalf, int ldp, int m, int n, double C, double targetleak,

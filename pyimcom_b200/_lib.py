@@ -114,6 +114,7 @@ PROTOTYPES = {
     "b200_dev_transpose": [vp, i32, vp, i32, i32, i32, vp],
     "b200_dev_eigh_batch": [C.POINTER(EighProblem), i32, i32, C.POINTER(i32), vp],
     "b200_dev_eigh": [vp, i32, i32, vp, i32, vp, i32, C.POINTER(i32), vp],
+    "b200_dev_tridiag": [vp, i32, i32, vp, vp, vp, vp],
     "b200_dev_lakernel1": [vp, vp, i32, i32, i32, f64, f64, f64, f64, i32, vp, vp, vp, vp, i32, f64, vp],
     "b200_dev_eigen_single": [vp, vp, i32, i32, i32, f64, f64, vp, vp, vp, i32, vp],
     "b200_dev_lsolve_sps": [i32, vp, vp, vp, vp, vp],

@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libpyimcom_b200.so")
-SOURCES = ["capi.cu", "interp.cu", "linalg.cu", "eigen.cu", "kappa.cu", "iter.cu", "coadd.cu", "partition.cu", "ozaki.cu"]
+SOURCES = ["capi.cu", "interp.cu", "linalg.cu", "eigen.cu", "kappa.cu", "iter.cu", "coadd.cu", "partition.cu", "ozaki.cu", "trieig.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC"]
 
 

@@ -1,6 +1,7 @@
 // C ABI of libpyimcom_b200.so (declared in include/pyimcom_b200.h): error plumbing, the grow-only device
 // scratch of the host-seam functions, and thin extern "C" wrappers over the launchers in kernels.h.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <vector>
@@ -67,6 +68,7 @@ struct ProfRec {
 };
 static int g_prof_on = 0;
 static std::vector<ProfRec> g_prof;
+static std::vector<size_t> g_prof_open;  // begin/end pairs nest (the eigensolver's scope holds its GEMMs' scopes)
 
 // events are pooled: creating them inside the timed region would put driver calls between the launches
 static std::vector<cudaEvent_t> g_event_pool;
@@ -89,18 +91,21 @@ void prof_begin(int kind, cudaStream_t st) {
     r.work = 0.0;
     if (!prof_event(&r.a) || !prof_event(&r.b)) return;
     cudaEventRecord(r.a, st);
+    g_prof_open.push_back(g_prof.size());
     g_prof.push_back(r);
 }
 
 void prof_end(double work, cudaStream_t st) {
-    if (!g_prof_on || g_prof.empty()) return;
-    ProfRec& r = g_prof.back();
+    if (!g_prof_on || g_prof_open.empty()) return;
+    ProfRec& r = g_prof[g_prof_open.back()];
+    g_prof_open.pop_back();
     r.work = work;
     cudaEventRecord(r.b, st);
 }
 
 static void prof_reset() {
     g_prof.clear();
+    g_prof_open.clear();
     g_event_next = 0;  // the pooled events are reused by the next recording
 }
 
@@ -163,7 +168,10 @@ int b200_profile_read(int kind, double* ms, double* work, long long* count) {
     for (auto& r : g_prof) {
         if (r.kind != kind) continue;
         float e = 0.f;
-        if (cudaEventElapsedTime(&e, r.a, r.b) != cudaSuccess) continue;
+        if (cudaEventElapsedTime(&e, r.a, r.b) != cudaSuccess) {
+            (void)cudaGetLastError();  // a scope that never closed: drop it, and do not leave the error for the next call
+            continue;
+        }
         t += e;
         w += r.work;
         c++;
@@ -359,7 +367,13 @@ int b200_dev_transpose(const double* A, int lda, double* At, int ldat, int rows,
 }
 int b200_dev_eigh_batch(const b200_eigh_problem* problems, int nsys, int max_sweeps, int* sweeps, void* s) {
     B200_REQUIRE(problems != nullptr || nsys <= 0, "eigh_batch: null problem list");
-    return launch_jacobi_eigh_batch(problems, nsys, max_sweeps, sweeps, ST(s));
+    const char* e = getenv("B200_EIGH");  // "jacobi": the block-Jacobi solver of round 1 (eigen.cu)
+    if (e && e[0] == 'j') return launch_jacobi_eigh_batch(problems, nsys, max_sweeps, sweeps, ST(s));
+    if (sweeps) *sweeps = 0;
+    return launch_tri_eigh_batch(problems, nsys, ST(s));
+}
+int b200_dev_tridiag(double* A, int lda, int n, double* d, double* e, double* tau, void* s) {
+    return launch_tridiag(A, lda, n, d, e, tau, ST(s));
 }
 int b200_dev_eigh(double* A, int lda, int n, double* Vt, int ldv, double* lam, int max_sweeps, int* sweeps, void* s) {
     return launch_jacobi_eigh(A, lda, n, Vt, ldv, lam, max_sweeps, sweeps, ST(s));

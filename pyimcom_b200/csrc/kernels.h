@@ -24,6 +24,17 @@ struct SolveBatch {
     SolveSys s[MAXB];
 };
 
+// one product of a batched GEMM launch (linalg.cu: launch_gemm_nt_batch)
+struct GemmProb {
+    const double* A;
+    const double* B;
+    double* C;
+    int lda, ldb, ldc, M, N, K;
+};
+struct GemmBatch {
+    GemmProb p[MAXB];
+};
+
 struct DiagNodes {
     double v[16];
 };
@@ -61,6 +72,7 @@ int launch_chol_solve(const SolveSys* h_sys, int nsys, int do_factor, int do_sol
 size_t chol_work_bytes(int npad, int mpad);
 int launch_gemm_nt(const double* A, int lda, const double* B, int ldb, double* C, int ldc, int M, int N, int K,
                    int accumulate, cudaStream_t s);
+int launch_gemm_nt_batch(const GemmProb* probs, int nprob, int accumulate, cudaStream_t s);
 int launch_pad_system(double* W, int ldw, int n, int npad, const double* A, int lda, const double* incs, int ninc,
                       cudaStream_t s);
 int launch_transpose(const double* A, int lda, double* At, int ldat, int rows, int cols, cudaStream_t s);
@@ -96,6 +108,10 @@ int launch_iter_cg(const double* AA, int lda, double diag_add, const double* mB,
 int launch_jacobi_eigh_batch(const EighProblem* pr, int nsys, int max_sweeps, int* sweeps_done, cudaStream_t s);
 int launch_jacobi_eigh(double* A, int lda, int n, double* Vt, int ldv, double* lam, int max_sweeps, int* sweeps_done,
                        cudaStream_t s);
+
+// trieig.cu
+int launch_tri_eigh_batch(const EighProblem* pr, int nsys, cudaStream_t s);
+int launch_tridiag(double* A, int lda, int n, double* d, double* e, double* tau, cudaStream_t s);
 
 // coadd.cu
 int launch_finalize(const FinalizeArgs& a, cudaStream_t s);

@@ -315,6 +315,18 @@ __global__ void __launch_bounds__(GT2, CTAS2) k_gemm64_nt(const double* __restri
                       C + (size_t)tm * TB * ldc + (size_t)tn * TB, ldc, K, smem);
 }
 
+// The same tile over several independent products at once (blockIdx.z = problem): the eigensolver's Gram matrices and
+// compact-WY panel products of all systems of a batch share each launch.
+template <int MODE>
+__global__ void __launch_bounds__(GT2, CTAS2) k_gemm64_nt_batch(GemmBatch gb) {
+    extern __shared__ __align__(16) double smem[];
+    const GemmProb& g = gb.p[blockIdx.z];
+    const int tn = blockIdx.x, tm = blockIdx.y;
+    if (tm * TB >= g.M || tn * TB >= g.N) return;
+    gemm_tile64<MODE>(g.A + (size_t)tm * TB * g.lda, g.lda, g.B + (size_t)tn * TB * g.ldb, g.ldb,
+                      g.C + (size_t)tm * TB * g.ldc + (size_t)tn * TB, g.ldc, g.K, smem);
+}
+
 // Row-tile r of the right-hand sides holds at most 64 real rows (mrows = number of real rows; 0 = unknown: all tiles full).
 __device__ __forceinline__ bool x_half_tile(const SolveSys& s, int r) {
     return s.mrows > 0 && s.mrows - r * NB <= NB / 2;
@@ -671,6 +683,9 @@ int gemm_attrs() {
     B200_CUDA(cudaFuncSetAttribute(k_gemm64_nt<TILE_ASSIGN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM2_SMEM));
     B200_CUDA(cudaFuncSetAttribute(k_gemm64_nt<TILE_SUB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM2_SMEM));
     B200_CUDA(cudaFuncSetAttribute(k_gemm64_nt<TILE_ADD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM2_SMEM));
+    B200_CUDA(cudaFuncSetAttribute(k_gemm64_nt_batch<TILE_ASSIGN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM2_SMEM));
+    B200_CUDA(cudaFuncSetAttribute(k_gemm64_nt_batch<TILE_SUB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM2_SMEM));
+    B200_CUDA(cudaFuncSetAttribute(k_gemm64_nt_batch<TILE_ADD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM2_SMEM));
     {
         const char* e = getenv("B200_TILE64");  // 0: the 128x128 one-CTA-per-SM tile everywhere (A/B comparisons)
         g_tile64 = !(e && e[0] == '0');
@@ -974,7 +989,7 @@ int launch_chol_solve(const SolveSys* h_sys, int nsys, int do_factor, int do_sol
         }
         B200_CUDA(cudaGetLastError());
     }
-    if (do_solve && mbmax > 0) {
+    if (do_solve == 1 && mbmax > 0) {  // (do_solve == 2: forward substitution only, X <- X L^-T)
         double mbsum = 0;
         for (int q = 0; q < nsys; q++) mbsum += mb_eff(q);
         const int SP = g_sp;
@@ -1056,6 +1071,39 @@ int launch_gemm_nt(const double* A, int lda, const double* B, int ldb, double* C
     else
         k_gemm_nt<TILE_SUB><<<grid, GT, GEMM_SMEM, st>>>(A, lda, B, ldb, C, ldc, K);
     prof_end(2.0 * M * (double)N * K, st);
+    B200_LAUNCH_CHECK();
+    return 0;
+}
+
+// Several products C_q (M_q x N_q) = [C_q +/-] A_q B_q^T in one launch (M, N multiples of 64, K even, at most MAXB).
+int launch_gemm_nt_batch(const GemmProb* probs, int nprob, int accumulate, cudaStream_t st) {
+    if (nprob <= 0) return 0;
+    B200_REQUIRE(nprob <= MAXB, "at most MAXB products per batched GEMM");
+    if (int rc = gemm_attrs()) return rc;
+    GemmBatch gb;
+    int mmax = 0, nmax = 0;
+    double flops = 0;
+    for (int q = 0; q < nprob; q++) {
+        const GemmProb& g = probs[q];
+        B200_REQUIRE(g.M % TB == 0 && g.N % TB == 0 && g.K % 2 == 0 && g.K > 0 && g.lda % 2 == 0 && g.ldb % 2 == 0 &&
+                         g.ldc % 2 == 0,
+                     "gemm_nt_batch wants M, N multiples of 64, even K and leading dimensions");
+        gb.p[q] = g;
+        mmax = g.M > mmax ? g.M : mmax;
+        nmax = g.N > nmax ? g.N : nmax;
+        flops += 2.0 * g.M * (double)g.N * g.K;
+    }
+    for (int q = nprob; q < MAXB; q++) gb.p[q] = gb.p[0];
+    if (mmax == 0 || nmax == 0) return 0;
+    const dim3 grid(nmax / TB, mmax / TB, nprob);
+    prof_begin(PROF_GEMM, st);
+    if (accumulate == 0)
+        k_gemm64_nt_batch<TILE_ASSIGN><<<grid, GT2, GEMM2_SMEM, st>>>(gb);
+    else if (accumulate > 0)
+        k_gemm64_nt_batch<TILE_ADD><<<grid, GT2, GEMM2_SMEM, st>>>(gb);
+    else
+        k_gemm64_nt_batch<TILE_SUB><<<grid, GT2, GEMM2_SMEM, st>>>(gb);
+    prof_end(flops, st);
     B200_LAUNCH_CHECK();
     return 0;
 }

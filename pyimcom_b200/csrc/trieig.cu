@@ -1,0 +1,650 @@
+// Symmetric eigendecomposition by tridiagonalisation (replaces np.linalg.eigh at lakernel.py:162, 201, 266 for the
+// EigenKernel and the Cholesky repair branch).
+//
+// The matrices of this path have spectra graded over ten decades with ~1 % relative gaps everywhere, so the ABSOLUTE gaps
+// between neighbours are far below the rounding level of the large eigenvalues: two-sided Jacobi (eigen.cu) then only
+// converges linearly, ~37 sweeps of 12 n^3 flops.  This solver does what LAPACK-class solvers do, arranged for the GPU
+// and batched over the OutStamps of a batch (one grid dimension = the system):
+//
+//   1. Householder tridiagonalisation  A = Q T Q^T, unblocked but FUSED: one pass over the trailing matrix per column
+//      applies the rank-2 update of column k-1 and forms the symmetric matrix-vector product of column k
+//      (k_tri_reflect + k_tri_update: two launches per column, 16 n^3 / 3 bytes of traffic per system);
+//   2. eigenvalues of T by bisection on Sturm counts, one thread per eigenvalue (k_tri_bisect);
+//   3. eigenvectors of T by inverse iteration, one thread per eigenvalue, every eigenvalue independently
+//      (k_tri_invit: LU with partial pivoting of T - lambda I, three iterations from a pseudo-random start).  Vectors of
+//      neighbouring eigenvalues come out orthogonal only to eps |T| / gap;
+//   4. which is repaired for ALL pairs at once by two rounds of Cholesky-QR on the n x n matrix of vectors: G = Z Z^T
+//      (DMMA GEMM), G = L L^T and Z <- L^-1 Z through the batched Cholesky / triangular solve of linalg.cu.  G is
+//      I + small except inside numerically degenerate clusters, where the random starts make it a well-conditioned Gram
+//      matrix of generic vectors of the cluster's subspace (any orthonormal basis of it serves the callers);
+//   5. back-transformation Z <- Q Z with the reflectors in compact-WY panels of 128: three DMMA GEMMs per panel.
+//
+// Checked on the device against NumPy (tests/test_gpu_parity.py::test_eigh_device, tools/eigh_bench.py): orthogonality and
+// residual at the 1e-15 |A| level, eigenvalues to eps |A|.
+#include <math.h>
+#include <stdlib.h>
+
+#include "common.cuh"
+#include "kernels.h"
+
+namespace b200 {
+
+namespace {
+
+struct TriSys {
+    double* A;     // (n, lda): in the matrix; out: reflector k in row k, columns k+1.. (v[k+1] = 1 stored)
+    double* d;     // [n] diagonal of T
+    double* e;     // [n] sub-diagonal of T (e[k] couples k and k+1; e[n-1] = 0)
+    double* tau;   // [n]
+    double* vbuf;  // [2][n] reflector of the current / previous column (zeros up to and including the column index)
+    double* wbuf;  // [2][n]
+    double* p;     // [n]
+    int lda, n;
+};
+struct TriBatch {
+    TriSys s[MAXB];
+};
+
+// Column k, single-CTA part: finish w_{k-1} = p - (tau/2)(p.v) v, bring row k up to date with the pending rank-2
+// update of column k-1, then generate the reflector of column k (LAPACK dlarfg convention) from it.
+// last = 1 (k = n-2): no reflector any more; rows n-2 and n-1 are completed and d, e written.
+__global__ void __launch_bounds__(256) k_tri_reflect(TriBatch bt, int k) {
+    __shared__ double red[40];
+    const TriSys& s = bt.s[blockIdx.x];
+    const int n = s.n, tid = threadIdx.x;
+    if (k >= n || (n > 1 && k == n - 1)) return;  // (column n-1 is completed together with column n-2)
+    const double* vp = s.vbuf + (size_t)((k + 1) & 1) * n;  // reflector of column k-1
+    double* wp = s.wbuf + (size_t)((k + 1) & 1) * n;
+    if (k > 0) {
+        double dot = 0.0;
+        for (int i = k + tid; i < n; i += 256) dot += s.p[i] * vp[i];
+        dot = block_sum(dot, red);
+        const double alpha = -0.5 * s.tau[k - 1] * dot;
+        for (int i = k + tid; i < n; i += 256) wp[i] = s.p[i] + alpha * vp[i];
+        __syncthreads();
+    }
+    double* row = s.A + (size_t)k * s.lda;
+    if (k > 0) {
+        const double vk = vp[k], wk = wp[k];
+        for (int j = k + tid; j < n; j += 256) row[j] -= vk * wp[j] + wk * vp[j];
+        __syncthreads();
+    }
+    if (k >= n - 2) {  // tail: no reflector for the last two columns
+        if (k == n - 2) {
+            double* row1 = s.A + (size_t)(n - 1) * s.lda;
+            if (tid == 0) {
+                if (k > 0) row1[n - 1] -= 2.0 * vp[n - 1] * wp[n - 1];
+                s.d[n - 2] = row[n - 2];
+                s.e[n - 2] = row[n - 1];
+                s.d[n - 1] = row1[n - 1];
+                s.e[n - 1] = 0.0;
+                s.tau[n - 2] = 0.0;
+                s.tau[n - 1] = 0.0;
+            }
+        } else if (tid == 0) {  // n == 1
+            s.d[n - 1] = row[n - 1];
+            s.e[n - 1] = 0.0;
+            s.tau[n - 1] = 0.0;
+        }
+        return;
+    }
+    double* v = s.vbuf + (size_t)(k & 1) * n;
+    double ss = 0.0;
+    for (int j = k + 2 + tid; j < n; j += 256) ss += row[j] * row[j];
+    ss = block_sum(ss, red);
+    const double alpha0 = row[k + 1];
+    double beta = alpha0, tau = 0.0, scale = 0.0;
+    if (ss > 0.0) {
+        const double nrm = sqrt(alpha0 * alpha0 + ss);
+        beta = alpha0 >= 0.0 ? -nrm : nrm;
+        tau = (beta - alpha0) / beta;
+        scale = 1.0 / (alpha0 - beta);
+    }
+    __syncthreads();
+    for (int j = tid; j < n; j += 256) {
+        double vj = 0.0;
+        if (j == k + 1)
+            vj = 1.0;
+        else if (j > k + 1)
+            vj = row[j] * scale;
+        v[j] = vj;
+        if (j > k) row[j] = vj;  // the reflector lives in the dead row k from now on
+    }
+    if (tid == 0) {
+        s.d[k] = row[k];
+        s.e[k] = beta;
+        s.tau[k] = tau;
+    }
+}
+
+// Column k, parallel part: every row i > k of the trailing matrix receives the pending rank-2 update of column k-1
+// (columns > k) and contributes p_i = tau_k * (a_i . v_k).  One warp per row, 8 rows per CTA in flight.
+__global__ void __launch_bounds__(256) k_tri_update(TriBatch bt, int k) {
+    const TriSys& s = bt.s[blockIdx.y];
+    const int n = s.n;
+    if (k >= n - 2) return;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const double* vp = s.vbuf + (size_t)((k + 1) & 1) * n;
+    const double* wp = s.wbuf + (size_t)((k + 1) & 1) * n;
+    const double* v = s.vbuf + (size_t)(k & 1) * n;
+    const double tau = s.tau[k];
+    const bool pend = k > 0;
+    for (int i = k + 1 + blockIdx.x * 8 + warp; i < n; i += gridDim.x * 8) {
+        double* row = s.A + (size_t)i * s.lda;
+        const double vi = pend ? vp[i] : 0.0, wi = pend ? wp[i] : 0.0;
+        double acc = 0.0;
+        for (int j = k + 1 + lane; j < n; j += 32) {
+            double a = row[j];
+            if (pend) {
+                a -= vi * wp[j] + wi * vp[j];
+                row[j] = a;
+            }
+            acc += a * v[j];
+        }
+        acc = warp_sum(acc);
+        if (lane == 0) s.p[i] = tau * acc;
+    }
+}
+
+// ---- eigenvalues of the tridiagonal matrix: bisection on Sturm counts, one thread per eigenvalue ----------------
+__global__ void __launch_bounds__(256) k_tri_bisect(TriBatch bt, double* const* lam_out) {
+    extern __shared__ double sm[];  // d[n], e2[n]
+    const TriSys& s = bt.s[blockIdx.y];
+    const int n = s.n;
+    double* d = sm;
+    double* e2 = sm + n;
+    double lo = 1e300, hi = -1e300, emax = 0.0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const double di = s.d[i], ei = i + 1 < n ? s.e[i] : 0.0, em = i > 0 ? s.e[i - 1] : 0.0;
+        d[i] = di;
+        e2[i] = ei * ei;
+        const double r = fabs(ei) + fabs(em);
+        lo = fmin(lo, di - r);
+        hi = fmax(hi, di + r);
+        emax = fmax(emax, fabs(ei));
+    }
+    __shared__ double slo[256], shi[256], sem[256];
+    slo[threadIdx.x] = lo;
+    shi[threadIdx.x] = hi;
+    sem[threadIdx.x] = emax;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) {
+            slo[threadIdx.x] = fmin(slo[threadIdx.x], slo[threadIdx.x + o]);
+            shi[threadIdx.x] = fmax(shi[threadIdx.x], shi[threadIdx.x + o]);
+            sem[threadIdx.x] = fmax(sem[threadIdx.x], sem[threadIdx.x + o]);
+        }
+        __syncthreads();
+    }
+    const double gl = slo[0], gu = shi[0];
+    const double tnorm = fmax(fabs(gl), fabs(gu));
+    const double pivmin = fmax(2.2250738585072014e-308 * fmax(1.0, sem[0] * sem[0]), 1e-300);
+    const double gl2 = gl - 2.0 * tnorm * 2.220446049250313e-16 * n - 2.0 * pivmin;
+    const double gu2 = gu + 2.0 * tnorm * 2.220446049250313e-16 * n + 2.0 * pivmin;
+    double* lam = lam_out[blockIdx.y];
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
+        double a = gl2, b = gu2;  // eigenvalue j (ascending, 0-based): count(x) = #eigenvalues < x
+        for (int it = 0; it < 200; it++) {
+            const double x = 0.5 * (a + b);
+            if (!(x > a) || !(x < b)) break;
+            int cnt = 0;
+            double q = d[0] - x;
+            if (fabs(q) < pivmin) q = -pivmin;
+            cnt += q < 0.0;
+            for (int i = 1; i < n; i++) {
+                q = d[i] - x - e2[i - 1] / q;
+                if (fabs(q) < pivmin) q = -pivmin;
+                cnt += q < 0.0;
+            }
+            if (cnt > j)
+                b = x;
+            else
+                a = x;
+        }
+        lam[j] = 0.5 * (a + b);
+    }
+}
+
+// ---- eigenvectors of the tridiagonal matrix: inverse iteration, one thread per eigenvalue -----------------------
+// (T - x I) = P L U with partial pivoting (U has two super-diagonals); three solves from a pseudo-random start.
+// Per-thread arrays live in global scratch with the thread index fastest ([i][thread]: coalesced).
+__device__ __forceinline__ double hash_unit(unsigned a, unsigned b) {
+    unsigned h = a * 0x9E3779B1u ^ (b + 0x7F4A7C15u) * 0x85EBCA77u;
+    h ^= h >> 15;
+    h *= 0xC2B2AE3Du;
+    h ^= h >> 13;
+    h *= 0x27D4EB2Fu;
+    h ^= h >> 16;
+    return ((double)h + 0.5) * (2.0 / 4294967296.0) - 1.0;  // (-1, 1)
+}
+
+struct InvitSys {
+    const double* d;
+    const double* e;
+    const double* lam;
+    double* Zt;       // (ntot, ldz): row j <- eigenvector j of T
+    double* scratch;  // 4 * n * nthr doubles: u0, u1, u2, x
+    unsigned char* piv;  // n * nthr
+    int n, ldz, nthr;
+};
+struct InvitBatch {
+    InvitSys s[MAXB];
+};
+
+__global__ void __launch_bounds__(128) k_tri_invit(InvitBatch bt) {
+    const InvitSys& s = bt.s[blockIdx.y];
+    const int n = s.n, j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    const size_t st = (size_t)s.nthr;  // stride between consecutive i
+    double* u0 = s.scratch + j;
+    double* u1 = u0 + (size_t)n * st;
+    double* u2 = u1 + (size_t)n * st;
+    double* x = u2 + (size_t)n * st;
+    unsigned char* pv = s.piv + j;
+    // shift: neighbouring eigenvalues closer than a few ulps of |T| are pushed apart (dstein does the same), so that no
+    // two threads factor the same matrix
+    double tn = 0.0;
+    tn = fmax(fabs(s.lam[0]), fabs(s.lam[n - 1]));
+    const double sep = 10.0 * 2.220446049250313e-16 * fmax(tn, 1e-300);
+    double xs = s.lam[j];
+    {
+        // distance to the start of a run of too-close eigenvalues below j
+        int back = 0;
+        while (j - back - 1 >= 0 && s.lam[j - back] - s.lam[j - back - 1] < sep && back < 4096) back++;
+        if (back > 0) xs = s.lam[j - back] + back * sep;
+    }
+    const double tiny = 2.220446049250313e-16 * fmax(tn, 1e-300);
+    // ---- factorisation (row i of the working pair is (a, b, c) = (diag, super1, super2)) ----
+    double a = s.d[0] - xs, b = n > 1 ? s.e[0] : 0.0, c = 0.0;
+    for (int i = 0; i < n - 1; i++) {
+        const double sub = s.e[i];                                  // element (i+1, i)
+        const double dn = s.d[i + 1] - xs, en = i + 2 < n ? s.e[i + 1] : 0.0;  // row i+1: (dn, en)
+        double m;
+        if (fabs(a) >= fabs(sub)) {  // no interchange
+            if (a == 0.0) a = tiny;
+            m = sub / a;
+            u0[i * st] = a;
+            u1[i * st] = b;
+            u2[i * st] = c;
+            pv[i * st] = 0;
+            x[i * st] = m;  // multiplier parked in x until the solves start (x is rebuilt below)
+            a = dn - m * b;
+            b = en - m * c;
+            c = 0.0;
+        } else {  // rows i and i+1 swap
+            m = a / sub;
+            u0[i * st] = sub;
+            u1[i * st] = dn;
+            u2[i * st] = en;
+            pv[i * st] = 1;
+            x[i * st] = m;
+            a = b - m * dn;
+            b = c - m * en;
+            c = 0.0;
+        }
+    }
+    if (a == 0.0) a = tiny;
+    u0[(size_t)(n - 1) * st] = a;
+    u1[(size_t)(n - 1) * st] = 0.0;
+    u2[(size_t)(n - 1) * st] = 0.0;
+    double* zrow = s.Zt + (size_t)j * s.ldz;  // (own row: used as the multiplier store during the solves)
+    for (int i = 0; i < n - 1; i++) zrow[i] = x[i * st];
+    // ---- three solves ----
+    for (int it = 0; it < 3; it++) {
+        // right-hand side: pseudo-random start, then the previous (normalised) iterate
+        if (it == 0)
+            for (int i = 0; i < n; i++) x[i * st] = hash_unit((unsigned)j, (unsigned)i);
+        // forward: apply P and L
+        for (int i = 0; i < n - 1; i++) {
+            const double m = zrow[i];
+            double xi = x[i * st], xn = x[(size_t)(i + 1) * st];
+            if (pv[i * st]) {
+                const double t = xi;
+                xi = xn;
+                xn = t - m * xi;
+            } else {
+                xn -= m * xi;
+            }
+            x[i * st] = xi;
+            x[(size_t)(i + 1) * st] = xn;
+        }
+        // backward with U
+        double x1 = 0.0, x2 = 0.0, nrm2 = 0.0, big = 0.0;
+        for (int i = n - 1; i >= 0; i--) {
+            double v = (x[i * st] - u1[i * st] * x1 - u2[i * st] * x2) / u0[i * st];
+            x[i * st] = v;
+            x2 = x1;
+            x1 = v;
+            big = fmax(big, fabs(v));
+        }
+        // normalise (scaled to avoid overflow)
+        const double sc = big > 0.0 ? 1.0 / big : 1.0;
+        for (int i = 0; i < n; i++) {
+            const double v = x[i * st] * sc;
+            nrm2 += v * v;
+        }
+        const double inv = sc / sqrt(fmax(nrm2, 1e-300));
+        for (int i = 0; i < n; i++) x[i * st] *= inv;
+    }
+    for (int i = 0; i < n; i++) zrow[i] = x[i * st];
+}
+
+// ---- compact-WY panels of the reflectors ------------------------------------------------------------------------
+struct WySys {
+    const double* A;    // reflector store (row k: v_k at columns > k)
+    const double* tau;
+    double *Vt, *V, *S, *T;  // (128, ntot), (ntot, 128), (128, 128), (128, 128)
+    int lda, n, ntot, active;
+};
+struct WyBatch {
+    WySys s[MAXB];
+};
+
+// Vt (128, ntot) <- rows p0 .. p0+127 of the reflector store (v_k[k+1] = 1 is stored), zero elsewhere; V its transpose.
+__global__ void __launch_bounds__(256) k_wy_extract(WyBatch wb, int p0) {
+    const WySys& w = wb.s[blockIdx.z];
+    if (!w.active) return;
+    const int r = blockIdx.y;  // reflector inside the panel
+    const int k = p0 + r;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < w.ntot; i += gridDim.x * blockDim.x) {
+        double v = 0.0;
+        if (k < w.n - 2 && i > k && i < w.n) v = w.A[(size_t)k * w.lda + i];
+        w.Vt[(size_t)r * w.ntot + i] = v;
+        w.V[(size_t)i * NB + r] = v;
+    }
+}
+
+// T (128 x 128, upper triangular, row-major) of H_p0 ... H_p0+127 = I - V T V^T from the Gram matrix S = V^T V
+// (LAPACK dlarft, forward / columnwise): T[j][j] = tau_j, T[0:j, j] = -tau_j T[0:j, 0:j] S[0:j, j].  Thread i owns row i.
+__global__ void __launch_bounds__(128) k_wy_tfactor(WyBatch wb, int p0) {
+    extern __shared__ double Tsm[];  // [NB][NB + 1]
+    const WySys& w = wb.s[blockIdx.x];
+    if (!w.active) return;
+    const int tid = threadIdx.x;
+    auto Ts = [&](int r, int c) -> double& { return Tsm[r * (NB + 1) + c]; };
+    for (int c = 0; c < NB; c++) Ts(tid, c) = 0.0;
+    for (int j = 0; j < NB; j++) {
+        const int k = p0 + j;
+        const double tj = (k < w.n - 2) ? w.tau[k] : 0.0;
+        if (tid < j) {
+            double acc = 0.0;
+            for (int l = tid; l < j; l++) acc += Ts(tid, l) * w.S[(size_t)l * NB + j];
+            Ts(tid, j) = -tj * acc;
+        }
+        if (tid == j) Ts(j, j) = tj;
+    }
+    for (int c = 0; c < NB; c++) w.T[(size_t)tid * NB + c] = Ts(tid, c);
+}
+
+// Zt rows n .. ntot-1 = unit vectors, columns n .. of the real rows = 0 (the identity padding of the caller)
+__global__ void k_pad_vectors(double* __restrict__ Zt, int ldz, int n, int ntot) {
+    const int r = blockIdx.y;
+    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < ntot; c += gridDim.x * blockDim.x) {
+        if (r >= n)
+            Zt[(size_t)r * ldz + c] = (r == c) ? 1.0 : 0.0;
+        else if (c >= n)
+            Zt[(size_t)r * ldz + c] = 0.0;
+    }
+}
+
+}  // namespace
+
+// Tridiagonalisation of every problem (debug / test entry as well): d, e, tau are device arrays of n doubles.
+static int tridiagonalise(const TriBatch& bt, int nsys, int nmax, cudaStream_t st) {
+    for (int k = 0; k < nmax; k++) {
+        k_tri_reflect<<<nsys, 256, 0, st>>>(bt, k);
+        if (k < nmax - 2) {
+            const int rows = nmax - k - 1;
+            int gx = (rows + 7) / 8;
+            if (gx > 4 * 148) gx = 4 * 148;
+            k_tri_update<<<dim3(gx, nsys), 256, 0, st>>>(bt, k);
+        }
+    }
+    B200_LAUNCHED(2 * nmax);
+    B200_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// B200_EIGH_TIMING=1: wall time of each stage (synchronises the stream; experiments only)
+struct StageTimer {
+    cudaStream_t st;
+    bool on;
+    cudaEvent_t a, b;
+    explicit StageTimer(cudaStream_t s) : st(s), on(getenv("B200_EIGH_TIMING") != nullptr) {
+        if (on) {
+            cudaEventCreate(&a);
+            cudaEventCreate(&b);
+            cudaEventRecord(a, st);
+        }
+    }
+    void lap(const char* what) {
+        if (!on) return;
+        cudaEventRecord(b, st);
+        cudaEventSynchronize(b);
+        float ms = 0;
+        cudaEventElapsedTime(&ms, a, b);
+        fprintf(stderr, "  eigh stage %-22s %8.2f ms\n", what, ms);
+        cudaEventRecord(a, st);
+    }
+    ~StageTimer() {
+        if (on) {
+            cudaEventDestroy(a);
+            cudaEventDestroy(b);
+        }
+    }
+};
+
+int launch_tri_eigh_batch(const EighProblem* pr, int nsys, cudaStream_t st) {
+    if (nsys <= 0) return 0;
+    B200_REQUIRE(nsys <= MAXB, "at most MAXB eigenproblems per batched call");
+    int nmax = 0, ntot_max = 0;
+    for (int q = 0; q < nsys; q++) {
+        const int ntot = (pr[q].n + NB - 1) / NB * NB;
+        B200_REQUIRE(pr[q].n > 0 && pr[q].lda >= ntot && pr[q].ldv >= ntot && pr[q].lda % 2 == 0 && pr[q].ldv % 2 == 0,
+                     "eigh: A and Vt must be padded to a multiple of 128 rows / columns, even leading dimensions");
+        nmax = pr[q].n > nmax ? pr[q].n : nmax;
+        ntot_max = ntot > ntot_max ? ntot : ntot_max;
+    }
+    prof_begin(PROF_EIGH, st);
+    StageTimer tm(st);
+    // ---- scratch: vectors of the tridiagonalisation, inverse-iteration arrays, WY panels, Gram matrices ----
+    void* ws = nullptr;
+    const size_t per_vec = 8 * (size_t)nmax;
+    if (int rc = scratch(9, sizeof(double) * per_vec * nsys + sizeof(double*) * MAXB + 256, &ws)) return rc;
+    double* vec = static_cast<double*>(ws);
+    double** lam_ptrs = reinterpret_cast<double**>(vec + per_vec * nsys);
+    TriBatch bt;
+    double* h_lam[MAXB];
+    for (int q = 0; q < nsys; q++) {
+        TriSys& s = bt.s[q];
+        double* b = vec + per_vec * q;
+        s.A = pr[q].A;
+        s.lda = pr[q].lda;
+        s.n = pr[q].n;
+        s.d = b;
+        s.e = b + nmax;
+        s.tau = b + 2 * (size_t)nmax;
+        s.vbuf = b + 3 * (size_t)nmax;
+        s.wbuf = b + 5 * (size_t)nmax;
+        s.p = b + 7 * (size_t)nmax;
+        h_lam[q] = pr[q].lam;
+    }
+    for (int q = nsys; q < MAXB; q++) {
+        bt.s[q] = bt.s[0];
+        h_lam[q] = h_lam[0];
+    }
+    B200_CUDA(cudaMemcpyAsync(lam_ptrs, h_lam, sizeof(double*) * MAXB, cudaMemcpyHostToDevice, st));
+    if (int rc = tridiagonalise(bt, nsys, nmax, st)) return rc;
+    tm.lap("tridiagonalisation");
+    // ---- eigenvalues ----
+    {
+        const size_t smem = sizeof(double) * 2 * (size_t)nmax;
+        B200_REQUIRE(smem <= 200 * 1024, "eigh: matrix too large for the bisection kernel's shared memory");
+        static bool attr = false;
+        if (!attr) {
+            B200_CUDA(cudaFuncSetAttribute(k_tri_bisect, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            attr = true;
+        }
+        k_tri_bisect<<<dim3((nmax + 255) / 256, nsys), 256, smem, st>>>(bt, lam_ptrs);
+        B200_LAUNCH_CHECK();
+    }
+    tm.lap("bisection");
+    // ---- eigenvectors of T (rows of Vt) ----
+    {
+        void* is = nullptr;
+        const int nthr = (nmax + 127) / 128 * 128;
+        const size_t per = 4 * (size_t)nmax * nthr;
+        if (int rc = scratch(10, sizeof(double) * per * nsys + (size_t)nmax * nthr * nsys + 256, &is)) return rc;
+        double* base = static_cast<double*>(is);
+        unsigned char* pbase = reinterpret_cast<unsigned char*>(base + per * nsys);
+        InvitBatch ib;
+        for (int q = 0; q < nsys; q++) {
+            ib.s[q] = InvitSys{bt.s[q].d, bt.s[q].e, pr[q].lam, pr[q].Vt, base + per * q,
+                               pbase + (size_t)nmax * nthr * q, pr[q].n, pr[q].ldv, nthr};
+        }
+        for (int q = nsys; q < MAXB; q++) ib.s[q] = ib.s[0];
+        k_tri_invit<<<dim3(nthr / 128, nsys), 128, 0, st>>>(ib);
+        B200_LAUNCH_CHECK();
+    }
+    tm.lap("inverse iteration");
+    for (int q = 0; q < nsys; q++) {
+        const int ntot = (pr[q].n + NB - 1) / NB * NB;
+        k_pad_vectors<<<dim3((ntot + 255) / 256, ntot), 256, 0, st>>>(pr[q].Vt, pr[q].ldv, pr[q].n, ntot);
+        B200_LAUNCHED(1);
+    }
+    B200_CUDA(cudaGetLastError());
+    // ---- two rounds of Cholesky-QR on the rows of Vt:  G = Z Z^T = L L^T,  Z <- L^-1 Z ----
+    {
+        void* gs = nullptr;
+        const size_t per = 2 * (size_t)ntot_max * ntot_max + 2 * (size_t)(ntot_max / NB) * NB * NB;
+        if (int rc = scratch(11, sizeof(double) * per * nsys + sizeof(int) * MAXB + 256, &gs)) return rc;
+        double* gb = static_cast<double*>(gs);
+        int* info = reinterpret_cast<int*>(gb + per * nsys);
+        for (int round = 0; round < 2; round++) {
+            SolveSys sys[MAXB];
+            GemmProb gram[MAXB];
+            B200_CUDA(cudaMemsetAsync(info, 0, sizeof(int) * MAXB, st));
+            for (int q = 0; q < nsys; q++) {
+                const int ntot = (pr[q].n + NB - 1) / NB * NB;
+                double* G = gb + per * q;
+                double* Xt = G + (size_t)ntot_max * ntot_max;  // Z^T (components x vectors)
+                double* Dinv = Xt + (size_t)ntot_max * ntot_max;
+                gram[q] = GemmProb{pr[q].Vt, pr[q].Vt, G, pr[q].ldv, pr[q].ldv, ntot, ntot, ntot, ntot};
+                if (int rc = launch_transpose(pr[q].Vt, pr[q].ldv, Xt, ntot, ntot, ntot, st)) return rc;
+                SolveSys& s = sys[q];
+                s.W = G;
+                s.X = Xt;
+                s.Dinv = Dinv;
+                s.info = info + q;
+                s.npad = ntot;
+                s.mpad = ntot;
+                s.ldw = ntot;
+                s.ldx = ntot;
+                s.mrows = 0;
+                s.pad_ = 0;
+                s.work = nullptr;
+                s.work_bytes = 0;
+            }
+            if (int rc = launch_gemm_nt_batch(gram, nsys, 0, st)) return rc;
+            if (int rc = launch_chol_solve(sys, nsys, 1, 2, st)) return rc;  // factor + FORWARD solve only: X <- X L^-T
+            for (int q = 0; q < nsys; q++) {
+                const int ntot = (pr[q].n + NB - 1) / NB * NB;
+                double* Xt = gb + per * q + (size_t)ntot_max * ntot_max;
+                if (int rc = launch_transpose(Xt, ntot, pr[q].Vt, pr[q].ldv, ntot, ntot, st)) return rc;
+            }
+        }
+    }
+    tm.lap("Cholesky-QR x 2");
+    // ---- back-transformation: rows of Vt <- eigenvectors of A;  Z <- (I - V T V^T) Z panel by panel, last panel first,
+    // every launch over all systems ----
+    {
+        static bool attr2 = false;
+        if (!attr2) {
+            B200_CUDA(cudaFuncSetAttribute(k_wy_tfactor, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)(sizeof(double) * NB * (NB + 1))));
+            attr2 = true;
+        }
+        void* wsy = nullptr;
+        const size_t per = 2 * (size_t)NB * ntot_max + 2 * (size_t)NB * NB + 2 * (size_t)ntot_max * NB;
+        if (int rc = scratch(12, sizeof(double) * per * nsys, &wsy)) return rc;
+        WyBatch wb;
+        double *Wt[MAXB], *Yt[MAXB];
+        int npanel_max = 0;
+        for (int q = 0; q < nsys; q++) {
+            const int n = pr[q].n, ntot = (n + NB - 1) / NB * NB;
+            double* b = static_cast<double*>(wsy) + per * q;
+            WySys& w = wb.s[q];
+            w.A = bt.s[q].A;
+            w.tau = bt.s[q].tau;
+            w.lda = bt.s[q].lda;
+            w.n = n;
+            w.ntot = ntot;
+            w.Vt = b;                              // (128, ntot)
+            w.V = w.Vt + (size_t)NB * ntot_max;    // (ntot, 128)
+            w.S = w.V + (size_t)ntot_max * NB;     // (128, 128)
+            w.T = w.S + (size_t)NB * NB;           // (128, 128)
+            Wt[q] = w.T + (size_t)NB * NB;         // (ntot, 128)
+            Yt[q] = Wt[q] + (size_t)ntot_max * NB; // (ntot, 128)
+            w.active = 0;
+            const int np = n >= 3 ? (n - 2 + NB - 1) / NB : 0;
+            npanel_max = np > npanel_max ? np : npanel_max;
+        }
+        for (int q = nsys; q < MAXB; q++) {
+            wb.s[q] = wb.s[0];
+            wb.s[q].active = 0;
+        }
+        for (int pnl = npanel_max - 1; pnl >= 0; pnl--) {
+            const int p0 = pnl * NB;
+            GemmProb gS[MAXB], gW[MAXB], gY[MAXB], gZ[MAXB];
+            int na = 0;
+            for (int q = 0; q < nsys; q++) {
+                WySys& w = wb.s[q];
+                w.active = (w.n >= 3 && p0 < w.n - 2) ? 1 : 0;
+                if (!w.active) continue;
+                const int ntot = w.ntot;
+                gS[na] = GemmProb{w.Vt, w.Vt, w.S, ntot, ntot, NB, NB, NB, ntot};          // S = V^T V
+                gW[na] = GemmProb{pr[q].Vt, w.Vt, Wt[q], pr[q].ldv, ntot, NB, ntot, NB, ntot};  // Wt = Zt V
+                gY[na] = GemmProb{Wt[q], w.T, Yt[q], NB, NB, NB, ntot, NB, NB};            // Yt = Wt T^T
+                gZ[na] = GemmProb{Yt[q], w.V, pr[q].Vt, NB, NB, pr[q].ldv, ntot, ntot, NB};  // Zt -= Yt V^T
+                na++;
+            }
+            if (na == 0) continue;
+            k_wy_extract<<<dim3((ntot_max + 255) / 256, NB, nsys), 256, 0, st>>>(wb, p0);
+            B200_LAUNCHED(1);
+            if (int rc = launch_gemm_nt_batch(gS, na, 0, st)) return rc;
+            k_wy_tfactor<<<nsys, NB, sizeof(double) * NB * (NB + 1), st>>>(wb, p0);
+            B200_LAUNCHED(1);
+            if (int rc = launch_gemm_nt_batch(gW, na, 0, st)) return rc;
+            if (int rc = launch_gemm_nt_batch(gY, na, 0, st)) return rc;
+            if (int rc = launch_gemm_nt_batch(gZ, na, -1, st)) return rc;
+        }
+        B200_CUDA(cudaGetLastError());
+    }
+    tm.lap("back-transformation");
+    prof_end(0.0, st);
+    return 0;
+}
+
+// Householder tridiagonalisation alone (tests): A (n x n, lda) is overwritten by the reflectors, d / e / tau receive
+// T's diagonal, sub-diagonal and the reflector scales (device arrays of n doubles).
+int launch_tridiag(double* A, int lda, int n, double* d, double* e, double* tau, cudaStream_t st) {
+    if (n <= 0) return 0;
+    void* ws = nullptr;
+    if (int rc = scratch(9, sizeof(double) * 8 * (size_t)n + 1024, &ws)) return rc;
+    double* b = static_cast<double*>(ws);
+    TriBatch bt;
+    TriSys& s = bt.s[0];
+    s.A = A;
+    s.lda = lda;
+    s.n = n;
+    s.d = d;
+    s.e = e;
+    s.tau = tau;
+    s.vbuf = b;
+    s.wbuf = b + 2 * (size_t)n;
+    s.p = b + 4 * (size_t)n;
+    for (int q = 1; q < MAXB; q++) bt.s[q] = bt.s[0];
+    return tridiagonalise(bt, 1, n, st);
+}
+
+}  // namespace b200

@@ -310,7 +310,7 @@ def test_eigh_device():
     assert np.abs(np.sort(lam) - np.linalg.eigvalsh(A)).max() < 5e-13
     assert np.abs(V.T @ V - np.eye(n)).max() < 1e-12
     assert np.abs(A @ V - V * lam).max() < 5e-13
-    assert 0 < sweeps < 40
+    assert 0 <= sweeps < 40  # (0: the tridiagonalisation-based solver; the Jacobi solver counts its sweeps)
 
 
 # ---------------------------------------------------------------------------------------------------
