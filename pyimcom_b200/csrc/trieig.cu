@@ -223,7 +223,7 @@ struct InvitSys {
     const double* e;
     const double* lam;
     double* Zt;       // (ntot, ldz): row j <- eigenvector j of T
-    double* scratch;  // 4 * n * nthr doubles: u0, u1, u2, x
+    double* scratch;  // 5 * n * nthr doubles: u0, u1, u2, multipliers, x  (element i of thread j at [i * nthr + j])
     unsigned char* piv;  // n * nthr
     int n, ldz, nthr;
 };
@@ -231,7 +231,19 @@ struct InvitBatch {
     InvitSys s[MAXB];
 };
 
-__global__ void __launch_bounds__(128) k_tri_invit(InvitBatch bt) {
+// One step of inverse iteration per eigenvalue, one thread per eigenvalue, every eigenvalue independently.
+// stage 0: factor T - shift_j I = P L U (partial pivoting; the factors stay in the scratch arrays), solve from a
+//          pseudo-random start;  stage 1: solve again from row j of Zt (the orthonormalised vectors of stage 0).
+//
+// Shifts.  Bisection delivers every eigenvalue to the last bit, and the graded matrices of this path determine their
+// small eigenvalues to high RELATIVE accuracy: neighbours whose gap is far below ulp(|T|) are still resolved, and a
+// shift equal to the computed eigenvalue sits next to its own eigenvalue.  (Spreading the shifts of close eigenvalues
+// by multiples of ulp(|T|), as a first version did, moves them next to OTHER eigenvalues: several threads then converge
+// to the same vector and the Gram matrix of the orthogonalisation stage is singular - seen on the paper-4 stamp, whose
+// 3000 eigenvalues inside +-1.5e-11 |T| have gaps of 0.3 - 3 ulp(|T|).)  Only eigenvalues that agree to a few ulps of
+// THEMSELVES are pushed apart, by that amount (dstein's rule), so that no two threads factor the same matrix; such
+// a pair is numerically degenerate and the two solves return generic vectors of its invariant subspace.
+__global__ void __launch_bounds__(128) k_tri_invit(InvitBatch bt, int stage) {
     const InvitSys& s = bt.s[blockIdx.y];
     const int n = s.n, j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= n) return;
@@ -239,94 +251,107 @@ __global__ void __launch_bounds__(128) k_tri_invit(InvitBatch bt) {
     double* u0 = s.scratch + j;
     double* u1 = u0 + (size_t)n * st;
     double* u2 = u1 + (size_t)n * st;
-    double* x = u2 + (size_t)n * st;
+    double* mm = u2 + (size_t)n * st;
+    double* x = mm + (size_t)n * st;
     unsigned char* pv = s.piv + j;
-    // shift: neighbouring eigenvalues closer than a few ulps of |T| are pushed apart (dstein does the same), so that no
-    // two threads factor the same matrix
-    double tn = 0.0;
-    tn = fmax(fabs(s.lam[0]), fabs(s.lam[n - 1]));
-    const double sep = 10.0 * 2.220446049250313e-16 * fmax(tn, 1e-300);
-    double xs = s.lam[j];
-    {
-        // distance to the start of a run of too-close eigenvalues below j
-        int back = 0;
-        while (j - back - 1 >= 0 && s.lam[j - back] - s.lam[j - back - 1] < sep && back < 4096) back++;
-        if (back > 0) xs = s.lam[j - back] + back * sep;
-    }
-    const double tiny = 2.220446049250313e-16 * fmax(tn, 1e-300);
-    // ---- factorisation (row i of the working pair is (a, b, c) = (diag, super1, super2)) ----
-    double a = s.d[0] - xs, b = n > 1 ? s.e[0] : 0.0, c = 0.0;
-    for (int i = 0; i < n - 1; i++) {
-        const double sub = s.e[i];                                  // element (i+1, i)
-        const double dn = s.d[i + 1] - xs, en = i + 2 < n ? s.e[i + 1] : 0.0;  // row i+1: (dn, en)
-        double m;
-        if (fabs(a) >= fabs(sub)) {  // no interchange
-            if (a == 0.0) a = tiny;
-            m = sub / a;
-            u0[i * st] = a;
-            u1[i * st] = b;
-            u2[i * st] = c;
-            pv[i * st] = 0;
-            x[i * st] = m;  // multiplier parked in x until the solves start (x is rebuilt below)
-            a = dn - m * b;
-            b = en - m * c;
-            c = 0.0;
-        } else {  // rows i and i+1 swap
-            m = a / sub;
-            u0[i * st] = sub;
-            u1[i * st] = dn;
-            u2[i * st] = en;
-            pv[i * st] = 1;
-            x[i * st] = m;
-            a = b - m * dn;
-            b = c - m * en;
-            c = 0.0;
+    double* zrow = s.Zt + (size_t)j * s.ldz;
+    const double eps = 2.220446049250313e-16;
+    const double tn = fmax(fmax(fabs(s.lam[0]), fabs(s.lam[n - 1])), 1e-300);
+    if (stage == 0) {
+        const double floor_ = 1e-290;  // (denormal eigenvalues: push by something representable)
+        double xs = s.lam[j];
+        {
+            const double sep = 8.0 * eps * fmax(fabs(xs), floor_);
+            int back = 0;
+            while (j - back - 1 >= 0 && s.lam[j - back] - s.lam[j - back - 1] < sep && back < 4096) back++;
+            if (back > 0) xs = s.lam[j - back] + back * sep;
         }
-    }
-    if (a == 0.0) a = tiny;
-    u0[(size_t)(n - 1) * st] = a;
-    u1[(size_t)(n - 1) * st] = 0.0;
-    u2[(size_t)(n - 1) * st] = 0.0;
-    double* zrow = s.Zt + (size_t)j * s.ldz;  // (own row: used as the multiplier store during the solves)
-    for (int i = 0; i < n - 1; i++) zrow[i] = x[i * st];
-    // ---- three solves ----
-    for (int it = 0; it < 3; it++) {
-        // right-hand side: pseudo-random start, then the previous (normalised) iterate
-        if (it == 0)
-            for (int i = 0; i < n; i++) x[i * st] = hash_unit((unsigned)j, (unsigned)i);
-        // forward: apply P and L
+        const double tiny = eps * tn;
+        // ---- factorisation (row i of the working pair is (a, b, c) = (diag, super1, super2)) ----
+        double a = s.d[0] - xs, b = n > 1 ? s.e[0] : 0.0, c = 0.0;
         for (int i = 0; i < n - 1; i++) {
-            const double m = zrow[i];
-            double xi = x[i * st], xn = x[(size_t)(i + 1) * st];
-            if (pv[i * st]) {
-                const double t = xi;
-                xi = xn;
-                xn = t - m * xi;
-            } else {
-                xn -= m * xi;
+            const double sub = s.e[i];                                  // element (i+1, i)
+            const double dn = s.d[i + 1] - xs, en = i + 2 < n ? s.e[i + 1] : 0.0;  // row i+1: (dn, en)
+            double m;
+            if (fabs(a) >= fabs(sub)) {  // no interchange
+                if (a == 0.0) a = tiny;
+                m = sub / a;
+                u0[i * st] = a;
+                u1[i * st] = b;
+                u2[i * st] = c;
+                pv[i * st] = 0;
+                a = dn - m * b;
+                b = en - m * c;
+                c = 0.0;
+            } else {  // rows i and i+1 swap
+                m = a / sub;
+                u0[i * st] = sub;
+                u1[i * st] = dn;
+                u2[i * st] = en;
+                pv[i * st] = 1;
+                a = b - m * dn;
+                b = c - m * en;
+                c = 0.0;
             }
-            x[i * st] = xi;
-            x[(size_t)(i + 1) * st] = xn;
+            mm[i * st] = m;
         }
-        // backward with U
-        double x1 = 0.0, x2 = 0.0, nrm2 = 0.0, big = 0.0;
-        for (int i = n - 1; i >= 0; i--) {
-            double v = (x[i * st] - u1[i * st] * x1 - u2[i * st] * x2) / u0[i * st];
-            x[i * st] = v;
-            x2 = x1;
-            x1 = v;
-            big = fmax(big, fabs(v));
-        }
-        // normalise (scaled to avoid overflow)
-        const double sc = big > 0.0 ? 1.0 / big : 1.0;
-        for (int i = 0; i < n; i++) {
-            const double v = x[i * st] * sc;
-            nrm2 += v * v;
-        }
-        const double inv = sc / sqrt(fmax(nrm2, 1e-300));
-        for (int i = 0; i < n; i++) x[i * st] *= inv;
+        if (a == 0.0) a = tiny;
+        u0[(size_t)(n - 1) * st] = a;
+        u1[(size_t)(n - 1) * st] = 0.0;
+        u2[(size_t)(n - 1) * st] = 0.0;
+        pv[(size_t)(n - 1) * st] = 0;
+        for (int i = 0; i < n; i++) x[i * st] = hash_unit((unsigned)j, (unsigned)i);
+    } else {
+        for (int i = 0; i < n; i++) x[i * st] = zrow[i];
     }
-    for (int i = 0; i < n; i++) zrow[i] = x[i * st];
+    // ---- forward: apply P and L ----
+    for (int i = 0; i < n - 1; i++) {
+        const double m = mm[i * st];
+        double xi = x[i * st], xn = x[(size_t)(i + 1) * st];
+        if (pv[i * st] & 1) {
+            const double t = xi;
+            xi = xn;
+            xn = t - m * xi;
+        } else {
+            xn -= m * xi;
+        }
+        x[i * st] = xi;
+        x[(size_t)(i + 1) * st] = xn;
+    }
+    // ---- backward with U.  An eigenvector of a graded tridiagonal matrix is localised and decays by hundreds of decades
+    // away from its centre, so the substitution can grow past the float64 range on its way in: whenever an entry
+    // passes 1e150 everything (entries already computed and the rest of the right-hand side) is scaled by 1e-150.
+    // The entries already stored are not revisited: each carries the number of rescalings that preceded it (bits
+    // 1-7 of its pivot byte) and is brought to the final scale in the normalisation pass (dstein rescales likewise).
+    double x1 = 0.0, x2 = 0.0, big = 0.0, rs = 1.0;
+    int epoch = 0;
+    for (int i = n - 1; i >= 0; i--) {
+        double v = (x[i * st] * rs - u1[i * st] * x1 - u2[i * st] * x2) / u0[i * st];
+        if (fabs(v) > 1e150 && epoch < 127) {
+            v *= 1e-150;
+            x1 *= 1e-150;
+            big *= 1e-150;
+            rs *= 1e-150;
+            epoch++;
+        }
+        x[i * st] = v;
+        pv[i * st] = (unsigned char)((pv[i * st] & 1) | (epoch << 1));
+        x2 = x1;
+        x1 = v;
+        big = fmax(big, fabs(v));
+    }
+    // ---- normalise (scaled by the largest entry first, so that the squares neither overflow nor all underflow) ----
+    const double sc = big > 0.0 ? 1.0 / big : 1.0;
+    double nrm2 = 0.0;
+    for (int i = 0; i < n; i++) {
+        const int behind = epoch - (pv[i * st] >> 1);
+        const double f = behind == 0 ? 1.0 : (behind == 1 ? 1e-150 : 0.0);
+        const double v = x[i * st] * f * sc;
+        x[i * st] = v;
+        nrm2 += v * v;
+    }
+    const double inv = 1.0 / sqrt(fmax(nrm2, 1e-300));
+    for (int i = 0; i < n; i++) zrow[i] = x[i * st] * inv;
 }
 
 // ---- compact-WY panels of the reflectors ------------------------------------------------------------------------
@@ -434,6 +459,8 @@ struct StageTimer {
     }
 };
 
+constexpr int QR_ROUNDS = 3;
+
 int launch_tri_eigh_batch(const EighProblem* pr, int nsys, cudaStream_t st) {
     if (nsys <= 0) return 0;
     B200_REQUIRE(nsys <= MAXB, "at most MAXB eigenproblems per batched call");
@@ -447,6 +474,7 @@ int launch_tri_eigh_batch(const EighProblem* pr, int nsys, cudaStream_t st) {
     }
     prof_begin(PROF_EIGH, st);
     StageTimer tm(st);
+    int* qr_info = nullptr;
     // ---- scratch: vectors of the tridiagonalisation, inverse-iteration arrays, WY panels, Gram matrices ----
     void* ws = nullptr;
     const size_t per_vec = 8 * (size_t)nmax;
@@ -489,71 +517,78 @@ int launch_tri_eigh_batch(const EighProblem* pr, int nsys, cudaStream_t st) {
         B200_LAUNCH_CHECK();
     }
     tm.lap("bisection");
-    // ---- eigenvectors of T (rows of Vt) ----
+    // ---- eigenvectors of T (rows of Vt): solve, orthonormalise, solve again from the orthonormal vectors, orthonormalise
+    // twice.  Orthonormalisation = Cholesky-QR on the rows of Vt:  G = Z Z^T = L L^T,  Z <- L^-1 Z ----
+    InvitBatch ib;
+    const int nthr = (nmax + 127) / 128 * 128;
     {
         void* is = nullptr;
-        const int nthr = (nmax + 127) / 128 * 128;
-        const size_t per = 4 * (size_t)nmax * nthr;
+        const size_t per = 5 * (size_t)nmax * nthr;
         if (int rc = scratch(10, sizeof(double) * per * nsys + (size_t)nmax * nthr * nsys + 256, &is)) return rc;
         double* base = static_cast<double*>(is);
         unsigned char* pbase = reinterpret_cast<unsigned char*>(base + per * nsys);
-        InvitBatch ib;
         for (int q = 0; q < nsys; q++) {
             ib.s[q] = InvitSys{bt.s[q].d, bt.s[q].e, pr[q].lam, pr[q].Vt, base + per * q,
                                pbase + (size_t)nmax * nthr * q, pr[q].n, pr[q].ldv, nthr};
         }
         for (int q = nsys; q < MAXB; q++) ib.s[q] = ib.s[0];
-        k_tri_invit<<<dim3(nthr / 128, nsys), 128, 0, st>>>(ib);
-        B200_LAUNCH_CHECK();
     }
-    tm.lap("inverse iteration");
+    void* gs = nullptr;
+    const size_t per_g = 2 * (size_t)ntot_max * ntot_max + 2 * (size_t)(ntot_max / NB) * NB * NB;
+    if (int rc = scratch(11, sizeof(double) * per_g * nsys + sizeof(int) * QR_ROUNDS * MAXB + 256, &gs)) return rc;
+    double* gb = static_cast<double*>(gs);
+    qr_info = reinterpret_cast<int*>(gb + per_g * nsys);
+    B200_CUDA(cudaMemsetAsync(qr_info, 0, sizeof(int) * QR_ROUNDS * MAXB, st));
+    auto cholqr = [&](int round) -> int {
+        SolveSys sys[MAXB];
+        GemmProb gram[MAXB];
+        int* info = qr_info + round * MAXB;
+        for (int q = 0; q < nsys; q++) {
+            const int ntot = (pr[q].n + NB - 1) / NB * NB;
+            double* G = gb + per_g * q;
+            double* Xt = G + (size_t)ntot_max * ntot_max;  // Z^T (components x vectors)
+            double* Dinv = Xt + (size_t)ntot_max * ntot_max;
+            gram[q] = GemmProb{pr[q].Vt, pr[q].Vt, G, pr[q].ldv, pr[q].ldv, ntot, ntot, ntot, ntot};
+            if (int rc = launch_transpose(pr[q].Vt, pr[q].ldv, Xt, ntot, ntot, ntot, st)) return rc;
+            SolveSys& s = sys[q];
+            s.W = G;
+            s.X = Xt;
+            s.Dinv = Dinv;
+            s.info = info + q;
+            s.npad = ntot;
+            s.mpad = ntot;
+            s.ldw = ntot;
+            s.ldx = ntot;
+            s.mrows = 0;
+            s.pad_ = 0;
+            s.work = nullptr;
+            s.work_bytes = 0;
+        }
+        if (int rc = launch_gemm_nt_batch(gram, nsys, 0, st)) return rc;
+        if (int rc = launch_chol_solve(sys, nsys, 1, 2, st)) return rc;  // factor + FORWARD solve only: X <- X L^-T
+        for (int q = 0; q < nsys; q++) {
+            const int ntot = (pr[q].n + NB - 1) / NB * NB;
+            double* Xt = gb + per_g * q + (size_t)ntot_max * ntot_max;
+            if (int rc = launch_transpose(Xt, ntot, pr[q].Vt, pr[q].ldv, ntot, ntot, st)) return rc;
+        }
+        return 0;
+    };
+    k_tri_invit<<<dim3(nthr / 128, nsys), 128, 0, st>>>(ib, 0);
+    B200_LAUNCH_CHECK();
     for (int q = 0; q < nsys; q++) {
         const int ntot = (pr[q].n + NB - 1) / NB * NB;
         k_pad_vectors<<<dim3((ntot + 255) / 256, ntot), 256, 0, st>>>(pr[q].Vt, pr[q].ldv, pr[q].n, ntot);
         B200_LAUNCHED(1);
     }
     B200_CUDA(cudaGetLastError());
-    // ---- two rounds of Cholesky-QR on the rows of Vt:  G = Z Z^T = L L^T,  Z <- L^-1 Z ----
-    {
-        void* gs = nullptr;
-        const size_t per = 2 * (size_t)ntot_max * ntot_max + 2 * (size_t)(ntot_max / NB) * NB * NB;
-        if (int rc = scratch(11, sizeof(double) * per * nsys + sizeof(int) * MAXB + 256, &gs)) return rc;
-        double* gb = static_cast<double*>(gs);
-        int* info = reinterpret_cast<int*>(gb + per * nsys);
-        for (int round = 0; round < 2; round++) {
-            SolveSys sys[MAXB];
-            GemmProb gram[MAXB];
-            B200_CUDA(cudaMemsetAsync(info, 0, sizeof(int) * MAXB, st));
-            for (int q = 0; q < nsys; q++) {
-                const int ntot = (pr[q].n + NB - 1) / NB * NB;
-                double* G = gb + per * q;
-                double* Xt = G + (size_t)ntot_max * ntot_max;  // Z^T (components x vectors)
-                double* Dinv = Xt + (size_t)ntot_max * ntot_max;
-                gram[q] = GemmProb{pr[q].Vt, pr[q].Vt, G, pr[q].ldv, pr[q].ldv, ntot, ntot, ntot, ntot};
-                if (int rc = launch_transpose(pr[q].Vt, pr[q].ldv, Xt, ntot, ntot, ntot, st)) return rc;
-                SolveSys& s = sys[q];
-                s.W = G;
-                s.X = Xt;
-                s.Dinv = Dinv;
-                s.info = info + q;
-                s.npad = ntot;
-                s.mpad = ntot;
-                s.ldw = ntot;
-                s.ldx = ntot;
-                s.mrows = 0;
-                s.pad_ = 0;
-                s.work = nullptr;
-                s.work_bytes = 0;
-            }
-            if (int rc = launch_gemm_nt_batch(gram, nsys, 0, st)) return rc;
-            if (int rc = launch_chol_solve(sys, nsys, 1, 2, st)) return rc;  // factor + FORWARD solve only: X <- X L^-T
-            for (int q = 0; q < nsys; q++) {
-                const int ntot = (pr[q].n + NB - 1) / NB * NB;
-                double* Xt = gb + per * q + (size_t)ntot_max * ntot_max;
-                if (int rc = launch_transpose(Xt, ntot, pr[q].Vt, pr[q].ldv, ntot, ntot, st)) return rc;
-            }
-        }
-    }
+    tm.lap("inverse iteration 1");
+    if (int rc = cholqr(0)) return rc;
+    tm.lap("Cholesky-QR");
+    k_tri_invit<<<dim3(nthr / 128, nsys), 128, 0, st>>>(ib, 1);
+    B200_LAUNCH_CHECK();
+    tm.lap("inverse iteration 2");
+    if (int rc = cholqr(1)) return rc;
+    if (int rc = cholqr(2)) return rc;
     tm.lap("Cholesky-QR x 2");
     // ---- back-transformation: rows of Vt <- eigenvectors of A;  Z <- (I - V T V^T) Z panel by panel, last panel first,
     // every launch over all systems ----
@@ -622,6 +657,15 @@ int launch_tri_eigh_batch(const EighProblem* pr, int nsys, cudaStream_t st) {
     }
     tm.lap("back-transformation");
     prof_end(0.0, st);
+    // The Gram matrices of both Cholesky-QR rounds must have been positive definite: a failed factorisation means the
+    // inverse-iteration vectors were linearly dependent, and everything after it is garbage.  Fail loudly.
+    int h_info[QR_ROUNDS * MAXB];
+    B200_CUDA(cudaMemcpyAsync(h_info, qr_info, sizeof(h_info), cudaMemcpyDeviceToHost, st));
+    B200_CUDA(cudaStreamSynchronize(st));
+    for (int q = 0; q < nsys; q++)
+        B200_REQUIRE(h_info[q] == 0 && h_info[MAXB + q] == 0 && h_info[2 * MAXB + q] == 0,
+                     "eigh: Cholesky-QR of the inverse-iteration vectors failed (linearly dependent vectors); "
+                     "B200_EIGH=jacobi selects the Jacobi solver");
     return 0;
 }
 

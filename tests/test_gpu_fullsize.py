@@ -196,6 +196,29 @@ def test_full_size_vs_reference_golden(name):
         assert np.abs(np.log(kg / kr)).max() < 0.25 * np.log(step)
 
 
+def test_eigen_kernel_at_paper4_size_equals_the_reference_cholesky_golden():
+    """EigenKernel at the paper-4 stamp size (n = 6248): with a single kappa node, T = (-B/2 Q) diag(1/(lam + kappa)) Q^T
+    (lakernel.py:174-223) solves the same system as CholKernel, so the reference-made CholKernel golden of this stamp
+    pins it.  The eigendecomposition of a 6248 x 6248 matrix takes NumPy ~1 min on 16 cores; the device solver
+    (csrc/trieig.cu) is checked here through the coadded stamp."""
+    g = np.load(os.path.join(GOLDEN, "full_p4.npz"))
+    spec = dict(cases.FULL_CASES["p4"])
+    spec["cfg"] = dict(spec["cfg"], linear_algebra="Eigen")
+    cases.FULL_CASES["p4_eigen"] = spec
+    try:
+        s, blk = gpu_full_stamp("p4_eigen")
+    finally:
+        del cases.FULL_CASES["p4_eigen"]
+    e = cases.full_errors(s, g)
+    print("p4_eigen", {k: f"{v:.1e}" for k, v in e.items()})
+    assert e["sysmata"] < P64 and e["mhalfb"] < P64
+    # two different solvers of a system with cond ~ 1 / (kappa / C) = 1.7e3 relative to the top of the spectrum
+    assert e["T"] < 2e-5 and e["T_rowsum"] < 2e-5 and e["T_colabs"] < 2e-5
+    for nm in ("Sigma", "outimage", "Tsum_stamp", "Tsum_inpix", "Neff"):
+        assert e[nm] < 1e-4, nm
+    assert e["UC_abs"] < 1e-4
+
+
 def test_config3_inside_the_cg_spread():
     """Config 3 (IterKernel, kappa = 0, 24-30 CG iterations per output pixel).  tests/test_oracle_golden.py::
     test_cg_sensitivity shows that the reference's procedure amplifies a 1e-15 relative perturbation of A to ~1e-2 on T

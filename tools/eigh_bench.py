@@ -27,7 +27,10 @@ for setting in sys.argv[1:] or ["B200_EIGH_INNER=1"]:
         k, v = kv.split("=")
         os.environ[k] = v
     for nb in (1, 16):
-        items = [(ds.matrix().clone(), ds.n) for ds in dss[:nb]] if nb > 1 else [(dss[5].matrix().clone(), dss[5].n)]
+        mk = lambda: ([(ds.matrix().clone(), ds.n) for ds in dss[:nb]] if nb > 1  # noqa: E731
+                      else [(dss[5].matrix().clone(), dss[5].n)])
+        GL.eigh_device_batch(mk())  # warm-up: scratch allocations, kernel attributes
+        items = mk()
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()

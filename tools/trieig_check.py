@@ -58,5 +58,7 @@ def check(n, kind):
 
 if __name__ == "__main__":
     torch.cuda.set_device(0)
-    for n, kind in ((5, "random"), (130, "random"), (300, "graded"), (1000, "graded"), (1532, "graded")):
+    sizes = [(int(a), "graded") for a in sys.argv[1:]] or [(5, "random"), (130, "random"), (300, "graded"),
+                                                           (1000, "graded"), (1532, "graded")]
+    for n, kind in sizes:
         check(n, kind)
