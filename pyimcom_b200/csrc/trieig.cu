@@ -23,6 +23,7 @@
 // residual at the 1e-15 |A| level, eigenvalues to eps |A|.
 #include <math.h>
 #include <stdlib.h>
+#include <string.h>
 
 #include "common.cuh"
 #include "kernels.h"
@@ -412,10 +413,242 @@ __global__ void k_pad_vectors(double* __restrict__ Zt, int ldz, int n, int ntot)
     }
 }
 
+// ---- blocked tridiagonalisation (LAPACK dlatrd / dsytrd arrangement, rows in the role of columns) ----------------
+// Inside a panel of NBT columns the trailing matrix is NOT updated: column k is formed on the fly from the panel's
+// reflectors V and companions W (a_k = A[k, :] - V W[k, :]^T - W V[k, :]^T), the symmetric matrix-vector product only
+// READS the trailing matrix and is corrected with the same skinny products, and the 2 NBT rank-one updates of a panel
+// reach the matrix as ONE DMMA GEMM  A -= [V | W] [W | V]^T  (K = 128).  Per column the matrix is read once instead of
+// read and written once (8 n^3 / 3 instead of 16 n^3 / 3 bytes per system).  Three launches per column:
+//   k_trib_reflect (one CTA per system): finish w_{k-1} = p + alpha v (alpha from the partial dot products), column
+//                  a_k = c - 2 alpha v_{k-1}, reflector v_k (dlarfg), its copies (row k of A, VW / WV panels, vbuf);
+//   k_trib_symv    (grid-wide): y = A[k+1:, k+1:] v, one warp per row, 16-byte loads; a few extra CTAs form partial
+//                  sums of V^T v and W^T v;
+//   k_trib_p       (grid-wide, one warp per row): p_i = tau (y_i - V[i, :] (W^T v) - W[i, :] (V^T v)), the partial dot
+//                  products p . v, and the NEXT column with everything but the alpha terms: c_i = A[k+1, i] - (panel
+//                  corrections of columns < j) - (v_i p_{k+1} + p_i)  (row i of V / W is in registers already).
+constexpr int NBT = 64;      // panel width (the trailing update is a K = 2 NBT = 128 GEMM)
+constexpr int TRIB_ZC = 16;  // row chunks of the V^T v / W^T v partial sums
+constexpr int TRIB_GX = 1024;
+
+struct TribSys {
+    double* A;
+    double *d, *e, *tau;
+    double* VW;   // (ntot, 2 NBT): [V | W] of the current panel, row-major
+    double* WV;   // (ntot, 2 NBT): [W | V]
+    double *vbuf, *p, *c, *y, *abuf;  // [n]
+    double* zpart;  // [TRIB_ZC][2 NBT]
+    double* dpart;  // [TRIB_GX]
+    int lda, n, ntot;
+};
+struct TribBatch {
+    TribSys s[MAXB];
+};
+
+__global__ void __launch_bounds__(1024) k_trib_reflect(TribBatch bt, int k, int k0_prev, int k0, int finish, int reflect,
+                                                      int fresh, int ndpart) {
+    __shared__ double red[40];
+    const TribSys& s = bt.s[blockIdx.x];
+    const int n = s.n, tid = threadIdx.x;
+    double alpha = 0.0;
+    if (finish && k >= 1 && k - 1 <= n - 3) {
+        const int jp = k - 1 - k0_prev;
+        double acc = 0.0;
+        for (int i = tid; i < ndpart; i += 1024) acc += s.dpart[i];
+        acc = block_sum(acc, red);
+        alpha = -0.5 * s.tau[k - 1] * acc;
+        for (int i = k + tid; i < s.ntot; i += 1024) {  // (rows above k are dead: nobody reads them again)
+            const double w = i < n ? s.p[i] + alpha * s.vbuf[i] : 0.0;
+            s.VW[(size_t)i * (2 * NBT) + NBT + jp] = w;
+            s.WV[(size_t)i * (2 * NBT) + jp] = w;
+        }
+    }
+    if (!reflect || k > n - 3) return;
+    const int j = k - k0;
+    double* row = s.A + (size_t)k * s.lda;
+    for (int i = k + tid; i < n; i += 1024) s.abuf[i] = fresh ? row[i] : s.c[i] - 2.0 * alpha * s.vbuf[i];
+    __syncthreads();
+    double ss = 0.0;
+    for (int i = k + 2 + tid; i < n; i += 1024) ss += s.abuf[i] * s.abuf[i];
+    ss = block_sum(ss, red);
+    const double alpha0 = s.abuf[k + 1];
+    double beta = alpha0, tau = 0.0, scale = 0.0;
+    if (ss > 0.0) {
+        const double nrm = sqrt(alpha0 * alpha0 + ss);
+        beta = alpha0 >= 0.0 ? -nrm : nrm;
+        tau = (beta - alpha0) / beta;
+        scale = 1.0 / (alpha0 - beta);
+    }
+    for (int i = k + tid; i < s.ntot; i += 1024) {
+        double vi = 0.0;
+        if (i == k + 1)
+            vi = 1.0;
+        else if (i > k + 1 && i < n)
+            vi = s.abuf[i] * scale;
+        s.VW[(size_t)i * (2 * NBT) + j] = vi;
+        s.WV[(size_t)i * (2 * NBT) + NBT + j] = vi;
+        if (i < n) {
+            if (i >= k) s.vbuf[i] = vi;
+            if (i > k) row[i] = vi;  // the reflector lives in the dead row k from now on
+        }
+    }
+    if (tid == 0) {
+        s.d[k] = s.abuf[k];
+        s.e[k] = beta;
+        s.tau[k] = tau;
+    }
+}
+
+__global__ void __launch_bounds__(256) k_trib_symv(TribBatch bt, int k, int gx_rows, int zc) {
+    const TribSys& s = bt.s[blockIdx.y];
+    const int n = s.n;
+    if (k > n - 3) return;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const double* __restrict__ v = s.vbuf;
+    if ((int)blockIdx.x < gx_rows) {
+        int c0 = k + 1;
+        const bool head = c0 & 1;
+        if (head) c0++;
+        for (int i = k + 1 + blockIdx.x * 8 + warp; i < n; i += gx_rows * 8) {
+            const double* __restrict__ row = s.A + (size_t)i * s.lda;
+            double acc = (head && lane == 0) ? row[k + 1] * v[k + 1] : 0.0;
+            int c = c0 + 2 * lane;
+#pragma unroll 4
+            for (; c + 1 < n; c += 64) {
+                const double2 a = *reinterpret_cast<const double2*>(row + c);
+                const double2 b = *reinterpret_cast<const double2*>(v + c);
+                acc += a.x * b.x;
+                acc += a.y * b.y;
+            }
+            if (c < n) acc += row[c] * v[c];
+            acc = warp_sum(acc);
+            if (lane == 0) s.y[i] = acc;
+        }
+    } else {  // partial sums of [V | W]^T v over a chunk of rows: thread = (column t, row group h)
+        __shared__ double part[2][128];
+        const int chunk = blockIdx.x - gx_rows, t = threadIdx.x & 127, h = threadIdx.x >> 7;
+        const int per = (n - k - 1 + zc - 1) / zc;
+        const int i0 = k + 1 + chunk * per, i1 = min(n, i0 + per);
+        double acc = 0.0;
+#pragma unroll 4
+        for (int i = i0 + h; i < i1; i += 2) acc += s.VW[(size_t)i * (2 * NBT) + t] * v[i];
+        part[h][t] = acc;
+        __syncthreads();
+        if (h == 0) {
+            double z = 0.0;
+#pragma unroll
+            for (int q = 0; q < 2; q++) z += part[q][t];
+            s.zpart[chunk * (2 * NBT) + t] = z;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) k_trib_p(TribBatch bt, int k, int k0, int gx, int zc) {
+    __shared__ double zz[2 * NBT], rr[2 * NBT], wsum[8], pk1s;
+    const TribSys& s = bt.s[blockIdx.y];
+    const int n = s.n;
+    if (k > n - 3) return;
+    const int j = k - k0, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const double tau = s.tau[k];
+    if (tid < 2 * NBT) {
+        double z = 0.0, r = 0.0;
+        if ((tid & (NBT - 1)) < j) {
+            const int src = tid < NBT ? tid + NBT : tid - NBT;  // V columns pair with W^T v and vice versa
+#pragma unroll
+            for (int q = 0; q < TRIB_ZC; q++) z += s.zpart[q * (2 * NBT) + src];
+            r = s.WV[(size_t)(k + 1) * (2 * NBT) + tid];
+        }
+        zz[tid] = z;
+        rr[tid] = r;
+    }
+    __syncthreads();
+    if (warp == 0) {
+        const double* vw = s.VW + (size_t)(k + 1) * (2 * NBT);
+        double sp = 0.0;
+        if (j > 0) {
+#pragma unroll
+            for (int q = 0; q < 4; q++) sp += vw[lane + 32 * q] * zz[lane + 32 * q];
+            sp = warp_sum(sp);
+        }
+        if (lane == 0) pk1s = tau * (s.y[k + 1] - sp);
+    }
+    __syncthreads();
+    const double pk1 = pk1s;
+    const double* rowk1 = s.A + (size_t)(k + 1) * s.lda;
+    double dot = 0.0;
+    for (int i = k + 1 + blockIdx.x * 8 + warp; i < n; i += gx * 8) {
+        const double* vw = s.VW + (size_t)i * (2 * NBT);
+        double sp = 0.0, sc = 0.0;
+        if (j > 0) {
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                const double x = vw[lane + 32 * q];
+                sp += x * zz[lane + 32 * q];
+                sc += x * rr[lane + 32 * q];
+            }
+            sp = warp_sum(sp);
+            sc = warp_sum(sc);
+        }
+        if (lane == 0) {
+            const double pi = tau * (s.y[i] - sp), vi = s.vbuf[i];
+            s.p[i] = pi;
+            s.c[i] = rowk1[i] - sc - (vi * pk1 + pi);
+            dot += pi * vi;
+        }
+    }
+    if (lane == 0) wsum[warp] = dot;
+    __syncthreads();
+    if (tid == 0) {
+        double t = 0.0;
+        for (int q = 0; q < 8; q++) t += wsum[q];
+        s.dpart[blockIdx.x] = t;
+    }
+}
+
+// last two rows: d[n-2], e[n-2], d[n-1] from the matrix and the reflectors of the last (unfinished) panel
+__global__ void __launch_bounds__(32) k_trib_tail(TribBatch bt) {
+    const TribSys& s = bt.s[blockIdx.x];
+    const int n = s.n, lane = threadIdx.x;
+    if (n == 1) {
+        if (lane == 0) {
+            s.d[0] = s.A[0];
+            s.e[0] = 0.0;
+            s.tau[0] = 0.0;
+        }
+        return;
+    }
+    int J = 0;
+    if (n >= 3) {
+        const int kl = n - 3;
+        J = kl - (kl / NBT) * NBT + 1;
+    }
+    const double* r0 = s.VW + (size_t)(n - 2) * (2 * NBT);
+    const double* r1 = s.VW + (size_t)(n - 1) * (2 * NBT);
+    double c00 = 0.0, c01 = 0.0, c11 = 0.0;
+    for (int l = lane; l < J; l += 32) {
+        const double v0 = r0[l], w0 = r0[NBT + l], v1 = r1[l], w1 = r1[NBT + l];
+        c00 += 2.0 * v0 * w0;
+        c01 += v0 * w1 + w0 * v1;
+        c11 += 2.0 * v1 * w1;
+    }
+    c00 = warp_sum(c00);
+    c01 = warp_sum(c01);
+    c11 = warp_sum(c11);
+    if (lane == 0) {
+        const double* a0 = s.A + (size_t)(n - 2) * s.lda;
+        const double* a1 = s.A + (size_t)(n - 1) * s.lda;
+        s.d[n - 2] = a0[n - 2] - c00;
+        s.e[n - 2] = a0[n - 1] - c01;
+        s.d[n - 1] = a1[n - 1] - c11;
+        s.e[n - 1] = 0.0;
+        s.tau[n - 2] = 0.0;
+        s.tau[n - 1] = 0.0;
+    }
+}
+
 }  // namespace
 
 // Tridiagonalisation of every problem (debug / test entry as well): d, e, tau are device arrays of n doubles.
-static int tridiagonalise(const TriBatch& bt, int nsys, int nmax, cudaStream_t st) {
+static int tridiagonalise_unblocked(const TriBatch& bt, int nsys, int nmax, cudaStream_t st) {
     for (int k = 0; k < nmax; k++) {
         k_tri_reflect<<<nsys, 256, 0, st>>>(bt, k);
         if (k < nmax - 2) {
@@ -426,6 +659,86 @@ static int tridiagonalise(const TriBatch& bt, int nsys, int nmax, cudaStream_t s
         }
     }
     B200_LAUNCHED(2 * nmax);
+    B200_CUDA(cudaGetLastError());
+    return 0;
+}
+
+static int tridiagonalise(const TriBatch& bt, int nsys, int nmax, cudaStream_t st) {
+    static const bool unblocked = [] {
+        const char* e = getenv("B200_TRIDIAG");
+        return e && strcmp(e, "unblocked") == 0;
+    }();
+    if (unblocked) return tridiagonalise_unblocked(bt, nsys, nmax, st);
+    int ntot_max = 0;
+    for (int q = 0; q < nsys; q++) {
+        const int ntot = (bt.s[q].n + NB - 1) / NB * NB;
+        ntot_max = ntot > ntot_max ? ntot : ntot_max;
+    }
+    void* ws = nullptr;
+    const size_t nv = ((size_t)nmax + 1) & ~(size_t)1;  // (even: the vectors are read with 16-byte loads)
+    const size_t per = 2 * (size_t)ntot_max * (2 * NBT) + 5 * nv + TRIB_ZC * 2 * NBT + TRIB_GX + 64;
+    if (int rc = scratch(13, sizeof(double) * per * nsys, &ws)) return rc;
+    // stale panel entries are multiplied by zero masks: they must be finite
+    B200_CUDA(cudaMemsetAsync(ws, 0, sizeof(double) * per * nsys, st));
+    TribBatch tb;
+    for (int q = 0; q < nsys; q++) {
+        TribSys& t = tb.s[q];
+        double* b = static_cast<double*>(ws) + per * q;
+        t.A = bt.s[q].A;
+        t.d = bt.s[q].d;
+        t.e = bt.s[q].e;
+        t.tau = bt.s[q].tau;
+        t.lda = bt.s[q].lda;
+        t.n = bt.s[q].n;
+        t.ntot = (t.n + NB - 1) / NB * NB;
+        t.VW = b;
+        t.WV = t.VW + (size_t)ntot_max * (2 * NBT);
+        t.vbuf = t.WV + (size_t)ntot_max * (2 * NBT);
+        t.p = t.vbuf + nv;
+        t.c = t.p + nv;
+        t.y = t.c + nv;
+        t.abuf = t.y + nv;
+        t.zpart = t.abuf + nv;
+        t.dpart = t.zpart + TRIB_ZC * 2 * NBT;
+    }
+    for (int q = nsys; q < MAXB; q++) tb.s[q] = tb.s[0];
+    int launches = 0, gx_prev = 0;
+    const int klast = nmax - 3;  // last column with a reflector
+    for (int k = 0; k <= klast; k++) {
+        const int k0 = (k / NBT) * NBT, fresh = k == k0;
+        k_trib_reflect<<<nsys, 1024, 0, st>>>(tb, k, k0, k0, !fresh, 1, fresh, gx_prev);
+        const int rows = nmax - k - 1;
+        int gs = (rows + 7) / 8;  // symv: one warp per row, 8 rows per CTA
+        if (gs > TRIB_GX) gs = TRIB_GX;
+        // p: a few CTAs per SM over all systems (each pays a fixed preamble), several rows per warp
+        int gx = (rows + 7) / 8;
+        const int cap = (4 * 148 + nsys - 1) / nsys;
+        if (gx > cap) gx = cap;
+        const int zc = fresh ? 0 : TRIB_ZC;
+        k_trib_symv<<<dim3(gs + zc, nsys), 256, 0, st>>>(tb, k, gs, zc);
+        k_trib_p<<<dim3(gx, nsys), 256, 0, st>>>(tb, k, k0, gx, zc);
+        launches += 3;
+        gx_prev = gx;
+        if (k - k0 == NBT - 1 || k == klast) {  // end of the panel: finish its last w, then the trailing update
+            k_trib_reflect<<<nsys, 1024, 0, st>>>(tb, k + 1, k0, k0, 1, 0, 0, gx_prev);
+            launches++;
+            if (k < klast) {
+                const int k1 = k0 + NBT;
+                GemmProb g[MAXB];
+                int ng = 0;
+                for (int q = 0; q < nsys; q++) {
+                    const TribSys& t = tb.s[q];
+                    if (t.n - 3 < k1) continue;  // no further column: the tail kernel reads the panel directly
+                    g[ng++] = GemmProb{t.VW + (size_t)k1 * (2 * NBT), t.WV + (size_t)k1 * (2 * NBT),
+                                       t.A + (size_t)k1 * t.lda + k1, 2 * NBT, 2 * NBT, t.lda, t.ntot - k1, t.ntot - k1,
+                                       2 * NBT};
+                }
+                if (int rc = launch_gemm_nt_batch(g, ng, -1, st)) return rc;
+            }
+        }
+    }
+    k_trib_tail<<<nsys, 32, 0, st>>>(tb);
+    B200_LAUNCHED(launches + 1);
     B200_CUDA(cudaGetLastError());
     return 0;
 }
