@@ -152,9 +152,12 @@ __device__ __forceinline__ void gemm_tile_nt(const double* A, int lda, const dou
 // 87 % busy, 30.5 TFLOP/s).  The library DGEMM that sets the roofline (ncu on torch.matmul, tools/probe/dgemm_probe.py:
 // cutlass d884gemm 64x64_16x4, 128 threads, 120 registers, 64 KB, three CTAs per SM, DMMA pipe 97.5 % busy) hides that
 // barrier behind the other resident CTAs.  Same recipe here: 64x64 output tile, 4 warps of 32x32, K stages of 16 in a
-// 4-deep cp.async ring (64 KB, so three CTAs share an SM), rows of one stage are exactly 128 B and the 16-byte chunks of
-// a row are XOR-swizzled with (row & 7): cp.async keeps its 16-byte granularity and the fragment loads (8 rows x 4
-// consecutive doubles per instruction) touch every 8-byte bank word exactly twice, the minimum for 256 B.
+// 4-deep cp.async ring (64 KB, so three CTAs share an SM), rows of one stage are exactly 128 B and the four 32-byte
+// granules of a row are XOR-swizzled with (row & 3): cp.async keeps its 16-byte granularity, and a fragment load (8 rows x
+// 4 consecutive doubles per instruction = one 32-byte granule per row) is served as two half-warps of 4 rows whose
+// granules fall on four different bank groups - conflict-free.  (Round 1 swizzled the 16-byte chunks with (row & 7),
+// TMA's 128-byte pattern: rows g and g ^ 1 of a half-warp then share their two chunks, a two-way conflict on every
+// fragment load - ncu: 43 % of the shared wavefronts.)
 // Used by the four update kernels (operands and output never overlap there); the in-place products with inv(L_kk)
 // keep the 128x128 tile, which stages the whole K = 128 operand before it writes.
 #ifndef B200_T64_STAGES
@@ -193,7 +196,7 @@ __device__ __forceinline__ void gemm_tile64(const double* A, int lda, const doub
         for (int r = 0; r < TB * (KT2 / 2) / GT2; r++) {
             const int c = tid + GT2 * r;
             const int row = c >> 3, ch = c & 7;
-            const int dst = row * KT2 + ((ch ^ (row & 7)) << 1);
+            const int dst = row * KT2 + (((((ch >> 1) ^ (row & 3)) << 1) | (ch & 1)) << 1);
             if (k0 + 2 * ch < K) {
                 cp_async16(As + dst, A + (size_t)row * lda + k0 + 2 * ch);
                 cp_async16(Bs + dst, B + (size_t)row * ldb + k0 + 2 * ch);
@@ -219,8 +222,8 @@ __device__ __forceinline__ void gemm_tile64(const double* A, int lda, const doub
                 acc[mi][ni][1] = (MODE == TILE_SUB) ? -v.y : v.y;
             }
     }
-    // element (row, 4 kk + q) of a stage sits at row * 16 + (off0 ^ 4 kk): all fragment rows have row & 7 == g
-    const int off0 = ((((q >> 1) ^ g)) << 1) | (q & 1);
+    // element (row, 4 kk + q) of a stage sits at row * 16 + (off0 ^ 4 kk): all fragment rows have row & 3 == g & 3
+    const int off0 = ((g & 3) << 2) | q;
     const int arow = (wm * 32 + g) * KT2, brow = TB * KT2 + (wn * 32 + g) * KT2;
     for (int kt = 0; kt < nk; kt++) {
         cp_async_wait<ST2 - 2>();
