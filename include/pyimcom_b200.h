@@ -209,8 +209,14 @@ int b200_dev_transpose(const double* A, int lda, double* At, int ldat, int rows,
 int b200_dev_eigh(double* A, int lda, int n, double* Vt, int ldv, double* lam, int max_sweeps, int* sweeps,
                   void* stream);
 
-/* The same for up to B200_MAXB independent matrices at once (the OutStamps of a batch): every round is one launch
- * over all systems, so the 16-row block pairs of all of them fill the GPU; a system that has converged drops out. */
+/* np.linalg.eigh (lakernel.py:162, 201, 266) for up to B200_MAXB independent matrices at once (the OutStamps of a
+ * batch), every launch over all of them: blocked Householder tridiagonalisation, bisection, inverse iteration,
+ * Cholesky-QR orthonormalisation, compact-WY back-transformation (csrc/trieig.cu).  A and Vt must be padded to a multiple
+ * of 128 rows and columns (A with the identity), lda and ldv even.  Synchronises the stream once at the end; *sweeps is
+ * set to 0.  A system whose orthonormalisation fails (linearly dependent inverse-iteration vectors) is solved again with
+ * the block-Jacobi method of b200_dev_eigh; b200_eigh_fallback_count() counts those.  Environment: B200_EIGH=jacobi selects
+ * the Jacobi solver for everything (then max_sweeps / *sweeps have the meaning of b200_dev_eigh and the padding rule is
+ * b200_dev_eigh's). */
 typedef struct b200_eigh_problem {
     double* A;   /* (ntot, lda) in, destroyed; identity padding as for b200_dev_eigh */
     double* Vt;  /* (ntot, ldv) out: eigenvectors as rows */
@@ -218,6 +224,7 @@ typedef struct b200_eigh_problem {
     int lda, ldv, n, pad_;
 } b200_eigh_problem;
 int b200_dev_eigh_batch(const b200_eigh_problem* problems, int nsys, int max_sweeps, int* sweeps, void* stream);
+long long b200_eigh_fallback_count(void);
 /* Householder tridiagonalisation A = Q T Q^T of one symmetric matrix (the first stage of the eigensolver; exposed for the
  * tests): A (n x n, lda) is overwritten -- row k holds reflector k at columns k+1.. (leading 1 stored) -- and the device
  * arrays d, e, tau (n doubles each) receive T's diagonal, its sub-diagonal (e[n-1] = 0) and the reflector scales. */

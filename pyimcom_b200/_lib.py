@@ -150,6 +150,8 @@ lib.b200_chol_work_bytes.restype = C.c_size_t
 lib.b200_chol_work_bytes.argtypes = [i32, i32]
 lib.b200_launch_count.restype = C.c_longlong
 lib.b200_launch_count.argtypes = []
+lib.b200_eigh_fallback_count.restype = C.c_longlong
+lib.b200_eigh_fallback_count.argtypes = []
 
 
 def _wrap(name, argtypes):
@@ -189,6 +191,11 @@ def profile_read():
 
 def launch_count() -> int:
     return int(lib.b200_launch_count())
+
+
+def eigh_fallback_count() -> int:
+    """How many eigenproblems the tridiagonalisation-based solver handed to the Jacobi solver so far."""
+    return int(lib.b200_eigh_fallback_count())
 
 
 def version() -> int:

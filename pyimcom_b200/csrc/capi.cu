@@ -372,6 +372,7 @@ int b200_dev_eigh_batch(const b200_eigh_problem* problems, int nsys, int max_swe
     if (sweeps) *sweeps = 0;
     return launch_tri_eigh_batch(problems, nsys, ST(s));
 }
+long long b200_eigh_fallback_count(void) { return eigh_fallback_count(); }
 int b200_dev_tridiag(double* A, int lda, int n, double* d, double* e, double* tau, void* s) {
     return launch_tridiag(A, lda, n, d, e, tau, ST(s));
 }

@@ -111,6 +111,7 @@ int launch_jacobi_eigh(double* A, int lda, int n, double* Vt, int ldv, double* l
 
 // trieig.cu
 int launch_tri_eigh_batch(const EighProblem* pr, int nsys, cudaStream_t s);
+long long eigh_fallback_count();
 int launch_tridiag(double* A, int lda, int n, double* d, double* e, double* tau, cudaStream_t s);
 
 // coadd.cu

@@ -258,7 +258,7 @@ __global__ void __launch_bounds__(128) k_tri_invit(InvitBatch bt, int stage) {
     double* zrow = s.Zt + (size_t)j * s.ldz;
     const double eps = 2.220446049250313e-16;
     const double tn = fmax(fmax(fabs(s.lam[0]), fabs(s.lam[n - 1])), 1e-300);
-    if (stage == 0) {
+    if ((stage & 1) == 0) {
         const double floor_ = 1e-290;  // (denormal eigenvalues: push by something representable)
         double xs = s.lam[j];
         {
@@ -267,6 +267,7 @@ __global__ void __launch_bounds__(128) k_tri_invit(InvitBatch bt, int stage) {
             while (j - back - 1 >= 0 && s.lam[j - back] - s.lam[j - back - 1] < sep && back < 4096) back++;
             if (back > 0) xs = s.lam[j - back] + back * sep;
         }
+        if (stage & 2) xs = s.lam[n / 2];  // test hook (B200_EIGH_TEST_FAIL): every thread takes the same shift
         const double tiny = eps * tn;
         // ---- factorisation (row i of the working pair is (a, b, c) = (diag, super1, super2)) ----
         double a = s.d[0] - xs, b = n > 1 ? s.e[0] : 0.0, c = 0.0;
@@ -773,6 +774,7 @@ struct StageTimer {
 };
 
 constexpr int QR_ROUNDS = 3;
+static long long g_eigh_fallbacks = 0;
 
 int launch_tri_eigh_batch(const EighProblem* pr, int nsys, cudaStream_t st) {
     if (nsys <= 0) return 0;
@@ -788,6 +790,16 @@ int launch_tri_eigh_batch(const EighProblem* pr, int nsys, cudaStream_t st) {
     prof_begin(PROF_EIGH, st);
     StageTimer tm(st);
     int* qr_info = nullptr;
+    // copies of the matrices (the tridiagonalisation destroys them): only read again if the orthogonalisation fails
+    void* acopy = nullptr;
+    if (int rc = scratch(14, sizeof(double) * (size_t)ntot_max * ntot_max * nsys, &acopy)) return rc;
+    for (int q = 0; q < nsys; q++) {
+        const int ntot = (pr[q].n + NB - 1) / NB * NB;
+        B200_CUDA(cudaMemcpy2DAsync(static_cast<double*>(acopy) + (size_t)ntot_max * ntot_max * q, sizeof(double) * ntot,
+                                    pr[q].A, sizeof(double) * pr[q].lda, sizeof(double) * ntot, ntot,
+                                    cudaMemcpyDeviceToDevice, st));
+    }
+    const int test_fail = getenv("B200_EIGH_TEST_FAIL") != nullptr ? 2 : 0;
     // ---- scratch: vectors of the tridiagonalisation, inverse-iteration arrays, WY panels, Gram matrices ----
     void* ws = nullptr;
     const size_t per_vec = 8 * (size_t)nmax;
@@ -886,7 +898,7 @@ int launch_tri_eigh_batch(const EighProblem* pr, int nsys, cudaStream_t st) {
         }
         return 0;
     };
-    k_tri_invit<<<dim3(nthr / 128, nsys), 128, 0, st>>>(ib, 0);
+    k_tri_invit<<<dim3(nthr / 128, nsys), 128, 0, st>>>(ib, 0 | test_fail);
     B200_LAUNCH_CHECK();
     for (int q = 0; q < nsys; q++) {
         const int ntot = (pr[q].n + NB - 1) / NB * NB;
@@ -970,17 +982,40 @@ int launch_tri_eigh_batch(const EighProblem* pr, int nsys, cudaStream_t st) {
     }
     tm.lap("back-transformation");
     prof_end(0.0, st);
-    // The Gram matrices of both Cholesky-QR rounds must have been positive definite: a failed factorisation means the
-    // inverse-iteration vectors were linearly dependent, and everything after it is garbage.  Fail loudly.
+    // The Gram matrices of all Cholesky-QR rounds must have been positive definite: a failed factorisation means the
+    // inverse-iteration vectors were linearly dependent, and everything after it is garbage.  Such a system is solved
+    // again from the saved copy of its matrix with the block-Jacobi solver of eigen.cu (slow, but it has no such failure
+    // mode); b200_eigh_fallback_count() reports how often that happened.
     int h_info[QR_ROUNDS * MAXB];
     B200_CUDA(cudaMemcpyAsync(h_info, qr_info, sizeof(h_info), cudaMemcpyDeviceToHost, st));
     B200_CUDA(cudaStreamSynchronize(st));
-    for (int q = 0; q < nsys; q++)
-        B200_REQUIRE(h_info[q] == 0 && h_info[MAXB + q] == 0 && h_info[2 * MAXB + q] == 0,
-                     "eigh: Cholesky-QR of the inverse-iteration vectors failed (linearly dependent vectors); "
-                     "B200_EIGH=jacobi selects the Jacobi solver");
+    EighProblem redo[MAXB];
+    int nredo = 0;
+    for (int q = 0; q < nsys; q++) {
+        bool bad = false;
+        for (int r = 0; r < QR_ROUNDS; r++) bad = bad || h_info[r * MAXB + q] != 0;
+        if (!bad) continue;
+        const int ntot = (pr[q].n + NB - 1) / NB * NB;
+        B200_CUDA(cudaMemcpy2DAsync(pr[q].A, sizeof(double) * pr[q].lda,
+                                    static_cast<double*>(acopy) + (size_t)ntot_max * ntot_max * q, sizeof(double) * ntot,
+                                    sizeof(double) * ntot, ntot, cudaMemcpyDeviceToDevice, st));
+        redo[nredo++] = pr[q];
+    }
+    if (nredo > 0) {
+        g_eigh_fallbacks += nredo;
+        int sweeps = 0;
+        if (int rc = launch_jacobi_eigh_batch(redo, nredo, 80, &sweeps, st)) return rc;
+        for (int q = 0; q < nredo; q++) {  // (the Jacobi solver owns a smaller padding: restore ours)
+            const int ntot = (redo[q].n + NB - 1) / NB * NB;
+            k_pad_vectors<<<dim3((ntot + 255) / 256, ntot), 256, 0, st>>>(redo[q].Vt, redo[q].ldv, redo[q].n, ntot);
+            B200_LAUNCHED(1);
+        }
+        B200_CUDA(cudaGetLastError());
+    }
     return 0;
 }
+
+long long eigh_fallback_count() { return g_eigh_fallbacks; }
 
 // Householder tridiagonalisation alone (tests): A (n x n, lda) is overwritten by the reflectors, d / e / tau receive
 // T's diagonal, sub-diagonal and the reflector scales (device arrays of n doubles).

@@ -313,6 +313,78 @@ def test_eigh_device():
     assert 0 <= sweeps < 40  # (0: the tridiagonalisation-based solver; the Jacobi solver counts its sweeps)
 
 
+def _graded_matrix(n, seed):
+    """Spectrum like the system matrices of this path: a numerically zero cluster + ten decades, ~uniform in log."""
+    rng = np.random.default_rng(seed)
+    Q, _ = np.linalg.qr(rng.standard_normal((n, n)))
+    lam = np.concatenate([np.zeros(n // 5), np.logspace(-11, -1, n - n // 5)])
+    A = (Q * lam) @ Q.T
+    return 0.5 * (A + A.T)
+
+
+def _padded(A):
+    n = A.shape[0]
+    npad = (n + 127) // 128 * 128
+    Ad = torch.eye(npad, dtype=torch.float64, device="cuda")
+    Ad[:n, :n] = torch.from_numpy(A).cuda()
+    return Ad
+
+
+def test_eigh_batch_of_unequal_sizes():
+    """The batched eigensolver (csrc/trieig.cu) on systems of different sizes in ONE call, including sizes around the
+    panel width of the blocked tridiagonalisation (64) and the compact-WY panel (128) and the trivial ones."""
+    sizes = [1, 2, 3, 63, 64, 65, 66, 127, 129, 191, 200, 333]
+    mats = [_graded_matrix(n, 10 + n) if n > 3 else np.random.default_rng(n).standard_normal((n, n)) for n in sizes]
+    mats = [0.5 * (A + A.T) for A in mats]
+    res, _ = GL.eigh_device_batch([(_padded(A), A.shape[0]) for A in mats])
+    for A, (lam, Vt) in zip(mats, res):
+        n = A.shape[0]
+        npad = Vt.shape[0]
+        lam, V = lam[:n].cpu().numpy(), Vt[:n, :n].cpu().numpy().T
+        scale = max(np.abs(A).max(), 1e-300)
+        assert np.abs(np.sort(lam) - np.linalg.eigvalsh(A)).max() < 1e-13 * scale * max(n, 10), n
+        assert np.abs(V.T @ V - np.eye(n)).max() < 1e-13, n
+        assert np.abs(A @ V - V * lam).max() < 1e-13 * scale * max(n, 10), n
+        # the padding stays the identity and does not leak into the vectors
+        assert torch.equal(Vt[n:, n:], torch.eye(npad - n, dtype=torch.float64, device="cuda"))
+        assert float(Vt[:n, n:].abs().max()) == 0.0 if npad > n else True
+
+
+def test_tridiag_blocked_equals_unblocked_spectrum():
+    """b200_dev_tridiag: the tridiagonal matrix has the spectrum of A (blocked dlatrd-style reduction, panels of 64)."""
+    import scipy.linalg as sl
+
+    for n in (5, 64, 130, 400):
+        A = _graded_matrix(n, n) if n > 5 else np.diag(np.arange(1.0, 6.0)) + 0.1
+        Ad = _padded(A)
+        d, e, tau = (torch.zeros(n, dtype=torch.float64, device="cuda") for _ in range(3))
+        _lib.dev_tridiag(GL.ptr(Ad), Ad.stride(0), n, GL.ptr(d), GL.ptr(e), GL.ptr(tau), GL.stream_handle())
+        torch.cuda.synchronize()
+        lt = sl.eigvalsh_tridiagonal(d.cpu().numpy(), e.cpu().numpy()[: n - 1])
+        assert np.abs(lt - np.linalg.eigvalsh(A)).max() < 1e-14 * max(np.abs(A).max(), 1.0) * n
+
+
+def test_eigh_falls_back_to_jacobi_when_orthonormalisation_fails(monkeypatch):
+    """B200_EIGH_TEST_FAIL gives every inverse-iteration thread the same shift: the vectors are linearly dependent, the
+    Gram matrix of the Cholesky-QR stage is singular, and the system must be solved again by the Jacobi solver - never
+    returned as garbage."""
+    n = 200
+    A = _graded_matrix(n, 5)
+    before = _lib.eigh_fallback_count()
+    monkeypatch.setenv("B200_EIGH_TEST_FAIL", "1")
+    lam, Vt, _ = GL.eigh_device(_padded(A), n)
+    monkeypatch.delenv("B200_EIGH_TEST_FAIL")
+    assert _lib.eigh_fallback_count() == before + 1
+    lam, V = lam[:n].cpu().numpy(), Vt[:n, :n].cpu().numpy().T
+    assert np.isfinite(V).all()
+    assert np.abs(np.sort(lam) - np.linalg.eigvalsh(A)).max() < 1e-13
+    assert np.abs(V.T @ V - np.eye(n)).max() < 1e-12
+    assert np.abs(A @ V - V * lam).max() < 1e-13
+    # and without the hook the fast path does not fall back
+    GL.eigh_device(_padded(A), n)
+    assert _lib.eigh_fallback_count() == before + 1
+
+
 # ---------------------------------------------------------------------------------------------------
 # kernel-class seam on the reference's own unit-test inputs (tests/pyimcom/test_la.py)
 # ---------------------------------------------------------------------------------------------------
