@@ -403,6 +403,35 @@ __global__ void __launch_bounds__(128) k_wy_tfactor(WyBatch wb, int p0) {
     for (int c = 0; c < NB; c++) w.T[(size_t)tid * NB + c] = Ts(tid, c);
 }
 
+// max |G - I| of each system's Gram matrix (non-finite entries count as +inf); dev[] zeroed by the caller
+struct GramDev {
+    const double* G[MAXB];
+    int ntot[MAXB];
+};
+__global__ void __launch_bounds__(256) k_gram_dev(GramDev gd, double* dev) {
+    __shared__ double red[40];
+    const int q = blockIdx.y, ntot = gd.ntot[q];
+    const double* G = gd.G[q];
+    double m = 0.0;
+    const size_t tot = (size_t)ntot * ntot;
+    for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < tot; t += (size_t)gridDim.x * blockDim.x) {
+        const int i = (int)(t / ntot), j = (int)(t - (size_t)i * ntot);
+        double v = fabs(G[t] - (i == j ? 1.0 : 0.0));
+        if (!(v <= 1.7e308)) v = INFINITY;
+        m = fmax(m, v);
+    }
+    // block maximum, then one atomic per CTA (the bit patterns of non-negative doubles are ordered like the values)
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if (lane == 0) red[w] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int k = 1; k < 8; k++) m = fmax(m, red[k]);
+        atomicMax(reinterpret_cast<unsigned long long*>(dev + q), (unsigned long long)__double_as_longlong(m));
+    }
+}
+
 // Zt rows n .. ntot-1 = unit vectors, columns n .. of the real rows = 0 (the identity padding of the caller)
 __global__ void k_pad_vectors(double* __restrict__ Zt, int ldz, int n, int ntot) {
     const int r = blockIdx.y;
@@ -860,20 +889,49 @@ int launch_tri_eigh_batch(const EighProblem* pr, int nsys, cudaStream_t st) {
     }
     void* gs = nullptr;
     const size_t per_g = 2 * (size_t)ntot_max * ntot_max + 2 * (size_t)(ntot_max / NB) * NB * NB;
-    if (int rc = scratch(11, sizeof(double) * per_g * nsys + sizeof(int) * QR_ROUNDS * MAXB + 256, &gs)) return rc;
+    if (int rc = scratch(11, sizeof(double) * per_g * nsys + sizeof(int) * QR_ROUNDS * MAXB + sizeof(double) * MAXB + 256, &gs))
+        return rc;
     double* gb = static_cast<double*>(gs);
     qr_info = reinterpret_cast<int*>(gb + per_g * nsys);
     B200_CUDA(cudaMemsetAsync(qr_info, 0, sizeof(int) * QR_ROUNDS * MAXB, st));
-    auto cholqr = [&](int round) -> int {
+    double* d_dev = reinterpret_cast<double*>(qr_info + QR_ROUNDS * MAXB);
+    static const bool always_qr = getenv("B200_EIGH_ALWAYS_QR") != nullptr;  // (experiments: never skip a round)
+    // One round.  The Gram matrix is always formed and its distance from the identity read back (one stream
+    // synchronisation); when that is below skip_below the vectors are orthonormal enough for what follows and the
+    // factorisation + triangular solve are skipped.  *dev_out receives the distance.
+    auto cholqr = [&](int round, double skip_below, double* dev_out) -> int {
         SolveSys sys[MAXB];
         GemmProb gram[MAXB];
+        GramDev gd;
         int* info = qr_info + round * MAXB;
+        for (int q = 0; q < nsys; q++) {
+            const int ntot = (pr[q].n + NB - 1) / NB * NB;
+            double* G = gb + per_g * q;
+            gram[q] = GemmProb{pr[q].Vt, pr[q].Vt, G, pr[q].ldv, pr[q].ldv, ntot, ntot, ntot, ntot};
+            gd.G[q] = G;
+            gd.ntot[q] = ntot;
+        }
+        for (int q = nsys; q < MAXB; q++) {
+            gd.G[q] = gd.G[0];
+            gd.ntot[q] = 0;
+        }
+        if (int rc = launch_gemm_nt_batch(gram, nsys, 0, st)) return rc;
+        B200_CUDA(cudaMemsetAsync(d_dev, 0, sizeof(double) * MAXB, st));
+        k_gram_dev<<<dim3(64, nsys), 256, 0, st>>>(gd, d_dev);
+        B200_LAUNCH_CHECK();
+        double h_dev[MAXB];
+        B200_CUDA(cudaMemcpyAsync(h_dev, d_dev, sizeof(double) * MAXB, cudaMemcpyDeviceToHost, st));
+        B200_CUDA(cudaStreamSynchronize(st));
+        double dev = 0.0;
+        for (int q = 0; q < nsys; q++) dev = h_dev[q] > dev ? h_dev[q] : dev;
+        if (dev_out) *dev_out = dev;
+        if (tm.on) fprintf(stderr, "  eigh round %d: max |G - I| = %.2e\n", round, dev);
+        if (dev < skip_below && !always_qr) return 0;
         for (int q = 0; q < nsys; q++) {
             const int ntot = (pr[q].n + NB - 1) / NB * NB;
             double* G = gb + per_g * q;
             double* Xt = G + (size_t)ntot_max * ntot_max;  // Z^T (components x vectors)
             double* Dinv = Xt + (size_t)ntot_max * ntot_max;
-            gram[q] = GemmProb{pr[q].Vt, pr[q].Vt, G, pr[q].ldv, pr[q].ldv, ntot, ntot, ntot, ntot};
             if (int rc = launch_transpose(pr[q].Vt, pr[q].ldv, Xt, ntot, ntot, ntot, st)) return rc;
             SolveSys& s = sys[q];
             s.W = G;
@@ -889,7 +947,6 @@ int launch_tri_eigh_batch(const EighProblem* pr, int nsys, cudaStream_t st) {
             s.work = nullptr;
             s.work_bytes = 0;
         }
-        if (int rc = launch_gemm_nt_batch(gram, nsys, 0, st)) return rc;
         if (int rc = launch_chol_solve(sys, nsys, 1, 2, st)) return rc;  // factor + FORWARD solve only: X <- X L^-T
         for (int q = 0; q < nsys; q++) {
             const int ntot = (pr[q].n + NB - 1) / NB * NB;
@@ -907,14 +964,20 @@ int launch_tri_eigh_batch(const EighProblem* pr, int nsys, cudaStream_t st) {
     }
     B200_CUDA(cudaGetLastError());
     tm.lap("inverse iteration 1");
-    if (int rc = cholqr(0)) return rc;
+    // max |G - I| * ntot bounds the 2-norm of G - I: below 0.1 the Gram matrix has a condition number < 1.25.
+    // Between the solves the vectors only have to be far from collapsing: such nearly orthonormal ones go on as they are
+    const double well = 0.1 / ntot_max;
+    if (int rc = cholqr(0, well, nullptr)) return rc;
     tm.lap("Cholesky-QR");
     k_tri_invit<<<dim3(nthr / 128, nsys), 128, 0, st>>>(ib, 1);
     B200_LAUNCH_CHECK();
     tm.lap("inverse iteration 2");
-    if (int rc = cholqr(1)) return rc;
-    if (int rc = cholqr(2)) return rc;
-    tm.lap("Cholesky-QR x 2");
+    // one round leaves an orthogonality error of ~ eps * cond(G): a second one only after an ill-conditioned first
+    double dev1 = 0.0;
+    if (int rc = cholqr(1, 0.0, &dev1)) return rc;
+    if (dev1 >= well || always_qr)
+        if (int rc = cholqr(2, 0.0, nullptr)) return rc;
+    tm.lap("Cholesky-QR x 1-2");
     // ---- back-transformation: rows of Vt <- eigenvectors of A;  Z <- (I - V T V^T) Z panel by panel, last panel first,
     // every launch over all systems ----
     {
