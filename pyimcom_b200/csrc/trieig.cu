@@ -382,25 +382,40 @@ __global__ void __launch_bounds__(256) k_wy_extract(WyBatch wb, int p0) {
 }
 
 // T (128 x 128, upper triangular, row-major) of H_p0 ... H_p0+127 = I - V T V^T from the Gram matrix S = V^T V
-// (LAPACK dlarft, forward / columnwise): T[j][j] = tau_j, T[0:j, j] = -tau_j T[0:j, 0:j] S[0:j, j].  Thread i owns row i.
-__global__ void __launch_bounds__(128) k_wy_tfactor(WyBatch wb, int p0) {
-    extern __shared__ double Tsm[];  // [NB][NB + 1]
+// (LAPACK dlarft, forward / columnwise): T[j][j] = tau_j, T[0:j, j] = -tau_j T[0:j, 0:j] S[0:j, j].  Row i of T only
+// depends on row i of T and on S: four lanes of one warp own a row (quarters of the inner sum, two shuffles); the upper
+// triangles of S and T are held packed in shared memory (2 x 66 KB).
+constexpr int WY_PACKED = NB * (NB + 1) / 2;
+__device__ __forceinline__ int wy_pk(int r, int c) { return r * NB - r * (r - 1) / 2 + (c - r); }  // r <= c
+__global__ void __launch_bounds__(512) k_wy_tfactor(WyBatch wb, int p0) {
+    extern __shared__ double wy_sm[];  // S packed, then T packed
+    double* Ss = wy_sm;
+    double* Ts = wy_sm + WY_PACKED;
     const WySys& w = wb.s[blockIdx.x];
     if (!w.active) return;
     const int tid = threadIdx.x;
-    auto Ts = [&](int r, int c) -> double& { return Tsm[r * (NB + 1) + c]; };
-    for (int c = 0; c < NB; c++) Ts(tid, c) = 0.0;
-    for (int j = 0; j < NB; j++) {
+    for (int e = tid; e < NB * NB; e += 512) {
+        const int r = e / NB, c = e - r * NB;
+        if (r <= c) Ss[wy_pk(r, c)] = w.S[e];
+    }
+    __syncthreads();
+    const int i = tid >> 2, part = tid & 3;  // row, quarter
+    for (int j = (tid >> 5) * 8; j < NB; j++) {  // (warp-uniform trip count: the eight rows of a warp start at 8 w)
         const int k = p0 + j;
         const double tj = (k < w.n - 2) ? w.tau[k] : 0.0;
-        if (tid < j) {
-            double acc = 0.0;
-            for (int l = tid; l < j; l++) acc += Ts(tid, l) * w.S[(size_t)l * NB + j];
-            Ts(tid, j) = -tj * acc;
-        }
-        if (tid == j) Ts(j, j) = tj;
+        double acc = 0.0;
+        if (j > i)
+            for (int l = i + part; l < j; l += 4) acc += Ts[wy_pk(i, l)] * Ss[wy_pk(l, j)];
+        acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+        acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+        if (part == 0 && j >= i) Ts[wy_pk(i, j)] = (j == i) ? tj : -tj * acc;
+        __syncwarp();
     }
-    for (int c = 0; c < NB; c++) w.T[(size_t)tid * NB + c] = Ts(tid, c);
+    __syncthreads();
+    for (int e = tid; e < NB * NB; e += 512) {
+        const int r = e / NB, c = e - r * NB;
+        w.T[e] = r <= c ? Ts[wy_pk(r, c)] : 0.0;
+    }
 }
 
 // max |G - I| of each system's Gram matrix (non-finite entries count as +inf); dev[] zeroed by the caller
@@ -1035,7 +1050,7 @@ int launch_tri_eigh_batch(const EighProblem* pr, int nsys, cudaStream_t st) {
             k_wy_extract<<<dim3((ntot_max + 255) / 256, NB, nsys), 256, 0, st>>>(wb, p0);
             B200_LAUNCHED(1);
             if (int rc = launch_gemm_nt_batch(gS, na, 0, st)) return rc;
-            k_wy_tfactor<<<nsys, NB, sizeof(double) * NB * (NB + 1), st>>>(wb, p0);
+            k_wy_tfactor<<<nsys, 512, sizeof(double) * 2 * WY_PACKED, st>>>(wb, p0);
             B200_LAUNCHED(1);
             if (int rc = launch_gemm_nt_batch(gW, na, 0, st)) return rc;
             if (int rc = launch_gemm_nt_batch(gY, na, 0, st)) return rc;

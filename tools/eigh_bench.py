@@ -26,7 +26,7 @@ for setting in sys.argv[1:] or ["B200_EIGH_INNER=1"]:
     for kv in setting.split(","):
         k, v = kv.split("=")
         os.environ[k] = v
-    for nb in (1, 16):
+    for nb in ((16,) if os.environ.get("EIGH_BENCH_ONLY16") else (1, 16)):
         mk = lambda: ([(ds.matrix().clone(), ds.n) for ds in dss[:nb]] if nb > 1  # noqa: E731
                       else [(dss[5].matrix().clone(), dss[5].n)])
         GL.eigh_device_batch(mk())  # warm-up: scratch allocations, kernel attributes
