@@ -489,27 +489,107 @@ struct TribBatch {
     TribSys s[MAXB];
 };
 
+constexpr int RC = 8;  // elements of a column one thread of k_trib_reflect keeps in registers (columns up to 8192 long)
 __global__ void __launch_bounds__(1024) k_trib_reflect(TribBatch bt, int k, int k0_prev, int k0, int finish, int reflect,
                                                       int fresh, int ndpart) {
     __shared__ double red[40];
+    __shared__ double sh_a[2];
     const TribSys& s = bt.s[blockIdx.x];
     const int n = s.n, tid = threadIdx.x;
+    const bool do_finish = finish && k >= 1 && k - 1 <= n - 3;
+    const bool do_reflect = reflect && k <= n - 3;
+    if (!do_finish && !do_reflect) return;
+    double* row = s.A + (size_t)k * s.lda;
+    if (s.ntot - k <= RC * 1024) {
+        // every global load is issued before the first reduction: one round trip to memory, then registers only
+        double pv[RC], cv[RC], vv[RC];
+#pragma unroll
+        for (int u = 0; u < RC; u++) {
+            const int i = k + tid + u * 1024;
+            pv[u] = cv[u] = vv[u] = 0.0;
+            if (i < n) {
+                if (!fresh || do_finish) vv[u] = s.vbuf[i];
+                if (do_finish) pv[u] = s.p[i];
+                if (do_reflect) cv[u] = fresh ? row[i] : s.c[i];
+            }
+        }
+        double alpha = 0.0;
+        if (do_finish) {
+            double acc = 0.0;
+            for (int i = tid; i < ndpart; i += 1024) acc += s.dpart[i];
+            const double tprev = s.tau[k - 1];
+            acc = block_sum(acc, red);
+            alpha = -0.5 * tprev * acc;
+            const int jp = k - 1 - k0_prev;
+#pragma unroll
+            for (int u = 0; u < RC; u++) {
+                const int i = k + tid + u * 1024;
+                if (i < s.ntot) {  // (rows above k are dead: nobody reads them again)
+                    const double w = i < n ? pv[u] + alpha * vv[u] : 0.0;
+                    s.VW[(size_t)i * (2 * NBT) + NBT + jp] = w;
+                    s.WV[(size_t)i * (2 * NBT) + jp] = w;
+                }
+            }
+        }
+        if (!do_reflect) return;
+        const int j = k - k0;
+        double ss = 0.0;
+#pragma unroll
+        for (int u = 0; u < RC; u++) {
+            const int i = k + tid + u * 1024;
+            if (!fresh) cv[u] -= 2.0 * alpha * vv[u];  // cv = column k of the current matrix from here on
+            if (i >= k + 2 && i < n) ss += cv[u] * cv[u];
+        }
+        if (tid < 2) sh_a[tid] = cv[0];  // a[k], a[k+1]
+        ss = block_sum(ss, red);
+        const double alpha0 = sh_a[1];
+        double beta = alpha0, tau = 0.0, scale = 0.0;
+        if (ss > 0.0) {
+            const double nrm = sqrt(alpha0 * alpha0 + ss);
+            beta = alpha0 >= 0.0 ? -nrm : nrm;
+            tau = (beta - alpha0) / beta;
+            scale = 1.0 / (alpha0 - beta);
+        }
+#pragma unroll
+        for (int u = 0; u < RC; u++) {
+            const int i = k + tid + u * 1024;
+            if (i < s.ntot) {
+                double vi = 0.0;
+                if (i == k + 1)
+                    vi = 1.0;
+                else if (i > k + 1 && i < n)
+                    vi = cv[u] * scale;
+                s.VW[(size_t)i * (2 * NBT) + j] = vi;
+                s.WV[(size_t)i * (2 * NBT) + NBT + j] = vi;
+                if (i < n) {
+                    s.vbuf[i] = vi;
+                    if (i > k) row[i] = vi;  // the reflector lives in the dead row k from now on
+                }
+            }
+        }
+        if (tid == 0) {
+            s.d[k] = sh_a[0];
+            s.e[k] = beta;
+            s.tau[k] = tau;
+        }
+        return;
+    }
+    // ---- general path (columns longer than RC * 1024): the same steps through the global work vector abuf ----
     double alpha = 0.0;
-    if (finish && k >= 1 && k - 1 <= n - 3) {
+    if (do_finish) {
         const int jp = k - 1 - k0_prev;
         double acc = 0.0;
         for (int i = tid; i < ndpart; i += 1024) acc += s.dpart[i];
         acc = block_sum(acc, red);
         alpha = -0.5 * s.tau[k - 1] * acc;
-        for (int i = k + tid; i < s.ntot; i += 1024) {  // (rows above k are dead: nobody reads them again)
+        for (int i = k + tid; i < s.ntot; i += 1024) {
             const double w = i < n ? s.p[i] + alpha * s.vbuf[i] : 0.0;
             s.VW[(size_t)i * (2 * NBT) + NBT + jp] = w;
             s.WV[(size_t)i * (2 * NBT) + jp] = w;
         }
     }
-    if (!reflect || k > n - 3) return;
+    if (!do_reflect) return;
     const int j = k - k0;
-    double* row = s.A + (size_t)k * s.lda;
     for (int i = k + tid; i < n; i += 1024) s.abuf[i] = fresh ? row[i] : s.c[i] - 2.0 * alpha * s.vbuf[i];
     __syncthreads();
     double ss = 0.0;
@@ -533,7 +613,7 @@ __global__ void __launch_bounds__(1024) k_trib_reflect(TribBatch bt, int k, int 
         s.WV[(size_t)i * (2 * NBT) + NBT + j] = vi;
         if (i < n) {
             if (i >= k) s.vbuf[i] = vi;
-            if (i > k) row[i] = vi;  // the reflector lives in the dead row k from now on
+            if (i > k) row[i] = vi;
         }
     }
     if (tid == 0) {
@@ -588,7 +668,7 @@ __global__ void __launch_bounds__(256) k_trib_symv(TribBatch bt, int k, int gx_r
 }
 
 __global__ void __launch_bounds__(256) k_trib_p(TribBatch bt, int k, int k0, int gx, int zc) {
-    __shared__ double zz[2 * NBT], rr[2 * NBT], wsum[8], pk1s;
+    __shared__ double zz[2 * NBT], rr[2 * NBT], wsum[8];
     const TribSys& s = bt.s[blockIdx.y];
     const int n = s.n;
     if (k > n - 3) return;
@@ -606,22 +686,24 @@ __global__ void __launch_bounds__(256) k_trib_p(TribBatch bt, int k, int k0, int
         rr[tid] = r;
     }
     __syncthreads();
-    if (warp == 0) {
+    // p_{k+1} (every warp for itself: no block-wide phase for it)
+    double pk1;
+    {
         const double* vw = s.VW + (size_t)(k + 1) * (2 * NBT);
+        const double yk1 = s.y[k + 1];
         double sp = 0.0;
         if (j > 0) {
 #pragma unroll
             for (int q = 0; q < 4; q++) sp += vw[lane + 32 * q] * zz[lane + 32 * q];
             sp = warp_sum(sp);
         }
-        if (lane == 0) pk1s = tau * (s.y[k + 1] - sp);
+        pk1 = tau * (yk1 - sp);
     }
-    __syncthreads();
-    const double pk1 = pk1s;
     const double* rowk1 = s.A + (size_t)(k + 1) * s.lda;
     double dot = 0.0;
     for (int i = k + 1 + blockIdx.x * 8 + warp; i < n; i += gx * 8) {
         const double* vw = s.VW + (size_t)i * (2 * NBT);
+        const double yi = s.y[i], vi = s.vbuf[i], ai = rowk1[i];  // (same address in every lane: one broadcast load each)
         double sp = 0.0, sc = 0.0;
         if (j > 0) {
 #pragma unroll
@@ -634,9 +716,9 @@ __global__ void __launch_bounds__(256) k_trib_p(TribBatch bt, int k, int k0, int
             sc = warp_sum(sc);
         }
         if (lane == 0) {
-            const double pi = tau * (s.y[i] - sp), vi = s.vbuf[i];
+            const double pi = tau * (yi - sp);
             s.p[i] = pi;
-            s.c[i] = rowk1[i] - sc - (vi * pk1 + pi);
+            s.c[i] = ai - sc - (vi * pk1 + pi);
             dot += pi * vi;
         }
     }
