@@ -816,7 +816,12 @@ class GpuBlock:
         """OutStamps solved together: as many as MAXB systems allow, within an HBM budget (A, W, mBhalf and X of
         every stamp of the batch are live at once: ~(2 npad^2 + 2 n_out mpad npad) * 8 bytes per kappa node)."""
         if self.kernel == "Eigen" and self.order:
-            return min(self.max_batch, _lib.MAXB)
+            # per stamp: A, its working copy, Vt, Q, the solver's saved copy, Gram matrix and transposed vectors
+            # (7 npad^2), the inverse-iteration factors (5 n npad), -B/2, P, tt and T per output PSF
+            nmax = max(p.n for p in self.plans.values())
+            npad, mpad = rup(nmax), rup(self.cfg.n2f**2)
+            per = 8.0 * (12 * npad * npad + (3 + self.cfg.n_out) * mpad * npad)
+            return int(max(1, min(0.5 * hbm_free_estimate() // per, self.max_batch, _lib.MAXB)))
         if self.kernel != "Cholesky" or not self.order:
             return 1
         cfg = self.cfg

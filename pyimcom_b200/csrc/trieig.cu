@@ -6,21 +6,27 @@
 // converges linearly, ~37 sweeps of 12 n^3 flops.  This solver does what LAPACK-class solvers do, arranged for the GPU
 // and batched over the OutStamps of a batch (one grid dimension = the system):
 //
-//   1. Householder tridiagonalisation  A = Q T Q^T, unblocked but FUSED: one pass over the trailing matrix per column
-//      applies the rank-2 update of column k-1 and forms the symmetric matrix-vector product of column k
-//      (k_tri_reflect + k_tri_update: two launches per column, 16 n^3 / 3 bytes of traffic per system);
-//   2. eigenvalues of T by bisection on Sturm counts, one thread per eigenvalue (k_tri_bisect);
+//   1. Householder tridiagonalisation  A = Q T Q^T, blocked in panels of 64 columns (dlatrd / dsytrd arrangement): the
+//      trailing matrix is only read inside a panel and receives the panel's 128 rank-one updates as one DMMA GEMM
+//      (k_trib_reflect / k_trib_symv / k_trib_p, three launches per column, 8 n^3 / 3 bytes of traffic per system);
+//      B200_TRIDIAG=unblocked keeps the first version (k_tri_reflect + k_tri_update, one read-write pass per column);
+//   2. eigenvalues of T by bisection on Sturm counts to the last bit, one thread per eigenvalue (k_tri_bisect);
 //   3. eigenvectors of T by inverse iteration, one thread per eigenvalue, every eigenvalue independently
-//      (k_tri_invit: LU with partial pivoting of T - lambda I, three iterations from a pseudo-random start).  Vectors of
-//      neighbouring eigenvalues come out orthogonal only to eps |T| / gap;
-//   4. which is repaired for ALL pairs at once by two rounds of Cholesky-QR on the n x n matrix of vectors: G = Z Z^T
-//      (DMMA GEMM), G = L L^T and Z <- L^-1 Z through the batched Cholesky / triangular solve of linalg.cu.  G is
-//      I + small except inside numerically degenerate clusters, where the random starts make it a well-conditioned Gram
-//      matrix of generic vectors of the cluster's subspace (any orthonormal basis of it serves the callers);
-//   5. back-transformation Z <- Q Z with the reflectors in compact-WY panels of 128: three DMMA GEMMs per panel.
+//      (k_tri_invit: LU with partial pivoting of T - lambda_j I, the computed eigenvalue itself as the shift, overflow-
+//      safe back substitution): one solve from a pseudo-random start, orthonormalisation, one more solve from the
+//      orthonormal vectors, orthonormalisation;
+//   4. orthonormalisation of ALL vectors at once by Cholesky-QR on the n x n matrix of vectors: G = Z Z^T (DMMA GEMM),
+//      G = L L^T and Z <- L^-1 Z through the batched Cholesky / triangular solve of linalg.cu.  A round whose Gram matrix
+//      is already within 0.1 / n of the identity is skipped, a second final round runs only after an ill-conditioned
+//      first.  Inside numerically degenerate clusters the pseudo-random starts make G a well-conditioned Gram matrix of
+//      generic vectors of the cluster's subspace (any orthonormal basis of it serves the callers);
+//   5. back-transformation Z <- Q Z with the reflectors in compact-WY panels of 128: three batched DMMA GEMMs per panel;
+//   6. a system whose Gram matrix fails to factorise (linearly dependent vectors) is solved again, from a saved copy of
+//      its matrix, by the block-Jacobi solver of eigen.cu.
 //
-// Checked on the device against NumPy (tests/test_gpu_parity.py::test_eigh_device, tools/eigh_bench.py): orthogonality and
-// residual at the 1e-15 |A| level, eigenvalues to eps |A|.
+// Checked on the device against NumPy (tests/test_gpu_parity.py::test_eigh_*, tests/test_gpu_fullsize.py at n = 1532 and
+// n = 6248, tools/trieig_check.py, tools/eig_p4_debug.py): orthogonality and residual at the 1e-15 |A| level,
+// eigenvalues to a few eps |A|.
 #include <math.h>
 #include <stdlib.h>
 #include <string.h>
