@@ -384,7 +384,7 @@ __global__ void __launch_bounds__(256, 3) k_pair_blocks(const double* __restrict
                 v = __dadd_rn(v, -tr.penalty_sub);
                 if (ci == cj) v = __dadd_rn(v, flat_penalty);
             }
-            blk[(size_t)i * d.ld + j] = v;
+            __stcs(blk + (size_t)i * d.ld + j, v);  // streaming store: the blocks must not evict the tables from L2
         }
         tile[li][lj] = v;
     }
@@ -394,7 +394,7 @@ __global__ void __launch_bounds__(256, 3) k_pair_blocks(const double* __restrict
     for (int r = 0; r < 4; r++) {
         const int lj = ty + 8 * r;
         const int jj = bj * 32 + lj, ii = bi * 32 + tx;
-        if (jj < d.nB && ii < d.nA && ii < jj) blk[(size_t)jj * d.ld + ii] = tile[tx][lj];
+        if (jj < d.nB && ii < d.nA && ii < jj) __stcs(blk + (size_t)jj * d.ld + ii, tile[tx][lj]);
     }
 }
 
