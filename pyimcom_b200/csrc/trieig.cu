@@ -6,6 +6,7 @@
 // converges linearly, ~37 sweeps of 12 n^3 flops.  This solver does what LAPACK-class solvers do, arranged for the GPU
 // and batched over the OutStamps of a batch (one grid dimension = the system):
 //
+//   0. a matrix whose entries sit near the ends of the float64 range is scaled by a power of two first (dsyev's rule);
 //   1. Householder tridiagonalisation  A = Q T Q^T, blocked in panels of 64 columns (dlatrd / dsytrd arrangement): the
 //      trailing matrix is only read inside a panel and receives the panel's 128 rank-one updates as one DMMA GEMM
 //      (k_trib_reflect / k_trib_symv / k_trib_p, three launches per column, 8 n^3 / 3 bytes of traffic per system);
@@ -422,6 +423,60 @@ __global__ void __launch_bounds__(512) k_wy_tfactor(WyBatch wb, int p0) {
         const int r = e / NB, c = e - r * NB;
         w.T[e] = r <= c ? Ts[wy_pk(r, c)] : 0.0;
     }
+}
+
+// ---- scaling (what dsyev does): a matrix whose entries sit near the ends of the float64 range is brought to max |a| ~ 1
+// by a power of two before the reduction (squares of its entries would under- or overflow), and the eigenvalues are
+// scaled back at the end.  All on the device: k_eigh_absmax, k_eigh_scale (a no-op pass unless max |a| is outside
+// [1e-100, 1e100]), k_eigh_unscale.
+struct ScaleBatch {
+    double* A[MAXB];
+    double* lam[MAXB];
+    int lda[MAXB], n[MAXB];
+};
+__global__ void __launch_bounds__(256) k_eigh_absmax(ScaleBatch sb, double* amax) {
+    __shared__ double red[8];
+    const int q = blockIdx.y, n = sb.n[q];
+    const double* A = sb.A[q];
+    double m = 0.0;
+    const size_t tot = (size_t)n * n;
+    for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < tot; t += (size_t)gridDim.x * blockDim.x) {
+        const int i = (int)(t / n), j = (int)(t - (size_t)i * n);
+        const double v = fabs(A[(size_t)i * sb.lda[q] + j]);
+        if (v <= 1.7e308) m = fmax(m, v);  // (non-finite entries do not steer the scaling)
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int k = 1; k < 8; k++) m = fmax(m, red[k]);
+        atomicMax(reinterpret_cast<unsigned long long*>(amax + q), (unsigned long long)__double_as_longlong(m));
+    }
+}
+__device__ __forceinline__ double eigh_scale_factor(double amax) {
+    if (amax == 0.0 || (amax >= 1e-100 && amax <= 1e100)) return 1.0;
+    int ex;
+    frexp(amax, &ex);       // amax = f * 2^ex, 0.5 <= f < 1
+    return ldexp(1.0, -ex);  // exact power of two: the scaled matrix has the same significands
+}
+__global__ void __launch_bounds__(256) k_eigh_scale(ScaleBatch sb, const double* amax) {
+    const int q = blockIdx.y, n = sb.n[q];
+    const double sc = eigh_scale_factor(amax[q]);
+    if (sc == 1.0) return;
+    double* A = sb.A[q];
+    const size_t tot = (size_t)n * n;
+    for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < tot; t += (size_t)gridDim.x * blockDim.x) {
+        const int i = (int)(t / n), j = (int)(t - (size_t)i * n);
+        A[(size_t)i * sb.lda[q] + j] *= sc;
+    }
+}
+__global__ void __launch_bounds__(256) k_eigh_unscale(ScaleBatch sb, const double* amax) {
+    const int q = blockIdx.y, n = sb.n[q];
+    const double sc = eigh_scale_factor(amax[q]);
+    if (sc == 1.0) return;
+    const double inv = 1.0 / sc;  // (a power of two as well)
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) sb.lam[q][i] *= inv;
 }
 
 // max |G - I| of each system's Gram matrix (non-finite entries count as +inf); dev[] zeroed by the caller
@@ -922,6 +977,23 @@ int launch_tri_eigh_batch(const EighProblem* pr, int nsys, cudaStream_t st) {
     prof_begin(PROF_EIGH, st);
     StageTimer tm(st);
     int* qr_info = nullptr;
+    // scaling of badly scaled matrices (no-op passes for everything this path produces: max |a| = 1)
+    void* sc_ws = nullptr;
+    if (int rc = scratch(15, sizeof(double) * MAXB, &sc_ws)) return rc;
+    double* d_amax = static_cast<double*>(sc_ws);
+    ScaleBatch sbt;
+    for (int q = 0; q < MAXB; q++) {
+        const int qq = q < nsys ? q : 0;
+        sbt.A[q] = pr[qq].A;
+        sbt.lam[q] = pr[qq].lam;
+        sbt.lda[q] = pr[qq].lda;
+        sbt.n[q] = pr[qq].n;
+    }
+    B200_CUDA(cudaMemsetAsync(d_amax, 0, sizeof(double) * MAXB, st));
+    k_eigh_absmax<<<dim3(64, nsys), 256, 0, st>>>(sbt, d_amax);
+    k_eigh_scale<<<dim3(64, nsys), 256, 0, st>>>(sbt, d_amax);
+    B200_LAUNCHED(2);
+    B200_CUDA(cudaGetLastError());
     // copies of the matrices (the tridiagonalisation destroys them): only read again if the orthogonalisation fails
     void* acopy = nullptr;
     if (int rc = scratch(14, sizeof(double) * (size_t)ntot_max * ntot_max * nsys, &acopy)) return rc;
@@ -1178,6 +1250,8 @@ int launch_tri_eigh_batch(const EighProblem* pr, int nsys, cudaStream_t st) {
         }
         B200_CUDA(cudaGetLastError());
     }
+    k_eigh_unscale<<<dim3(8, nsys), 256, 0, st>>>(sbt, d_amax);
+    B200_LAUNCH_CHECK();
     return 0;
 }
 

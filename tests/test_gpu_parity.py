@@ -364,6 +364,53 @@ def test_tridiag_blocked_equals_unblocked_spectrum():
         assert np.abs(lt - np.linalg.eigvalsh(A)).max() < 1e-14 * max(np.abs(A).max(), 1.0) * n
 
 
+def _nasty_matrices():
+    rng = np.random.default_rng(77)
+
+    def rot(lam):
+        n = len(lam)
+        Q, _ = np.linalg.qr(rng.standard_normal((n, n)))
+        A = (Q * np.asarray(lam, dtype=np.float64)) @ Q.T
+        return 0.5 * (A + A.T)
+
+    n = 150
+    w = np.abs(np.arange(21) - 10.0)  # Wilkinson W21+: pairs of eigenvalues agreeing to ~1e-14
+    W21 = np.diag(w) + np.diag(np.ones(20), 1) + np.diag(np.ones(20), -1)
+    return {
+        "zero": np.zeros((40, 40)),
+        "identity": np.eye(70),
+        "diagonal_distinct": np.diag(np.linspace(-3.0, 5.0, 90)),
+        "diagonal_repeats": np.diag(np.repeat([1.0, 2.0, 2.0, 7.0, 7.0, 7.0], 20)),
+        "rank_one": np.outer(np.arange(1.0, 81.0), np.arange(1.0, 81.0)),
+        "exact_multiplicities": rot(np.repeat([0.0, 1e-9, 1.0, 1.0 + 1e-13, 3.0], n // 5)),
+        "wilkinson": W21,
+        "wilkinson_embedded": rot(np.concatenate([np.linalg.eigvalsh(W21), np.linspace(20, 30, 60)])),
+        "tiny_scale": 1e-200 * rot(np.logspace(-8, 0, n)),
+        "huge_scale": 1e150 * rot(np.logspace(-8, 0, n)),
+        "negative_definite": -rot(np.logspace(-12, 0, n)),
+        "indefinite_graded": rot(np.concatenate([-np.logspace(-14, -2, n // 2), np.logspace(-14, 0, n - n // 2)])),
+    }
+
+
+def test_eigh_on_degenerate_and_badly_scaled_matrices():
+    """The eigensolver must return a finite orthonormal eigenbasis for every symmetric input: exact multiplicities,
+    reducible (diagonal) matrices, the zero matrix, Wilkinson pairs, scales near the ends of the float64 range.
+    (Whether it gets there through inverse iteration or through the Jacobi fallback is reported, not asserted.)"""
+    mats = _nasty_matrices()
+    before = _lib.eigh_fallback_count()
+    res, _ = GL.eigh_device_batch([(_padded(A), A.shape[0]) for A in mats.values()])
+    print("fallbacks:", _lib.eigh_fallback_count() - before, "of", len(mats))
+    for (name, A), (lam, Vt) in zip(mats.items(), res):
+        n = A.shape[0]
+        lam, V = lam[:n].cpu().numpy(), Vt[:n, :n].cpu().numpy().T
+        assert np.isfinite(lam).all() and np.isfinite(V).all(), name
+        scale = np.abs(A).max()
+        tol = 1e-13 * scale * n + 1e-299  # (bisection brackets are never narrower than its 1e-300 pivot floor)
+        assert np.abs(np.sort(lam) - np.linalg.eigvalsh(A)).max() <= tol, name
+        assert np.abs(V.T @ V - np.eye(n)).max() < 1e-12, name
+        assert np.abs(A @ V - V * lam).max() <= tol, name
+
+
 def test_eigh_falls_back_to_jacobi_when_orthonormalisation_fails(monkeypatch):
     """B200_EIGH_TEST_FAIL gives every inverse-iteration thread the same shift: the vectors are linearly dependent, the
     Gram matrix of the Cholesky-QR stage is singular, and the system must be solved again by the Jacobi solver - never
