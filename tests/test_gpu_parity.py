@@ -239,6 +239,29 @@ def test_ozaki_gemm(M, N, K):
     assert torch.equal(Cm[M // 2], C0[M // 2])
 
 
+def test_ozaki_gemm_extreme_row_scales():
+    """Rows of A scaled by 1e+250 and rows of B by 1e-250 (and the reverse): the digit planes are taken relative to
+    power-of-two row scales, so the products come out to the same relative accuracy as for rows of order 1."""
+    M, N, K = 256, 128, 320
+    g = torch.Generator(device="cuda").manual_seed(5)
+    rnd = lambda *sh: torch.randn(sh, dtype=torch.float64, device="cuda", generator=g)  # noqa: E731
+    A, B = rnd(M, K), rnd(N, K)
+    A[: M // 2] *= 1e250
+    A[M // 2:] *= 1e-250
+    B[: N // 2] *= 1e-250
+    B[N // 2:] *= 1e-20
+    C0 = torch.zeros(M, N, dtype=torch.float64, device="cuda")
+    nbytes = int(_lib.lib.b200_ozaki_gemm_work_bytes(M, N, K))
+    work = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
+    Cm = C0.clone()
+    _lib.dev_ozaki_gemm_nt(GL.ptr(A), K, GL.ptr(B), K, GL.ptr(Cm), N, M, N, K, GL.ptr(work), nbytes, GL.stream_handle())
+    torch.cuda.synchronize()
+    assert bool(torch.isfinite(Cm).all())
+    bound = A.abs() @ B.abs().T
+    ok = bound > 1e-300  # (products of 1e-250 rows with 1e-250 rows underflow in float64 itself)
+    assert float(((Cm + A @ B.T).abs()[ok] / bound[ok]).max()) < 4e-15
+
+
 def test_sliced_int8_path_matches_dmma_path():
     """The batched Cholesky + solves with the long-K updates on the INT8 tensor cores (default) and on the DMMA pipe
     (B200_OZAKI=0 / no workspace) solve the same ill-conditioned system (cond 1e6, n = 1500: three super-panels, a
