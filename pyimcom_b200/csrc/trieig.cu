@@ -154,6 +154,17 @@ __global__ void __launch_bounds__(256) k_tri_update(TriBatch bt, int k) {
     }
 }
 
+// 1 / q to a couple of ulps for normal q of any magnitude: the hardware's 20-bit estimate (MUFU.RCP64H) and two Newton
+// steps - a third of the instructions of an IEEE division, which is what the Sturm sweeps are bound by (|q| >= 1e-300 by
+// construction, so neither the estimate nor the steps meet denormals or infinities).
+__device__ __forceinline__ double fast_rcp(double q) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(q));
+    r = fma(fma(-q, r, 1.0), r, r);
+    r = fma(fma(-q, r, 1.0), r, r);
+    return r;
+}
+
 // ---- eigenvalues of the tridiagonal matrix: bisection on Sturm counts, one thread per eigenvalue ----------------
 __global__ void __launch_bounds__(256) k_tri_bisect(TriBatch bt, double* const* lam_out) {
     extern __shared__ double sm[];  // d[n], e2[n]
@@ -200,7 +211,7 @@ __global__ void __launch_bounds__(256) k_tri_bisect(TriBatch bt, double* const* 
             if (fabs(q) < pivmin) q = -pivmin;
             cnt += q < 0.0;
             for (int i = 1; i < n; i++) {
-                q = d[i] - x - e2[i - 1] / q;
+                q = d[i] - x - e2[i - 1] * fast_rcp(q);
                 if (fabs(q) < pivmin) q = -pivmin;
                 cnt += q < 0.0;
             }
@@ -231,7 +242,7 @@ struct InvitSys {
     const double* e;
     const double* lam;
     double* Zt;       // (ntot, ldz): row j <- eigenvector j of T
-    double* scratch;  // 5 * n * nthr doubles: u0, u1, u2, multipliers, x  (element i of thread j at [i * nthr + j])
+    double* scratch;  // 5 * n * nthr doubles: 1 / u0, u1, u2, multipliers, x  (element i of thread j at [i * nthr + j])
     unsigned char* piv;  // n * nthr
     int n, ldz, nthr;
 };
@@ -275,7 +286,7 @@ __global__ void __launch_bounds__(128) k_tri_invit(InvitBatch bt, int stage) {
             if (back > 0) xs = s.lam[j - back] + back * sep;
         }
         if (stage & 2) xs = s.lam[n / 2];  // test hook (B200_EIGH_TEST_FAIL): every thread takes the same shift
-        const double tiny = eps * tn;
+        const double tiny = fmax(eps * tn, 1e-290);  // (normal: the reciprocals below flush denormals)
         // ---- factorisation (row i of the working pair is (a, b, c) = (diag, super1, super2)) ----
         double a = s.d[0] - xs, b = n > 1 ? s.e[0] : 0.0, c = 0.0;
         for (int i = 0; i < n - 1; i++) {
@@ -283,9 +294,10 @@ __global__ void __launch_bounds__(128) k_tri_invit(InvitBatch bt, int stage) {
             const double dn = s.d[i + 1] - xs, en = i + 2 < n ? s.e[i + 1] : 0.0;  // row i+1: (dn, en)
             double m;
             if (fabs(a) >= fabs(sub)) {  // no interchange
-                if (a == 0.0) a = tiny;
-                m = sub / a;
-                u0[i * st] = a;
+                if (fabs(a) < 1e-290) a = tiny;
+                const double ra = fast_rcp(a);
+                m = sub * ra;
+                u0[i * st] = ra;  // (the pivots are stored as reciprocals: the solves multiply)
                 u1[i * st] = b;
                 u2[i * st] = c;
                 pv[i * st] = 0;
@@ -293,8 +305,9 @@ __global__ void __launch_bounds__(128) k_tri_invit(InvitBatch bt, int stage) {
                 b = en - m * c;
                 c = 0.0;
             } else {  // rows i and i+1 swap
-                m = a / sub;
-                u0[i * st] = sub;
+                const double rs_ = fast_rcp(sub);
+                m = a * rs_;
+                u0[i * st] = rs_;
                 u1[i * st] = dn;
                 u2[i * st] = en;
                 pv[i * st] = 1;
@@ -304,8 +317,8 @@ __global__ void __launch_bounds__(128) k_tri_invit(InvitBatch bt, int stage) {
             }
             mm[i * st] = m;
         }
-        if (a == 0.0) a = tiny;
-        u0[(size_t)(n - 1) * st] = a;
+        if (fabs(a) < 1e-290) a = tiny;
+        u0[(size_t)(n - 1) * st] = fast_rcp(a);
         u1[(size_t)(n - 1) * st] = 0.0;
         u2[(size_t)(n - 1) * st] = 0.0;
         pv[(size_t)(n - 1) * st] = 0;
@@ -335,7 +348,7 @@ __global__ void __launch_bounds__(128) k_tri_invit(InvitBatch bt, int stage) {
     double x1 = 0.0, x2 = 0.0, big = 0.0, rs = 1.0;
     int epoch = 0;
     for (int i = n - 1; i >= 0; i--) {
-        double v = (x[i * st] * rs - u1[i * st] * x1 - u2[i * st] * x2) / u0[i * st];
+        double v = (x[i * st] * rs - u1[i * st] * x1 - u2[i * st] * x2) * u0[i * st];
         if (fabs(v) > 1e150 && epoch < 127) {
             v *= 1e-150;
             x1 *= 1e-150;
