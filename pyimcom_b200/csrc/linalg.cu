@@ -785,7 +785,8 @@ int launch_chol_solve(const SolveSys* h_sys, int nsys, int do_factor, int do_sol
                 b1 = b1 < nb ? b1 : nb;
                 if (r1 > r0 && b1 > b0) {
                     OzSliceSys j{s.W, s.ldw, r0 * NB, (r1 - r0) * NB, b0 * KB, (b1 - b0) * KB,
-                                 which == 0 ? ow[q].scaleL : ow[q].scaleU, ow[q].SLW, s.npad, which == 1};
+                                 which == 0 ? ow[q].scaleL : ow[q].scaleU, ow[q].SLW, s.npad, which == 1,
+                                 which == 1 ? ow[q].scaleL : nullptr, which == 1 ? 2 : 0};
                     sb.s[nj++] = j;
                     rows_max = j.nrows > rows_max ? j.nrows : rows_max;
                     nkb_max = j.nkb > nkb_max ? j.nkb : nkb_max;
@@ -804,8 +805,9 @@ int launch_chol_solve(const SolveSys* h_sys, int nsys, int do_factor, int do_sol
                 }
                 b1 = b1 < nb ? b1 : nb;
                 if (b1 > b0) {
+                    // (backward solve: the columns of Ti are balanced with the row scales of L, see OzSliceSys)
                     OzSliceSys j{s.X, s.ldx, 0, s.mpad, b0 * KB, (b1 - b0) * KB, ow[q].scaleX + (size_t)xc * s.mpad,
-                                 ow[q].SLX, s.mpad, 0};
+                                 ow[q].SLX, s.mpad, 0, from_end ? ow[q].scaleL : nullptr, from_end ? 1 : 0};
                     // (the scale array is indexed by absolute row; chunk xc has its own array)
                     sb.s[nj++] = j;
                     mx.s[nmx++] = j;

@@ -277,9 +277,18 @@ __global__ void __launch_bounds__(256) k_oz_scale_max(OzSliceBatch p) {
     const double* src = s.src + (size_t)(s.row0 + r) * s.ld + (size_t)s.kb0 * OZ_BK;
     const int ncol = s.nkb * OZ_BK;
     const int cfirst = s.tri ? ((s.row0 + r) / NB + 1) * NB - s.kb0 * OZ_BK : 0;
+    if (s.colmode == 2) {  // quotients by the column scales are bounded a priori: the row scale is 1
+        if (lane == 0) s.scale[s.row0 + r] = 1.0;
+        return;
+    }
+    const double* cs = s.colmode == 1 ? s.colscale + (size_t)s.kb0 * OZ_BK : nullptr;
     double m = 0.0;
     for (int c = (cfirst > 0 ? cfirst : 0) + lane * 2; c < ncol; c += 64) {
-        const double2 v = *reinterpret_cast<const double2*>(src + c);
+        double2 v = *reinterpret_cast<const double2*>(src + c);
+        if (cs) {
+            v.x *= cs[c];
+            v.y *= cs[c + 1];
+        }
         m = fmax(m, fmax(fabs(v.x), fabs(v.y)));
     }
 #pragma unroll
@@ -329,6 +338,14 @@ __global__ void __launch_bounds__(256) k_oz_slice(OzSliceBatch p) {
         const double2 v = *reinterpret_cast<const double2*>(src + j);
         x[j] = v.x * inv;
         x[j + 1] = v.y * inv;
+    }
+    if (s.colmode) {  // powers of two: exact
+        const double* cs = s.colscale + (size_t)kb * OZ_BK + c8;
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            const double c = cs[j];
+            x[j] *= s.colmode == 1 ? c : (c > 0.0 ? 1.0 / c : 0.0);
+        }
     }
     int8_t* dst = s.S + (((size_t)kb * OZ_NS) * s.rows_total + row) * OZ_BK + c8;
     // Round-to-nearest-integer by the magic-number addition (|x| < 2^51): the low word of x + 1.5 * 2^52 IS the integer

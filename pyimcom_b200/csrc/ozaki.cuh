@@ -46,6 +46,12 @@ struct OzSliceSys {
     int8_t* S;       // digit planes [.][NS][rows_total][64]
     int rows_total;
     int tri;         // 1: row r only owns the K chunks to the right of its own 128 x 128 diagonal block (rows of L^T)
+    // Column (K index) scaling by powers of two, exact: colmode 1 slices src[r][k] * colscale[k], colmode 2 slices
+    // src[r][k] / colscale[k] with the row scale fixed at 1 (the quotient is bounded by 64 by construction).  The backward
+    // solve pairs X[i][k] with L[k][j]: X's columns scale like 1 / sqrt(W_kk) and L's row k like sqrt(W_kk), so the
+    // balanced operands are X[i][k] s_k and L[k][j] / s_k with s_k the a-priori row scale of L.
+    const double* colscale;
+    int colmode;
 };
 
 struct OzSliceBatch {

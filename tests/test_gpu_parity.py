@@ -215,6 +215,52 @@ def test_chol_solve_random(n, m):
     assert rel(L @ L.T, A) < 1e-13
 
 
+@pytest.mark.parametrize("case", ["identity", "diagonal_16_decades", "scaled_1e-150", "scaled_1e+150", "graded_rows",
+                                  "rhs_zero_rows"])
+def test_chol_solve_special_systems(case):
+    """The batched Cholesky + triangular solves (long-K updates on the sliced INT8 path: n = 1300 has three super-panels)
+    on systems that stress the digit-plane scales: trivial factors, diagonal entries over 16 decades, entries near the
+    ends of the float64 range, symmetric row / column scaling D A D, right-hand sides with all-zero rows."""
+    from scipy.linalg import cho_solve, cholesky
+
+    rng = np.random.default_rng(42)
+    n, m = 1300, 150
+    Q, _ = np.linalg.qr(rng.standard_normal((n, n)))
+    base = (Q * np.logspace(-4, 0, n)) @ Q.T
+    base = 0.5 * (base + base.T)
+    B = rng.standard_normal((m, n))
+    if case == "identity":
+        A = np.eye(n)
+    elif case == "diagonal_16_decades":
+        A = np.diag(np.logspace(-8, 8, n))
+    elif case == "scaled_1e-150":
+        A = 1e-150 * base
+    elif case == "scaled_1e+150":
+        A = 1e150 * base
+    elif case == "graded_rows":
+        d = np.logspace(-6, 6, n)[rng.permutation(n)]
+        A = d[:, None] * base * d[None, :]
+    else:
+        A = base
+        B[::7] = 0.0
+    ref = cho_solve((cholesky(A, lower=True), True), B.T).T
+    ds = GL.upload_system(A, B[None], [1.0], 1)
+    W = GL._padded_system(ds, [])
+    X = ds.mB[0].clone()
+    info, _k = GL.chol_solve_batch([W], [X])
+    assert int(info.item()) == 0
+    got = X[:m, :n].cpu().numpy()
+    assert np.isfinite(got).all()
+    # row by row: the rows of the solution differ by many decades in the scaled cases
+    num = np.abs(got - ref).max(axis=1)
+    den = np.maximum(np.abs(ref).max(axis=1), 1e-300)
+    assert (num / den).max() < 1e-8, (num / den).max()
+    if case == "rhs_zero_rows":
+        assert not got[::7].any()
+    L = np.tril(W[:n, :n].cpu().numpy())
+    assert np.abs(L @ L.T - A).max() <= 1e-13 * np.abs(A).max() * (1e4 if case in ("graded_rows", "diagonal_16_decades") else 1)
+
+
 @pytest.mark.parametrize("M,N,K", [(128, 64, 64), (256, 192, 448), (1024, 512, 2048)])
 def test_ozaki_gemm(M, N, K):
     """b200_dev_ozaki_gemm_nt: C -= A B^T from error-free INT8 digit planes on tcgen05 (csrc/ozaki.cu) against the float64
