@@ -355,6 +355,38 @@ def test_legacy_tile_path():
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
 
 
+def test_chol_solve_batch_of_unequal_systems_with_a_failing_one():
+    """One batched call over systems of different sizes (one, three and six block columns past the super-panel width,
+    right-hand sides with and without a half tile) and one matrix that is NOT positive definite: every healthy system
+    comes out as if solved alone, the failing one reports its LAPACK info code and stays finite."""
+    from scipy.linalg import cho_solve, cholesky
+
+    rng = np.random.default_rng(8)
+    shapes = [(300, 50), (1300, 200), (900, 129), (1300, 64), (128, 128)]
+    Ws, Xs, refs = [], [], []
+    for k, (n, m) in enumerate(shapes):
+        Q, _ = np.linalg.qr(rng.standard_normal((n, n)))
+        A = (Q * np.logspace(-5, 0, n)) @ Q.T
+        A = 0.5 * (A + A.T)
+        if k == 3:
+            A[700, 700] = -0.5  # not positive definite: the pivot of row 700 (or an earlier one) fails
+        B = rng.standard_normal((m, n))
+        ds = GL.upload_system(A, B[None], [1.0], 1)
+        Ws.append(GL._padded_system(ds, []))
+        Xs.append(ds.mB[0].clone())
+        refs.append(None if k == 3 else cho_solve((cholesky(A, lower=True), True), B.T).T)
+    info, _k = GL.chol_solve_batch(Ws, Xs)
+    info = info.cpu().numpy()
+    for k, (n, m) in enumerate(shapes):
+        got = Xs[k][:m, :n].cpu().numpy()
+        assert np.isfinite(got).all(), k
+        if k == 3:
+            assert 0 < info[k] <= 701
+        else:
+            assert info[k] == 0
+            assert rel(got, refs[k]) < 1e-9, (k, rel(got, refs[k]))
+
+
 def test_chol_info_nonpd():
     A = np.eye(200)
     A[150, 150] = -1.0
