@@ -540,6 +540,9 @@ class ApplySpec:
     want_Ti64: bool = False
 
 
+FINALIZE_MAX_LAYERS = 16  # input layers per k_finalize launch (two DMMA passes of 8)
+
+
 def apply_T(ds: DeviceSystem, ko: KernelOutput, j_out: int, spec: ApplySpec):
     """finalize + maps for one output PSF: returns a dict of device tensors.
 
@@ -575,7 +578,16 @@ def apply_T(ds: DeviceSystem, ko: KernelOutput, j_out: int, spec: ApplySpec):
     a.D, a.N = D.data_ptr(), N.data_ptr()
     a.outimage = outimage.data_ptr()
     a.Tsum_image = Tsum_image.data_ptr()
+    a.n_inframe = min(nfr, FINALIZE_MAX_LAYERS)
     _lib.dev_finalize(C.byref(a), st)
+    # more input layers than one launch takes (16): the remaining ones in further passes over the node solutions, which
+    # write the same T / D / N / Tsum again and the coadded images of their own layers
+    for f0 in range(FINALIZE_MAX_LAYERS, nfr, FINALIZE_MAX_LAYERS):
+        a.T32, a.ldt32, a.Ti64, a.ldt64 = None, 0, None, 0
+        a.indata = spec.indata.data_ptr() + 4 * f0 * spec.indata.stride(0)
+        a.outimage = outimage.data_ptr() + 4 * f0 * m
+        a.n_inframe = min(nfr - f0, FINALIZE_MAX_LAYERS)
+        _lib.dev_finalize(C.byref(a), st)
     kappa, Sigma, UC = ko.kappa, ko.Sigma, ko.UC
     if kappa is None:  # single kappa: maps from D and N (lakernel.py:312-316, 643-648)
         kappa, Sigma, UC = _f64(m), _f64(m), _f64(m)

@@ -734,6 +734,27 @@ def test_block_run_maps():
     assert rel(maps["UC_map"], UC) < 5e-6
 
 
+@pytest.mark.parametrize("nfr", [9, 19])
+def test_many_input_layers(nfr):
+    """More input layers than one DMMA pass (8) and than one T-apply launch (16) takes: every coadded layer equals the
+    oracle's (the reference's einsum over any number of layers, coadd.py:1339-1350)."""
+    spec = dict(cases.BLOCK_CASES["chol1"])
+    spec["cfg"] = dict(spec["cfg"], n_inframe=nfr)
+    blk = cases.make_block(spec)
+    tab = PSFTables(blk, G.iD5512C, G.gridD5512C)
+    j, i = spec["stamps"][0]
+    s = GpuOutStamp(GpuBlock(blk, tab).prepare(stamps=[(j, i)]), j, i)
+    o = OracleOutStamp(blk, PSFTables(blk, R.iD5512C, R.gridD5512C), j, i)
+    o.build_system_matrices()
+    OL.CholKernel(o)()
+    o.post_kernel()
+    o.perform_coaddition()
+    assert s.outimage.shape == o.outimage.shape and s.outimage.shape[1] == nfr
+    for f in range(nfr):
+        assert rel(s.outimage[:, f], o.outimage[:, f]) < 5e-6, f
+    assert rel(s.T, o.T) < 2e-6
+
+
 def test_strip_sharded_block_equals_unsharded():
     """SURVEY 8e, single-block sharding: the block coadded as two strips of 2x2 stamp-group rows (shard.
     assign_stamp_groups; each strip adds into its own zero-initialised cube, the cubes are summed as shard.reduce_cube
