@@ -32,15 +32,16 @@ __global__ void __launch_bounds__(CT) k_iter_cg(const double* __restrict__ AA, i
                                                 double rho_acc, double rtol,
                                                 int maxiter, double* __restrict__ Ti, int ldt,
                                                 int* __restrict__ niter, int* __restrict__ nsel,
-                                                const int* __restrict__ only /* nullable: process a only if only[a] */) {
+                                                const int* __restrict__ only /* nullable: process a only if only[a] */,
+                                                int ncap /* capacity of the per-pixel vectors (accepted inputs) */) {
     extern __shared__ __align__(16) double sm[];
     if (only && !only[blockIdx.x]) return;
     double* red = sm;           // 40
-    double* r = sm + 40;        // n
-    double* p = r + n;          // n
-    double* q = p + n;          // n
-    double* x = q + n;          // n
-    int* sel = reinterpret_cast<int*>(x + n);  // n
+    double* r = sm + 40;        // ncap
+    double* p = r + ncap;       // ncap
+    double* q = p + ncap;       // ncap
+    double* x = q + ncap;       // ncap
+    int* sel = reinterpret_cast<int*>(x + ncap);  // ncap
     __shared__ int wcount[CT / 32];
     __shared__ int sbase;
     const int a = blockIdx.x;
@@ -58,7 +59,10 @@ __global__ void __launch_bounds__(CT) k_iter_cg(const double* __restrict__ AA, i
         __syncthreads();
         int off = sbase;
         for (int w = 0; w < warp; w++) off += wcount[w];
-        if (ok) sel[off + __popc(bal & ((1u << lane) - 1u))] = i;
+        if (ok) {
+            const int pos = off + __popc(bal & ((1u << lane) - 1u));
+            if (pos < ncap) sel[pos] = i;
+        }
         __syncthreads();
         if (tid == 0) {
             int t = 0;
@@ -68,6 +72,10 @@ __global__ void __launch_bounds__(CT) k_iter_cg(const double* __restrict__ AA, i
         __syncthreads();
     }
     const int na = sbase;
+    if (na > ncap) {  // more accepted input pixels than the shared-memory vectors hold: reported, never truncated
+        if (tid == 0 && niter) niter[a] = -1;
+        return;
+    }
     // ---- CG ----
     const double* brow = mB + (size_t)a * ldb;
     double nb2 = 0.0;
@@ -362,12 +370,16 @@ __global__ void __launch_bounds__(CT) k_iter_cg_tile(const double* __restrict__ 
 
 }  // namespace
 
+constexpr int ITER_NCAP = 6100;
+
 int launch_iter_cg(const double* AA, int lda, double diag_add, const double* mB, int ldb, int m, int n,
                    const double* inx, const double* iny, const double* outx, const double* outy, double rho_acc,
                    double rtol, int maxiter, double* Ti, int ldt, int* niter, int* nsel, cudaStream_t s) {
     if (m <= 0 || n <= 0) return 0;
-    const size_t smem1 = sizeof(double) * (40 + 4 * (size_t)n) + sizeof(int) * (size_t)n + 16;
-    B200_REQUIRE(smem1 <= 220 * 1024, "iter_cg: n too large for the shared-memory CG vectors (n <= ~6200)");
+    // per-pixel kernel: four CG vectors + the index list of the ACCEPTED input pixels (those within rho_acc of the output
+    // pixel) in shared memory; at most ITER_NCAP of them (a pixel that accepts more gets niter = -1 and the host raises)
+    const int ncap = n < ITER_NCAP ? n : ITER_NCAP;
+    const size_t smem1 = sizeof(double) * (40 + 4 * (size_t)ncap) + sizeof(int) * (size_t)ncap + 16;
     // tile kernel: union of TP accepted sets, at most namax entries (4 vectors x TP doubles + index + mask per entry)
     int namax = (n + 7) / 8 * 8;
     if (namax > 1400) namax = 1400;
@@ -390,7 +402,7 @@ int launch_iter_cg(const double* AA, int lda, double diag_add, const double* mB,
     }
     // per-pixel kernel: every pixel (tiling off) or only those whose tile overflowed
     k_iter_cg<<<m, CT, smem1, s>>>(AA, lda, diag_add, mB, ldb, m, n, inx, iny, outx, outy, rho_acc, rtol, maxiter, Ti,
-                                   ldt, niter, nsel, tiled ? redo : nullptr);
+                                   ldt, niter, nsel, tiled ? redo : nullptr, ncap);
     prof_end(8.0 * m * (double)n * 2.0, s);  // bytes: mBhalf rows read + Ti rows written (A_sel gathers hit L2)
     B200_LAUNCH_CHECK();
     return 0;

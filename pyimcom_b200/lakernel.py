@@ -434,6 +434,9 @@ def solve_eigen(ds: DeviceSystem, cfg, j_out: int, eig=None, nbis: int = 13) -> 
                         extras=dict(lam=lam, sweeps=sweeps))
 
 
+ITER_NCAP = 6100  # accepted input pixels per output pixel the CG kernel holds (csrc/iter.cu)
+
+
 def solve_iter(ds: DeviceSystem, cfg, j_out: int, exact_UC=None) -> KernelOutput:
     """IterKernel for one output PSF (lakernel.py:592-744)."""
     assert ds.px is not None and ds.py is not None, "IterKernel needs the input pixel positions"
@@ -457,6 +460,9 @@ def solve_iter(ds: DeviceSystem, cfg, j_out: int, exact_UC=None) -> KernelOutput
         _lib.dev_iter_cg(ptr(AA), AA.stride(0), 0.0, ptr(mB), mB.stride(0), m, n, ptr(ds.px), ptr(ds.py), ptr(ds.outx),
                          ptr(ds.outy), float(rho), float(cfg.iter_rtol), int(cfg.iter_max),
                          ptr(Tpi[p]), Tpi.stride(1), ptr(niter[p]), ptr(nsel[p]), st)
+    if n > ITER_NCAP and int(niter.min().item()) < 0:
+        raise _lib.B200Error(f"IterKernel: an output pixel accepts more than {ITER_NCAP} input pixels within rho_acc = "
+                             f"{rho:.3f} (n = {n}); the conjugate-gradient kernel keeps its vectors in shared memory")
     if exact_UC is None:
         exact_UC = nv > 1  # defaults of the reference (lakernel.py:592, 656)
 

@@ -219,6 +219,33 @@ def test_eigen_kernel_at_paper4_size_equals_the_reference_cholesky_golden():
     assert e["UC_abs"] < 1e-4
 
 
+def test_iter_kernel_with_more_input_pixels_than_the_cg_vectors_hold():
+    """IterKernel on the paper-4 stamp of bench.py (n = 6248 selected input pixels: more than the 6100 the per-pixel CG
+    kernel could keep in shared memory if it sized its vectors by n; it sizes them by the accepted set, the ~1 k pixels
+    within rho_acc).  The CPU oracle needs > 1 min for this stamp, so the result is checked through the CG stopping rule
+    on the true residual, ||A_sel x - b|| <= rtol ||b|| (lakernel.py:397-443), at kappa / C = 1 where CG is well posed."""
+    spec = dict(cases.FULL_CASES["p4"])
+    spec["cfg"] = dict(spec["cfg"], linear_algebra="Iterative", kappaC_arr=[1.0], iter_rtol=1.5e-3, iter_max=30)
+    cases.FULL_CASES["p4_iter"] = spec
+    try:
+        s, blk = gpu_full_stamp("p4_iter")
+    finally:
+        del cases.FULL_CASES["p4_iter"]
+    cfg = blk.cfg
+    n = s.T.shape[-1]
+    assert n > GL.ITER_NCAP
+    niter = s.extras[0]["niter"].ravel()
+    assert niter.min() >= 1 and niter.max() < cfg.iter_max  # converged everywhere, no overflow flag (-1)
+    Tg = s.Ti64[0] if s.Ti64 is not None else s.T[0].astype(np.float64)
+    W = s.sysmata + 1.0 * float(np.asarray(s.outovlc).ravel()[0]) * np.eye(n)  # kappa = (kappa / C) C, unfaded
+    mB = s.mhalfb[0]
+    for a in range(0, cfg.n2f**2, 37):
+        sel = np.nonzero(Tg[a])[0]  # the accepted input pixels of this output pixel
+        assert 100 < sel.size < GL.ITER_NCAP
+        r = W[np.ix_(sel, sel)] @ Tg[a, sel] - mB[a, sel]
+        assert np.linalg.norm(r) <= 1.02 * cfg.iter_rtol * np.linalg.norm(mB[a, sel]), a
+
+
 def test_config3_inside_the_cg_spread():
     """Config 3 (IterKernel, kappa = 0, 24-30 CG iterations per output pixel).  tests/test_oracle_golden.py::
     test_cg_sensitivity shows that the reference's procedure amplifies a 1e-15 relative perturbation of A to ~1e-2 on T
