@@ -831,6 +831,24 @@ def test_pipelined_batches_equal_single_batch():
             assert np.array_equal(got[k], want[k]), (k, streams, tiny_pool)
 
 
+@pytest.mark.parametrize("kernel,kappaC", [("Eigen", [1e-5, 1e-4, 1e-3]), ("Eigen", [5e-4]), ("Iterative", [1e-2])])
+def test_eigen_and_iter_blocks_batched_equal_stamp_by_stamp(kernel, kappaC):
+    """GpuBlock.run() with the Eigen / Iterative kernels: the whole block in batches of 16 (one batched eigendecomposition
+    over stamps of different sizes) against the same block coadded one stamp per batch."""
+    spec = dict(cases.BLOCK_CASES["pad4"], kernel=kernel, kappaC=kappaC)
+    blk = cases.make_block(spec)
+    tab = PSFTables(blk, G.iD5512C, G.gridD5512C)
+    one = GpuBlock(blk, tab).prepare()
+    one.run(batch=1)
+    want = one.download()
+    gb = GpuBlock(blk, tab).prepare()
+    gb.run(batch=16)
+    got = gb.download()
+    for k in want:
+        scale = max(np.abs(want[k]).max(), 1e-30)
+        assert np.abs(got[k].astype(np.float64) - want[k]).max() <= 5e-6 * scale, k
+
+
 def test_repair_branch_survives_pool_eviction():
     """The eigen-shift repair of CholKernel._cholesky_wrapper (lakernel.py:262-279) re-assembles A from the cached
     InStamp-pair blocks.  In the pipelined run the blocks of batch k+1 are requested before batch k is finished; with a
