@@ -849,6 +849,31 @@ def test_eigen_and_iter_blocks_batched_equal_stamp_by_stamp(kernel, kappaC):
         assert np.abs(got[k].astype(np.float64) - want[k]).max() <= 5e-6 * scale, k
 
 
+@pytest.mark.parametrize("kernel,kappaC,tol", [("Eigen", [1e-5, 1e-4, 1e-3], 2e-5), ("Eigen", [5e-4], 2e-5),
+                                               ("Iterative", [1e-2], 1e-3), ("Cholesky", [1e-5, 1e-4, 1e-3], 2e-6)])
+def test_two_output_psfs_with_every_kernel(kernel, kappaC, tol):
+    """n_out = 2 with PSF splitting and a flat penalty (the nout2split block) through the Eigen, Iterative and multi-kappa
+    Cholesky kernels: one decomposition / one system matrix serves both output PSFs (lakernel.py:154-223, 281-394,
+    592-744); every output PSF against the oracle."""
+    spec = dict(cases.BLOCK_CASES["nout2split"], kernel=kernel, kappaC=kappaC)
+    blk = cases.make_block(spec)
+    tab = PSFTables(blk, G.iD5512C, G.gridD5512C)
+    j, i = spec["stamps"][0]
+    s = GpuOutStamp(GpuBlock(blk, tab).prepare(stamps=[(j, i)]), j, i)
+    o = OracleOutStamp(blk, PSFTables(blk, R.iD5512C, R.gridD5512C), j, i)
+    o.build_system_matrices()
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        {"Eigen": OL.EigenKernel, "Iterative": OL.IterKernel, "Cholesky": OL.CholKernel}[kernel](o)()
+    o.post_kernel()
+    o.perform_coaddition()
+    assert s.T.shape[0] == 2
+    for j_out in range(2):
+        assert rel(s.T[j_out], o.T[j_out]) < tol, j_out
+        assert rel(s.outimage[j_out], o.outimage[j_out]) < 5 * tol, j_out
+        assert rel(s.Sigma[j_out], o.Sigma[j_out]) < 5 * tol and rel(s.kappa[j_out], o.kappa[j_out]) < 5 * tol, j_out
+
+
 def test_repair_branch_survives_pool_eviction():
     """The eigen-shift repair of CholKernel._cholesky_wrapper (lakernel.py:262-279) re-assembles A from the cached
     InStamp-pair blocks.  In the pipelined run the blocks of batch k+1 are requested before batch k is finished; with a
