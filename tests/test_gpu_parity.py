@@ -874,6 +874,33 @@ def test_two_output_psfs_with_every_kernel(kernel, kappaC, tol):
         assert rel(s.Sigma[j_out], o.Sigma[j_out]) < 5 * tol and rel(s.kappa[j_out], o.kappa[j_out]) < 5 * tol, j_out
 
 
+@pytest.mark.parametrize("over,n_image", [(dict(oversamp=7, npixpsf=14), 2), (dict(oversamp=5, npixpsf=20), 3),
+                                          (dict(), 1), (dict(), 7), (dict(fade_kernel=0), 2), (dict(fade_kernel=3), 2),
+                                          (dict(n2=9), 2)])
+def test_unusual_geometries(over, n_image):
+    """Shapes the other cases do not visit: oversampling factors without a polyphase specialisation (7) and with one (5),
+    a single input image, seven input images, no fade margin, a fade margin of 3, an odd stamp size.  A, -B/2, T and the
+    coadded layers of one interior stamp against the oracle, through the cached pair blocks (GpuBlock) and the fused
+    assembly (a_cache off)."""
+    spec = dict(cases.BLOCK_CASES["pad4"])
+    spec["cfg"] = dict(spec["cfg"], **over)
+    spec["n_image"] = n_image
+    blk = cases.make_block(spec)
+    j, i = 2, 2
+    o = OracleOutStamp(blk, PSFTables(blk, R.iD5512C, R.gridD5512C), j, i)
+    o.build_system_matrices()
+    OL.CholKernel(o)()
+    o.post_kernel()
+    o.perform_coaddition()
+    for a_cache in (True, False):
+        gb = GpuBlock(blk, PSFTables(blk, G.iD5512C, G.gridD5512C))
+        gb.a_cache = a_cache
+        s = GpuOutStamp(gb.prepare(stamps=[(j, i)]), j, i)
+        assert np.array_equal(np.asarray(s.inpix_cumsum), np.asarray(o.inpix_cumsum))
+        assert rel(s.sysmata, o.sysmata) < 1e-9 and rel(s.mhalfb, o.mhalfb) < 1e-9, a_cache
+        assert rel(s.T, o.T) < 2e-6 and rel(s.outimage, o.outimage) < 1e-5, a_cache
+
+
 def test_repair_branch_survives_pool_eviction():
     """The eigen-shift repair of CholKernel._cholesky_wrapper (lakernel.py:262-279) re-assembles A from the cached
     InStamp-pair blocks.  In the pipelined run the blocks of batch k+1 are requested before batch k is finished; with a
