@@ -666,7 +666,7 @@ def test_pair_block_cache_is_bit_identical(name):
         assert cached.pair_points < tot
 
 
-@pytest.mark.parametrize("name", ["chol1", "pad4", "nout2split", "amp"])
+@pytest.mark.parametrize("name", ["chol1", "pad4", "nout2split", "amp", "oversamp7", "oversamp5_3img", "one_image"])
 def test_device_tables(name):
     """PSF-overlap tables built on the device (device iD5512C sampling + partial DFTs as DMMA
     products) equal the NumPy-FFT tables of the host builder, and a block coadded from them equals the oracle."""
@@ -674,6 +674,12 @@ def test_device_tables(name):
 
     if name == "amp":  # amplitude penalty on the Fourier modes (psfutil.py:661-671) + circular cut + normalisation
         spec = dict(cases.BLOCK_CASES["chol1"], cfg=dict(cases._MINI, amp_penalty=(0.5, 0.8), psf_circ=True, psf_norm=True))
+    elif name == "oversamp7":  # sizes with no factor of two anywhere: ns, nfft and the kept lags are odd
+        spec = dict(cases.BLOCK_CASES["chol1"], cfg=dict(cases._MINI, oversamp=7, npixpsf=14))
+    elif name == "oversamp5_3img":
+        spec = dict(cases.BLOCK_CASES["chol1"], cfg=dict(cases._MINI, oversamp=5, npixpsf=20), n_image=3)
+    elif name == "one_image":
+        spec = dict(cases.BLOCK_CASES["chol1"], n_image=1)
     else:
         spec = cases.BLOCK_CASES[name]  # "nout2split": PSF splitting, kept lags 2 ns + 1, two output PSFs
     blk = cases.make_block(spec)
