@@ -25,9 +25,12 @@ def _stale(target, deps):
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
+def build(force: bool = False, verbose: bool = False, tag: str = "", extra_flags=()) -> str:
+    """tag / extra_flags: an A/B build beside the product library (lib/libpyimcom_b200_<tag>.so, loaded with
+    B200_LIB=...), e.g. ``build(tag="ozcap", extra_flags=["-DB200_OZ_LB=512"])``."""
     os.makedirs(LIBDIR, exist_ok=True)
-    objdir = os.path.join(LIBDIR, "obj")
+    objdir = os.path.join(LIBDIR, "obj" + ("_" + tag if tag else ""))
+    LIB = os.path.join(LIBDIR, f"libpyimcom_b200{'_' + tag if tag else ''}.so")
     os.makedirs(objdir, exist_ok=True)
     headers = [os.path.join(CSRC, h) for h in os.listdir(CSRC) if h.endswith((".h", ".cuh"))]
     headers.append(os.path.join(os.path.dirname(HERE), "include", "pyimcom_b200.h"))
@@ -37,7 +40,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         s = os.path.join(CSRC, src)
         o = os.path.join(objdir, src[:-3] + ".o")
         if force or _stale(o, [s] + headers):
-            cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o]
+            cmd = [nvcc] + NVCC_FLAGS + list(extra_flags) + (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o]
             r = subprocess.run(cmd, capture_output=True, text=True)
             if verbose or r.returncode:
                 sys.stderr.write(r.stdout + r.stderr)
@@ -53,4 +56,6 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    _tag = next((a.split("=", 1)[1] for a in sys.argv if a.startswith("--tag=")), "")
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, tag=_tag,
+                extra_flags=[a for a in sys.argv[1:] if a.startswith("-D")]))

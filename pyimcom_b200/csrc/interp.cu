@@ -4,6 +4,8 @@
 //
 // Arithmetic follows routine.py statement by statement (inner sum over x taps then outer over y
 // taps) with fused multiply-adds; see the note at d5512_getw.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -325,29 +327,30 @@ __global__ void __launch_bounds__(256) k_build_A(const double* __restrict__ px, 
 // through its pixel selections.  Entry values, table choice, flips and the upper-triangle-then-mirror rule inside
 // a self block are those of k_build_A, so both routes give bit-identical matrices.
 // ------------------------------------------------------------------------------------------------
-template <int P>
-__global__ void __launch_bounds__(256, 3) k_pair_blocks(const double* __restrict__ gx, const double* __restrict__ gy,
-                                                     const int* __restrict__ gimg, const PairDesc* __restrict__ descs,
-                                                     const int* __restrict__ tile_prefix, int npair,
-                                                     const double* __restrict__ tables,
-                                                     const TableRef* __restrict__ lut, int nimg, int ngrid,
-                                                     double dscale, double nc, double flat_penalty,
-                                                     double* __restrict__ pool) {
-    __shared__ double tile[32][33];
-    // which pair does this tile belong to: largest q with tile_prefix[q] <= blockIdx.x
+// One 32 x 32 tile of the pair-block list, by NT threads (NT / 32 warps, 1024 / NT entries per thread).  Returns true
+// when the shared tile was read back (self block: the caller has to synchronise before the tile is written again).
+template <int P, int NT>
+__device__ __forceinline__ bool pair_tile(int tile_idx, double (*tile)[33], const double* __restrict__ gx,
+                                          const double* __restrict__ gy, const int* __restrict__ gimg,
+                                          const PairDesc* __restrict__ descs, const int* __restrict__ tile_prefix,
+                                          int npair, const double* __restrict__ tables,
+                                          const TableRef* __restrict__ lut, int nimg, int ngrid, double dscale,
+                                          double nc, double flat_penalty, double* __restrict__ pool) {
+    constexpr int NW = NT / 32, NR = 1024 / NT;
+    // which pair does this tile belong to: largest q with tile_prefix[q] <= tile_idx
     int lo = 0, hi = npair - 1;
     while (lo < hi) {
         const int mid = (lo + hi + 1) >> 1;
-        if (tile_prefix[mid] <= (int)blockIdx.x)
+        if (tile_prefix[mid] <= tile_idx)
             lo = mid;
         else
             hi = mid - 1;
     }
     const PairDesc d = descs[lo];
-    const int t = blockIdx.x - tile_prefix[lo];
+    const int t = tile_idx - tile_prefix[lo];
     const int ntj = (d.nB + 31) >> 5;
     const int bi = t / ntj, bj = t - bi * ntj;
-    if (d.same && bj < bi) return;  // self block: upper tiles only, mirrored below
+    if (d.same && bj < bi) return false;  // self block: upper tiles only, mirrored below
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     // A warp covers a 4 x 8 patch of the tile (4 consecutive pixels i, 8 consecutive pixels j), not one row of 32:
     // consecutive pixels of one image row are P table samples apart, so entry (i+1, j+1) reads (almost) the window of
@@ -357,8 +360,8 @@ __global__ void __launch_bounds__(256, 3) k_pair_blocks(const double* __restrict
     double* blk = pool + d.out;
     const TableRef* plut = lut + (size_t)d.lut * nimg * nimg;
 #pragma unroll
-    for (int r = 0; r < 4; r++) {
-        const int sub = ty + 8 * r;             // 32 patches per tile: 8 patch rows x 4 patch columns
+    for (int r = 0; r < NR; r++) {
+        const int sub = ty + NW * r;            // 32 patches per tile: 8 patch rows x 4 patch columns
         const int li = 4 * (sub >> 2) + pli;    // local row 0..31
         const int lj = 8 * (sub & 3) + plj;     // local column 0..31
         const int i = bi * 32 + li, j = bj * 32 + lj;
@@ -388,14 +391,51 @@ __global__ void __launch_bounds__(256, 3) k_pair_blocks(const double* __restrict
         }
         tile[li][lj] = v;
     }
-    if (!d.same) return;
+    if (!d.same) return false;
     __syncthreads();
 #pragma unroll
-    for (int r = 0; r < 4; r++) {
-        const int lj = ty + 8 * r;
+    for (int r = 0; r < NR; r++) {
+        const int lj = ty + NW * r;
         const int jj = bj * 32 + lj, ii = bi * 32 + tx;
         if (jj < d.nB && ii < d.nA && ii < jj) __stcs(blk + (size_t)jj * d.ld + ii, tile[tx][lj]);
     }
+    return true;
+}
+
+template <int P>
+__global__ void __launch_bounds__(256, 3) k_pair_blocks(const double* __restrict__ gx, const double* __restrict__ gy,
+                                                     const int* __restrict__ gimg, const PairDesc* __restrict__ descs,
+                                                     const int* __restrict__ tile_prefix, int npair,
+                                                     const double* __restrict__ tables,
+                                                     const TableRef* __restrict__ lut, int nimg, int ngrid,
+                                                     double dscale, double nc, double flat_penalty,
+                                                     double* __restrict__ pool) {
+    __shared__ double tile[32][33];
+    pair_tile<P, 256>((int)blockIdx.x, tile, gx, gy, gimg, descs, tile_prefix, npair, tables, lut, nimg, ngrid, dscale, nc,
+                      flat_penalty, pool);
+}
+
+// The same tiles by a SMALL resident grid (B200_PAIR_RESIDENT = CTAs of 128 threads per SM, each walking the tile list
+// with the grid's stride): an EXPERIMENT, off by default (tools/coresident_check.py).  The block
+// scheduler hands out the CTAs of one grid before it turns to the next, so a grid of thousands of tiles never shares an
+// SM with another stream's kernel; a grid that is resident at once does, and one such CTA (88 registers x 128 threads,
+// 8 KB of shared memory) fits beside a k_oz_gemm CTA.  Measured: it does run there, but makes 7 % of its standalone
+// progress while slowing the GEMM by 18 %, and with 4 warps per SM it is latency-bound (54 ms per launch against
+// 10.5 ms for one CTA per tile).  Same entries, same arithmetic: bit-identical blocks.
+template <int P>
+__global__ void __maxnreg__(88) k_pair_blocks_resident(const double* __restrict__ gx, const double* __restrict__ gy,
+                                                              const int* __restrict__ gimg,
+                                                              const PairDesc* __restrict__ descs,
+                                                              const int* __restrict__ tile_prefix, int npair, int ntiles,
+                                                              const double* __restrict__ tables,
+                                                              const TableRef* __restrict__ lut, int nimg, int ngrid,
+                                                              double dscale, double nc, double flat_penalty,
+                                                              double* __restrict__ pool) {
+    __shared__ double tile[32][33];
+    for (int t = blockIdx.x; t < ntiles; t += gridDim.x)
+        if (pair_tile<P, 128>(t, tile, gx, gy, gimg, descs, tile_prefix, npair, tables, lut, nimg, ngrid, dscale, nc,
+                              flat_penalty, pool))
+            __syncthreads();
 }
 
 // One OutStamp's A (npad x lda) from cached pair blocks.  Stamp pixel k (0 <= k < n) is pixel gidx[k] of the block's
@@ -842,10 +882,35 @@ int launch_pair_blocks(const double* gx, const double* gy, const int* gimg, cons
                        int nimg, int ngrid, double dscale, double nc, double flat_penalty, int poly, double* pool,
                        double points, cudaStream_t s) {
     if (npair <= 0 || ntiles <= 0) return 0;
+    // experiment knob (tools/coresident_check.py): shared-memory carve-out the kernel asks for, in per cent.  An SM holds
+    // one carve-out at a time, so a CTA of this kernel can only sit beside a k_oz_gemm CTA (198 KB of shared memory) when
+    // both ask for the large one.
+    const char* carve_env = getenv("B200_PAIR_CARVEOUT");
+    const int carve = carve_env ? atoi(carve_env) : -1;
     prof_begin(PROF_BUILD_A, s);
+    // B200_PAIR_RESIDENT = CTAs per SM of the resident form (0 / unset: one CTA per tile)
+    const char* res_env = getenv("B200_PAIR_RESIDENT");
+    const int res = res_env ? atoi(res_env) : 0;
+    static int n_sm = 0;
+    if (res > 0 && n_sm == 0) {
+        int dev = 0;
+        B200_CUDA(cudaGetDevice(&dev));
+        B200_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+    }
+    const int res_grid = res > 0 ? (ntiles < res * n_sm ? ntiles : res * n_sm) : 0;
 #define B200_PAIR(PP)                                                                                                \
-    k_pair_blocks<PP><<<(unsigned)ntiles, 256, 0, s>>>(gx, gy, gimg, descs, tile_prefix, npair, tables, lut, nimg, ngrid, \
-                                                       dscale, nc, flat_penalty, pool)
+    if (carve >= 0) {                                                                                                \
+        B200_CUDA(cudaFuncSetAttribute(k_pair_blocks<PP>, cudaFuncAttributePreferredSharedMemoryCarveout, carve));   \
+        B200_CUDA(cudaFuncSetAttribute(k_pair_blocks_resident<PP>, cudaFuncAttributePreferredSharedMemoryCarveout,   \
+                                       carve));                                                                      \
+    }                                                                                                                \
+    if (res_grid > 0)                                                                                                \
+        k_pair_blocks_resident<PP><<<(unsigned)res_grid, 128, 0, s>>>(gx, gy, gimg, descs, tile_prefix, npair, ntiles, \
+                                                                     tables, lut, nimg, ngrid, dscale, nc,           \
+                                                                     flat_penalty, pool);                            \
+    else                                                                                                             \
+        k_pair_blocks<PP><<<(unsigned)ntiles, 256, 0, s>>>(gx, gy, gimg, descs, tile_prefix, npair, tables, lut, nimg, \
+                                                           ngrid, dscale, nc, flat_penalty, pool)
     switch (poly) {
         case 0: B200_PAIR(0); break;
         case 2: B200_PAIR(2); break;

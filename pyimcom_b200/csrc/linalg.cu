@@ -490,8 +490,15 @@ __global__ void __launch_bounds__(T64 ? GT2 : GT, T64 ? CTAS2 : 1) k_back_update
 // those of the Z rows that are non-zero there (rows <= j0+7); then all threads apply the rank-8 update to
 // the trailing A block (lower triangle) and to the trailing columns of those Z rows in 4x4 micro-tiles.
 // Two barriers per panel.
+//
+// Shared-memory layout: row r starts at r * 129 + r / 4 doubles.  The trailing update works on 4 x 4 micro-tiles and the
+// lanes of a warp take micro-tiles that are 4 ROWS apart (column-major enumeration), so the lane-dependent part of
+// every address is a multiple of 4 rows = 517 doubles: odd, i.e. the 16 lanes of a 64-bit wavefront fall into 16
+// different bank pairs.  (With a plain stride of 129 and lanes 4 columns or 4 rows apart, ncu counted 340 k bank
+// conflicts in 601 k shared wavefronts per launch: profiles/ncu_r02_k_potrf_diag.txt.)
 constexpr int PD = NB + 1;
-constexpr size_t POTRF_SMEM = (size_t)NB * PD * sizeof(double);
+__device__ __forceinline__ int prow(int r) { return r * PD + (r >> 2); }
+constexpr size_t POTRF_SMEM = ((size_t)NB * PD + NB / 4) * sizeof(double);
 
 __global__ void __launch_bounds__(256, 1) k_potrf_diag(SolveBatch bt, int k) {
     extern __shared__ __align__(16) double S[];  // [128][129]
@@ -502,8 +509,8 @@ __global__ void __launch_bounds__(256, 1) k_potrf_diag(SolveBatch bt, int k) {
     double* Wkk = s.W + (size_t)k * NB * s.ldw + (size_t)k * NB;
     for (int e = tid; e < NB * NB; e += 256) {
         const int r = e >> 7, c = e & 127;
-        if (c <= r) S[r * PD + c] = Wkk[(size_t)r * s.ldw + c];
-        if (c >= r) S[r * PD + c + 1] = (c == r) ? 1.0 : 0.0;  // Z = I
+        if (c <= r) S[prow(r) + c] = Wkk[(size_t)r * s.ldw + c];
+        if (c >= r) S[prow(r) + c + 1] = (c == r) ? 1.0 : 0.0;  // Z = I
     }
     __syncthreads();
     int bad = 0;
@@ -512,7 +519,7 @@ __global__ void __launch_bounds__(256, 1) k_potrf_diag(SolveBatch bt, int k) {
 #pragma unroll
         for (int a = 0; a < 8; a++)
 #pragma unroll
-            for (int b = 0; b <= a; b++) D[a][b] = S[(j0 + a) * PD + j0 + b];
+            for (int b = 0; b <= a; b++) D[a][b] = S[prow(j0 + a) + j0 + b];
 #pragma unroll
         for (int c = 0; c < 8; c++) {
             double d = D[c][c];
@@ -533,7 +540,7 @@ __global__ void __launch_bounds__(256, 1) k_potrf_diag(SolveBatch bt, int k) {
             // row (r of A for tid < 128, r of Z otherwise): x[c] = (x[c] - sum_{q<c} x[q] L[c][q]) / L[c][c]
             const bool isz = tid >= NB;
             const int r = isz ? tid - NB : tid;
-            double* rowp = S + r * PD + j0 + (isz ? 1 : 0);
+            double* rowp = S + prow(r) + j0 + (isz ? 1 : 0);
             if (isz ? (r < j0 + 8) : (r >= j0 + 8)) {
                 double row[8];
 #pragma unroll
@@ -564,7 +571,7 @@ __global__ void __launch_bounds__(256, 1) k_potrf_diag(SolveBatch bt, int k) {
 #pragma unroll
             for (int a = 0; a < 8; a++)
 #pragma unroll
-                for (int b = 0; b <= a; b++) S[(j0 + a) * PD + j0 + b] = D[a][b];
+                for (int b = 0; b <= a; b++) S[prow(j0 + a) + j0 + b] = D[a][b];
         }
         const int T0 = j0 + 8;
         const int nt4 = (NB - T0) >> 2;
@@ -576,21 +583,26 @@ __global__ void __launch_bounds__(256, 1) k_potrf_diag(SolveBatch bt, int k) {
             int zrow = -1;  // first Z row of the tile (entries left of Z's diagonal are storage of A/L: read as 0)
             bool diag = false;  // diagonal A tile: only its lower triangle is A's storage (the rest belongs to Z)
             if (t < cntA) {
-                int bi = (int)((sqrtf(8.0f * (float)t + 1.0f) - 1.0f) * 0.5f);
-                while (bi * (bi + 1) / 2 > t) bi--;
-                while ((bi + 1) * (bi + 2) / 2 <= t) bi++;
-                const int bj = t - bi * (bi + 1) / 2;
+                // column-major walk of the lower triangle of micro-tiles (consecutive threads: consecutive tile ROWS of
+                // one tile column), written as the row-major walk of the mirrored triangle from the end
+                const int tr = cntA - 1 - t;
+                int mi = (int)((sqrtf(8.0f * (float)tr + 1.0f) - 1.0f) * 0.5f);
+                while (mi * (mi + 1) / 2 > tr) mi--;
+                while ((mi + 1) * (mi + 2) / 2 <= tr) mi++;
+                const int mj = tr - mi * (mi + 1) / 2;
+                const int bj = nt4 - 1 - mi, bi = nt4 - 1 - mj;
                 diag = bi == bj;
-                pa = S + (T0 + 4 * bi) * PD + j0;
-                pb = S + (T0 + 4 * bj) * PD + j0;
-                pc = S + (T0 + 4 * bi) * PD + T0 + 4 * bj;
+                pa = S + prow(T0 + 4 * bi) + j0;
+                pb = S + prow(T0 + 4 * bj) + j0;
+                pc = S + prow(T0 + 4 * bi) + T0 + 4 * bj;
             } else {
                 const int u = t - cntA;
-                const int zi = u / nt4, bj = u - zi * nt4;
+                const int nz4 = T0 >> 2;
+                const int bj = u / nz4, zi = u - bj * nz4;  // consecutive threads: consecutive Z row groups
                 zrow = 4 * zi;
-                pa = S + (4 * zi) * PD + j0 + 1;  // Z rows 4 zi .. 4 zi + 3, panel columns
-                pb = S + (T0 + 4 * bj) * PD + j0;
-                pc = S + (4 * zi) * PD + T0 + 4 * bj + 1;
+                pa = S + prow(4 * zi) + j0 + 1;  // Z rows 4 zi .. 4 zi + 3, panel columns
+                pb = S + prow(T0 + 4 * bj) + j0;
+                pc = S + prow(4 * zi) + T0 + 4 * bj + 1;
             }
             double c4[4][4];
 #pragma unroll
@@ -623,9 +635,9 @@ __global__ void __launch_bounds__(256, 1) k_potrf_diag(SolveBatch bt, int k) {
     double* Dt = s.Dinv + (size_t)(nb + k) * NB * NB;
     for (int e = tid; e < NB * NB; e += 256) {
         const int r = e >> 7, c = e & 127;
-        if (c <= r) Wkk[(size_t)r * s.ldw + c] = S[r * PD + c];  // L, lower triangle of the diagonal block
-        Dt[e] = (r <= c) ? S[r * PD + c + 1] : 0.0;              // inv(L)^T[r][c] = Z[r][c]
-        Di[e] = (c <= r) ? S[c * PD + r + 1] : 0.0;              // inv(L)[r][c] = Z[c][r]
+        if (c <= r) Wkk[(size_t)r * s.ldw + c] = S[prow(r) + c];  // L, lower triangle of the diagonal block
+        Dt[e] = (r <= c) ? S[prow(r) + c + 1] : 0.0;              // inv(L)^T[r][c] = Z[r][c]
+        Di[e] = (c <= r) ? S[prow(c) + r + 1] : 0.0;              // inv(L)[r][c] = Z[c][r]
     }
 }
 

@@ -111,7 +111,12 @@ static_assert(OZ_NS * OZ_BN <= OZ_TMEM_COLS, "the accumulators of all significan
 constexpr int OZ_EPI_LD = OZ_BN + 1;  // row stride (doubles) of the epilogue's staging tile
 constexpr size_t OZ_SMEM = 1024 + (size_t)OZ_STAGES * OZ_STAGE + 1024;
 
-__global__ void __launch_bounds__(OZ_THREADS, 1) k_oz_gemm(const __grid_constant__ OzBatch p) {
+// (B200_OZ_LB = 512 caps the kernel at 128 registers so that a small CTA of another stream can sit beside it: experiment
+// knob, tools/coresident_check.py)
+#ifndef B200_OZ_LB
+#define B200_OZ_LB OZ_THREADS
+#endif
+__global__ void __launch_bounds__(B200_OZ_LB, 1) k_oz_gemm(const __grid_constant__ OzBatch p) {
     const OzSys& s = p.s[blockIdx.z];
     const int tn = blockIdx.x, tm = blockIdx.y;
     if (tm >= s.m_tiles || tn >= s.n_tiles || s.kb1 <= s.kb0) return;
