@@ -828,11 +828,15 @@ class GpuBlock:
         nv = max(1, len(np.atleast_1d(cfg.kappaC_arr)))
         nmax = max(p.n for p in self.plans.values())  # of the stamps planned so far (at least the first chunk)
         npad, mpad = rup(nmax), rup(cfg.n2f**2)
-        per = 8.0 * ((1 + nv) * npad * npad + (cfg.n_out + nv) * mpad * npad)
+        # (A, W and the digit planes of L per node: (1 + 2 nv) npad^2; -B/2, X and the digit planes of Z per node)
+        per = 8.0 * ((1 + 2 * nv) * npad * npad + (cfg.n_out + 2 * nv) * mpad * npad)
         free = hbm_free_estimate()
         return int(max(1, min(0.5 * free // per, self.max_batch)))
 
-    max_batch = int(os.environ.get("B200_MAX_BATCH", "16"))
+    # 32 OutStamps per batch = two groups of 16 systems on the two solve streams: every serial k_potrf_diag launch and
+    # every partial last wave then serves 16 systems instead of 8 (64-stamp block 281.8 -> 276.1 ms, 256 stamps
+    # 1100.9 -> 1075.7 ms; 48 stamps on 3 streams 1070.0, 64 on 2 / 4 streams 1092.7 / 1077.6)
+    max_batch = int(os.environ.get("B200_MAX_BATCH", "32"))
 
     def run(self, batch: int | None = None):
         """coadd_output_stamps(sim_mode=False) (coadd.py:2056-2069): every planned stamp, in batches of

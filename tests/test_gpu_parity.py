@@ -666,6 +666,41 @@ def test_pair_block_cache_is_bit_identical(name):
         assert cached.pair_points < tot
 
 
+@pytest.mark.parametrize("name", ["pad4", "nout2split"])
+def test_pair_blocks_resident_grid_is_bit_identical(name, monkeypatch):
+    """The experiment form of the pair-block kernel (B200_PAIR_RESIDENT: a few resident CTAs per SM walking the tile
+    list, csrc/interp.cu) writes the same pool, bit for bit, as one CTA per tile -- self blocks with their mirrored
+    lower tiles included."""
+    spec = cases.BLOCK_CASES[name]
+    blk = cases.make_block(spec)
+    tab = PSFTables(blk, G.iD5512C, G.gridD5512C)
+    stamps = list(blk.stamp_order())
+    gb = GpuBlock(blk, tab, a_cache=True).prepare(stamps=stamps)
+    plans = [gb.plans[s] for s in stamps if gb.plans[s].n > 0]
+    monkeypatch.delenv("B200_PAIR_RESIDENT", raising=False)
+    gb.reset_cache()
+    gb.ensure_pairs(plans)  # (allocates the pool)
+    used = gb._pool_used
+    assert used > 0
+    gb._pool[:used].fill_(float("nan"))
+    gb.reset_cache()
+    gb.ensure_pairs(plans)
+    torch.cuda.synchronize()
+    assert gb._pool_used == used
+    ref = gb._pool[:used].clone()
+    assert not bool(torch.isnan(ref).all())
+    for per_sm in ("1", "3"):
+        monkeypatch.setenv("B200_PAIR_RESIDENT", per_sm)
+        gb._pool[:used].fill_(float("nan"))
+        gb.reset_cache()
+        gb.ensure_pairs(plans)
+        torch.cuda.synchronize()
+        assert gb._pool_used == used
+        # (padding columns of a block row are never written by either form: compare where the reference form wrote)
+        got = gb._pool[:used]
+        assert torch.equal(torch.nan_to_num(got, nan=0.0), torch.nan_to_num(ref, nan=0.0))
+
+
 @pytest.mark.parametrize("name", ["chol1", "pad4", "nout2split", "amp", "oversamp7", "oversamp5_3img", "one_image"])
 def test_device_tables(name):
     """PSF-overlap tables built on the device (device iD5512C sampling + partial DFTs as DMMA
