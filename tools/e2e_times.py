@@ -15,9 +15,9 @@ from pyimcom_b200.psfovl_host import PSFTables  # noqa: E402
 
 
 def main():
-    blk = bench.make_block(0, n1=2)
+    blk = bench.make_block(0, n1=int(sys.argv[1]) if len(sys.argv) > 1 else 2)
     tab = PSFTables(blk, G.iD5512C, G.gridD5512C, dedup=True)
-    for rep in range(8):
+    for rep in range(6):
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         gb = GpuBlock(blk, tab)
