@@ -206,7 +206,10 @@ def _padded_system(ds: DeviceSystem, incs):
 OZAKI = os.environ.get("B200_OZAKI", "1") != "0"  # long-K panel updates on the INT8 tcgen05 tensor cores (csrc/ozaki.cu)
 OZAKI_MIN_N = 512  # (the library itself only switches over when there is more than one super-panel)
 SOLVE_STREAMS = int(os.environ.get("B200_SOLVE_STREAMS", "2"))  # concurrent groups of systems in the batched factorisation (1 = everything on the caller's stream)
-STREAM_PRIORITIES = os.environ.get("B200_STREAM_PRIORITIES", "1") != "0"
+# Equal priorities: the groups' kernels interleave CTA by CTA.  (1: staggered priorities, the first group running as if
+# alone and the others filling what it leaves -- better with the all-DMMA kernels of round 1, worse now: 64-stamp block
+# 275.3 vs 266.4 ms, 256 stamps 1076.6 vs 1056.5 ms)
+STREAM_PRIORITIES = os.environ.get("B200_STREAM_PRIORITIES", "0") != "0"
 _SIDE = {}
 
 
@@ -214,8 +217,7 @@ def _side_streams(n):
     dev = torch.cuda.current_device()
     have = _SIDE.setdefault(dev, [])
     while len(have) < n:
-        # staggered priorities (lower number = higher priority): the first group runs as if alone, the others fill
-        # the SMs it leaves idle, instead of all groups contending for every freed SM
+        # (B200_STREAM_PRIORITIES=1: staggered priorities, lower number = higher priority)
         prio = -len(have) if STREAM_PRIORITIES else 0
         have.append(torch.cuda.Stream(priority=prio))
     return have[:n]
