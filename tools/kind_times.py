@@ -1,3 +1,6 @@
+#!/usr/bin/env python
+"""Per-kind device times of one 16-stamp paper-4-shaped block on one solve stream (the library's per-launch events),
+plus a hash of the block's output map: the quick A/B check of a kernel change (B200_LIB selects the other build)."""
 import os, sys, torch
 ROOT = os.getcwd()
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
