@@ -8,8 +8,9 @@ Workload (BASELINE.json configs[3], the configuration the metric is quoted on): 
 block -- n2 = 32, FADE = 3 (m = 1444 output px per stamp incl. fade), dtheta = 0.0390625", NPIXPSF = 48,
 oversamp = 8 (395^2-entry padded PSF-overlap tables), INPAD = 1.24", KAPPAC = [6e-4], 6 input images,
 n_inframe = 6 layers, CholKernel; n ~ 6.3 k selected input pixels per stamp -- reduced to n1P x n1P = 8 x 8
-output stamps per block so that a step takes about half a second.  One STEP = one block (64 OutStamps, two pipelined
-batches of 32): gather -> A / mBhalf assembly -> batched FP64 Cholesky + triangular solves -> T apply -> overlap-add.
+output stamps per block so that a step takes about a quarter of a second.  One STEP = one block (64 OutStamps, two pipelined
+batches of 32): gather -> A / mBhalf assembly -> batched FP64 Cholesky + triangular solves (long-K panel updates as
+error-free sliced INT8 products on tcgen05, the rest on the FP64 DMMA pipe) -> T apply -> overlap-add.
 Every rank owns its own block (weak scaling, seed = 1000 + rank); the only collective is the final gather of
 the output cube to rank 0 (NCCL).
 
