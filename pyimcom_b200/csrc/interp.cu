@@ -402,8 +402,12 @@ __device__ __forceinline__ bool pair_tile(int tile_idx, double (*tile)[33], cons
     return true;
 }
 
+// (B200_PAIR_MINB: resident CTAs per SM the register allocation aims at; 3 = 80 registers, 4 = 64 with ~150 B of spills)
+#ifndef B200_PAIR_MINB
+#define B200_PAIR_MINB 3
+#endif
 template <int P>
-__global__ void __launch_bounds__(256, 3) k_pair_blocks(const double* __restrict__ gx, const double* __restrict__ gy,
+__global__ void __launch_bounds__(256, B200_PAIR_MINB) k_pair_blocks(const double* __restrict__ gx, const double* __restrict__ gy,
                                                      const int* __restrict__ gimg, const PairDesc* __restrict__ descs,
                                                      const int* __restrict__ tile_prefix, int npair,
                                                      const double* __restrict__ tables,
