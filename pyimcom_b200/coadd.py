@@ -828,8 +828,10 @@ class GpuBlock:
         nv = max(1, len(np.atleast_1d(cfg.kappaC_arr)))
         nmax = max(p.n for p in self.plans.values())  # of the stamps planned so far (at least the first chunk)
         npad, mpad = rup(nmax), rup(cfg.n2f**2)
-        # (A, W and the digit planes of L per node: (1 + 2 nv) npad^2; -B/2, X and the digit planes of Z per node)
-        per = 8.0 * ((1 + 2 * nv) * npad * npad + (cfg.n_out + 2 * nv) * mpad * npad)
+        # A once; W and the digit planes of L per system; -B/2 per output PSF; X and the digit planes of Z per system
+        # (systems per stamp: kappa nodes x output PSFs -- every output PSF's factorisations are enqueued together)
+        nsys = nv * cfg.n_out
+        per = 8.0 * ((1 + 2 * nsys) * npad * npad + (cfg.n_out + 2 * nsys) * mpad * npad)
         free = hbm_free_estimate()
         return int(max(1, min(0.5 * free // per, self.max_batch)))
 
